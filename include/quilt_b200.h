@@ -1,0 +1,197 @@
+/*
+ * quilt_b200.h — C ABI of the B200-native QUILT2 per-sample imputation hot path.
+ *
+ * Drop-in boundary: everything here is plain C (pointers + sizes, no R / Rcpp /
+ * torch types).  A thin Rcpp translation unit (shim/quilt_gpu_shim.cpp, built
+ * only where R exists) keeps the reference's 63-SEXP entry point and forwards
+ * to these functions; INTEGRATION.md shows the binding.
+ *
+ * Reference interfaces replaced (paths relative to the QUILT repository):
+ *   quilt_gpu_gibbs / _batch      <- rcpp_forwardBackwardGibbsNIPT
+ *                                    QUILT/src/gibbs-nipt.cpp:2395-3307,
+ *                                    .Call glue QUILT/src/RcppExports.cpp:966-1038,
+ *                                    R wrapper QUILT/R/RcppExports.R:215-217,
+ *                                    production caller QUILT/R/functions.R:2614-2678
+ *   quilt_gpu_make_eMatRead_t     <- Rcpp_make_eMatRead_t_for_gibbs_using_objects
+ *                                    QUILT/src/gibbs-small.cpp:116-265 and the
+ *                                    rare/common sibling :275-465
+ *   quilt_gpu_unpack_panel        <- rcpp_int_expand / inflate_fhb /
+ *                                    rcpp_simple_binary_matrix_search
+ *                                    QUILT/src/copied-from-stitch.cpp:50-108,
+ *                                    QUILT/src/gibbs-small.cpp:69-105
+ *   quilt_gpu_forward_backward    <- Rcpp_run_forward_haploid / Rcpp_run_backward_haploid
+ *                                    QUILT/src/copied-from-stitch.cpp:340-409
+ *
+ * All real arrays are fp64, column-major (R / Armadillo), K is the fastest
+ * dimension.  Integer arrays are int32 unless stated.  Indices are 0-based
+ * unless the field name says otherwise (the reference mixes both; the names
+ * below keep the reference's convention so the shim is a flat copy).
+ *
+ * The functions never generate randomness: every uniform the reference draws
+ * from R's RNG inside the .Call is an input ("RNG").
+ */
+#ifndef QUILT_B200_H
+#define QUILT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- flags (QuiltGibbsArgs.flags); names follow param_list, functions.R:2566-2599 */
+#define QUILT_F_SAMPLE_IS_DIPLOID            (1u << 0)
+#define QUILT_F_GIBBS_INITIALIZE_ITERATIVELY (1u << 1)
+#define QUILT_F_PERFORM_BLOCK_GIBBS          (1u << 2)
+#define QUILT_F_DO_SHARD_BLOCK_GIBBS         (1u << 3)
+#define QUILT_F_SHARD_CHECK_EVERY_PAIR       (1u << 4)
+#define QUILT_F_DISABLE_READ_CATEGORY_USAGE  (1u << 5)
+#define QUILT_F_FORCE_RESET_READ_CATEGORY_0  (1u << 6)
+#define QUILT_F_MAKE_EMATREAD_RARE_COMMON    (1u << 7)
+#define QUILT_F_RESCALE_EMATREAD             (1u << 8)
+#define QUILT_F_RECORD_READ_SET              (1u << 9)
+#define QUILT_F_USE_SMOOTH_CM_IN_BLOCK_GIBBS (1u << 10)
+#define QUILT_F_RETURN_ALPHA                 (1u << 11)  /* debug: copy alpha/beta/c/eMatGrid out */
+#define QUILT_F_RETURN_EXTRA                 (1u << 12)  /* debug: copy eMatRead_t out            */
+
+/* production flag word for QUILT2 diploid common-SNP calls (functions.R:620-706) */
+#define QUILT_FLAGS_QUILT2_DIPLOID \
+    (QUILT_F_SAMPLE_IS_DIPLOID | QUILT_F_PERFORM_BLOCK_GIBBS | QUILT_F_DO_SHARD_BLOCK_GIBBS | \
+     QUILT_F_SHARD_CHECK_EVERY_PAIR | QUILT_F_RESCALE_EMATREAD | QUILT_F_RECORD_READ_SET |     \
+     QUILT_F_USE_SMOOTH_CM_IN_BLOCK_GIBBS)
+
+/* status codes */
+#define QUILT_OK                0
+#define QUILT_ERR_CUDA          1
+#define QUILT_ERR_BAD_ARG       2
+#define QUILT_ERR_UNSUPPORTED   3
+#define QUILT_ERR_NO_DEVICE     4
+
+/*
+ * Prepared reference panel in the compressed form QUILT2 keeps after
+ * QUILT_prepare_reference (format pinned by
+ * QUILT/tests/testthat/test-unit-reference-single.R:210-309).
+ */
+typedef struct QuiltPanel {
+    int32_t K_full;          /* haplotypes in the panel                               */
+    int32_t nGrids;          /* T over the panel's (common) SNPs = ceil(nSNPs/32)     */
+    int32_t nSNPs;           /* (common) SNPs                                          */
+    int32_t nMaxDH;          /* rows of distinctHapsB / distinctHapsIE (<= 255)        */
+    const uint8_t* hapMatcherR;      /* [K_full x nGrids] 1-based row of distinctHapsB, 0 = special */
+    const int32_t* distinctHapsB;    /* [nMaxDH x nGrids] packed 32-SNP words, LSB = first SNP      */
+    const double*  distinctHapsIE;   /* [nMaxDH x nSNPs]  (1-eps) if bit set else eps                */
+    const int32_t* eMatDH_special_matrix;        /* [n_special x 2] col 0 = 0-based hap, col 1 = word */
+    int32_t        n_special;
+    const int32_t* eMatDH_special_matrix_helper; /* [nGrids x 2] 1-based first / last row per grid    */
+    double  ref_error;
+    /* rare/common extras for the all-SNP stage (nSNPs_all == 0 when absent), rare_common.R:202-322 */
+    int32_t nSNPs_all;
+    const uint8_t* snp_is_common;      /* [nSNPs_all]                                      */
+    const int32_t* common_snp_index;   /* [nSNPs_all] 1-based index among common SNPs      */
+    const int64_t* rare_hap_offsets;   /* [K_full + 1] CSR over rare_per_hap_info          */
+    const int32_t* rare_hap_snps;      /* 1-based all-SNP indices where the hap carries alt */
+} QuiltPanel;
+
+/* sampleReads flattened to CSR (reference: R list of list(J, wif, bq, u), test-drivers.R:222-227) */
+typedef struct QuiltReads {
+    int32_t nReads;
+    const int32_t* offsets;  /* [nReads + 1]; read r owns u/bq[offsets[r] .. offsets[r+1]) ; J_r = count - 1 */
+    const int32_t* u;        /* 0-based SNP index                                        */
+    const int32_t* bq;       /* signed phred: <0 ref allele seen, >0 alt allele seen     */
+    const int32_t* wif0;     /* [nReads] 0-based grid of the read's central SNP, non-decreasing */
+} QuiltReads;
+
+/* one call of rcpp_forwardBackwardGibbsNIPT (one sample, one Gibbs start, S = 1) */
+typedef struct QuiltGibbsArgs {
+    const QuiltPanel* panel;
+    QuiltReads reads;
+    int32_t K;                          /* Ksubset                                           */
+    const int32_t* which_haps_to_use;   /* [K] 1-based, order defines the k axis             */
+    int32_t nGrids;                     /* T of THIS call (common-SNP or all-SNP grids)      */
+    int32_t nSNPs;                      /* SNPs of THIS call (= length(grid))                */
+    const double*  transMatRate_tc_H;   /* [2 x (nGrids-1)] row 0 = sigma (stay), row 1 = 1-sigma */
+    const int32_t* L_grid;              /* [nGrids] physical position per grid               */
+    const double*  smooth_cm;           /* [nGrids-1] (unused by results, kept for parity)   */
+    double  ff;                         /* fetal fraction; 0 for diploid                     */
+    int32_t n_gibbs_burn_in_its;
+    int32_t n_gibbs_sample_its;
+    const int32_t* block_gibbs_iterations; /* 0-based sweep indices, e.g. {3,6,9}            */
+    int32_t n_block_gibbs_iterations;
+    const int32_t* H0;                  /* [nReads] starting labels, 1-based                 */
+    int32_t first_read_for_gibbs_initialization; /* 0-based (gibbs-nipt.cpp:2848)            */
+    const double* runif_reads;          /* [nReads * n_full_its]      (gibbs-nipt.cpp:2845)  */
+    const double* runif_block;          /* [n_block_its x nReads]     (gibbs-nipt.cpp:3017)  */
+    const double* runif_shard;          /* [n_block_its x (nGrids-1)] (gibbs-nipt-block.cpp:2054) */
+    const double* runif_H_class;        /* NIPT only: [n_block_its x nReads] unif_rand per Rcpp::sample (block.cpp:226-243) */
+    double  maxDifferenceBetweenReads;
+    int32_t Jmax;
+    double  class_sum_cutoff;
+    int32_t shuffle_bin_radius;
+    double  block_gibbs_quantile_prob;
+    uint32_t flags;
+} QuiltGibbsArgs;
+
+typedef struct QuiltGibbsOut {
+    int32_t underflow_problem;   /* reference: list(underflow_problem=TRUE) early return     */
+    double* hapProbs_t;          /* [3 x nSNPs]                                              */
+    double* genProbsM_t;         /* [3 x nSNPs]                                              */
+    double* genProbsF_t;         /* [3 x nSNPs]                                              */
+    int32_t* H;                  /* [nReads] final labels                                    */
+    int32_t* H_class;            /* [nReads]                                                 */
+    double* per_it_likelihoods;  /* [n_full_its x 13] column-major                           */
+    /* optional (may be NULL); filled when QUILT_F_RETURN_ALPHA / _EXTRA are set */
+    double* alphaHat_t[3];       /* each [K x nGrids]                                        */
+    double* betaHat_t[3];
+    double* eMatGrid_t[3];
+    double* c[3];                /* each [nGrids]                                            */
+    double* eMatRead_t;          /* [K x nReads]                                             */
+    int32_t* read_category;      /* [nReads]                                                 */
+} QuiltGibbsOut;
+
+/* ------------------------------------------------------------------ GPU library (libquiltgpu.so) */
+
+/* drop-in granularity: one sample, one call; host pointers in, host pointers out */
+int quilt_gpu_gibbs(const QuiltGibbsArgs* args, QuiltGibbsOut* out);
+/* benchmark / production granularity: n independent samples, one launch sequence */
+int quilt_gpu_gibbs_batch(int32_t n, const QuiltGibbsArgs* args, QuiltGibbsOut* out);
+
+/* staged form of the same call, so inputs can be resident in HBM before a timed region */
+typedef struct QuiltGpuBatch QuiltGpuBatch;
+int quilt_gpu_batch_stage(int32_t n, const QuiltGibbsArgs* args, QuiltGpuBatch** batch); /* H2D   */
+int quilt_gpu_batch_run(QuiltGpuBatch* batch);                                           /* kernels, async on the library stream */
+int quilt_gpu_batch_sync(QuiltGpuBatch* batch);
+int quilt_gpu_batch_fetch(QuiltGpuBatch* batch, QuiltGibbsOut* out);                     /* D2H   */
+int quilt_gpu_batch_free(QuiltGpuBatch* batch);
+/* device time of the last quilt_gpu_batch_run in ms, measured with CUDA events on the library stream;
+ * sweep_ms = time inside the dominant (sweep) kernel launches, n_sweep_launches their count */
+int quilt_gpu_batch_timing(QuiltGpuBatch* batch, double* total_ms, double* sweep_ms, int32_t* n_sweep_launches);
+
+/* component entry points (parity tests of the individual reference functions) */
+int quilt_gpu_make_eMatRead_t(const QuiltGibbsArgs* args, double* eMatRead_t /*[K x nReads]*/,
+                              int32_t* read_category /*[nReads] or NULL*/);
+int quilt_gpu_unpack_panel(const QuiltPanel* panel, int32_t K, const int32_t* which_haps_to_use,
+                           int32_t all_snps /*0: common grids, 1: all-SNP grids*/,
+                           uint32_t* words /*[K x nGrids(_all)]*/);
+int quilt_gpu_forward_backward(int32_t K, int32_t nGrids, const double* eMatGrid_t, const double* transMatRate_tc_H,
+                               double* alphaHat_t, double* betaHat_t, double* c);
+
+/* housekeeping */
+int         quilt_gpu_device_count(void);
+int         quilt_gpu_set_device(int32_t device);
+const char* quilt_gpu_last_error(void);
+int64_t     quilt_gpu_kernel_launches(void);   /* cumulative count of this library's kernel launches */
+void        quilt_gpu_release_panel_cache(void);
+
+/* ------------------------------------------------------------------ CPU oracle (oracle/libquiltoracle.so)
+ * Test infrastructure only: a statement-order restatement of the reference C++.  Same structs. */
+int quilt_oracle_gibbs(const QuiltGibbsArgs* args, QuiltGibbsOut* out);
+int quilt_oracle_make_eMatRead_t(const QuiltGibbsArgs* args, double* eMatRead_t, int32_t* read_category);
+int quilt_oracle_unpack_panel(const QuiltPanel* panel, int32_t K, const int32_t* which_haps_to_use,
+                              int32_t all_snps, uint32_t* words);
+int quilt_oracle_forward_backward(int32_t K, int32_t nGrids, const double* eMatGrid_t, const double* transMatRate_tc_H,
+                                  double* alphaHat_t, double* betaHat_t, double* c);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QUILT_B200_H */
