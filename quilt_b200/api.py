@@ -1,0 +1,223 @@
+"""Host-side mirror of the reference's interface for the Gibbs hot path, over the C ABI of libquiltgpu.so.
+
+`rcpp_forwardBackwardGibbsNIPT(...)` keeps the reference's argument names and meaning
+(QUILT/R/RcppExports.R:215-217, production call site QUILT/R/functions.R:2614-2678) for the arguments
+that influence results on this path, and returns an object whose fields are named like the reference's
+return list (QUILT/src/gibbs-nipt.cpp:3217-3306).  The random numbers the reference draws from R's RNG
+inside the .Call are inputs here — the library never generates randomness.
+
+There is no CPU fallback: if libquiltgpu.so is missing or no B200 is visible the calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import cabi
+from .cabi import GibbsCall, GibbsResult, Panel, Reads
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(_HERE, "libquiltgpu.so")
+
+
+class QuiltGpuError(RuntimeError):
+    pass
+
+
+class GpuLib(cabi._LibAPI):
+    """ctypes binding of libquiltgpu.so (include/quilt_b200.h)."""
+
+    prefix = "quilt_gpu"
+
+    def __init__(self, path: str = SO_PATH):
+        if not os.path.exists(path):
+            raise QuiltGpuError(
+                f"{path} is missing: build it with `python -m quilt_b200.build` (nvcc, sm_100a). There is no CPU fallback."
+            )
+        self.lib = C.CDLL(path)
+        cabi.declare(self.lib, self.prefix)
+        L = self.lib
+        pa, po = C.POINTER(cabi.QuiltGibbsArgs), C.POINTER(cabi.QuiltGibbsOut)
+        L.quilt_gpu_gibbs_batch.argtypes = [C.c_int32, pa, po]
+        L.quilt_gpu_gibbs_batch.restype = C.c_int
+        L.quilt_gpu_batch_stage.argtypes = [C.c_int32, pa, C.POINTER(C.c_void_p)]
+        L.quilt_gpu_batch_stage.restype = C.c_int
+        for f in ("run", "sync", "free"):
+            getattr(L, f"quilt_gpu_batch_{f}").argtypes = [C.c_void_p]
+            getattr(L, f"quilt_gpu_batch_{f}").restype = C.c_int
+        L.quilt_gpu_batch_fetch.argtypes = [C.c_void_p, po]
+        L.quilt_gpu_batch_fetch.restype = C.c_int
+        L.quilt_gpu_batch_timing.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int32)]
+        L.quilt_gpu_batch_timing.restype = C.c_int
+        L.quilt_gpu_device_count.restype = C.c_int
+        L.quilt_gpu_set_device.argtypes = [C.c_int32]
+        L.quilt_gpu_set_device.restype = C.c_int
+        L.quilt_gpu_last_error.restype = C.c_char_p
+        L.quilt_gpu_kernel_launches.restype = C.c_int64
+        L.quilt_gpu_release_panel_cache.restype = None
+
+    # ---- housekeeping
+    def last_error(self) -> str:
+        return (self.lib.quilt_gpu_last_error() or b"").decode()
+
+    def device_count(self) -> int:
+        return int(self.lib.quilt_gpu_device_count())
+
+    def set_device(self, device: int):
+        self._check(self.lib.quilt_gpu_set_device(int(device)), "quilt_gpu_set_device")
+
+    def kernel_launches(self) -> int:
+        return int(self.lib.quilt_gpu_kernel_launches())
+
+    def release_panel_cache(self):
+        self.lib.quilt_gpu_release_panel_cache()
+
+    def _check(self, rc: int, what: str):
+        if rc != cabi.OK:
+            raise QuiltGpuError(f"{what} failed with status {rc}: {self.last_error()}")
+
+    # ---- batches
+    def gibbs_batch(self, calls: Sequence[GibbsCall]) -> List[GibbsResult]:
+        """n independent calls through quilt_gpu_gibbs_batch (host buffers in, host buffers out)."""
+        b = Batch(self, calls)
+        try:
+            b.run()
+            b.sync()
+            return b.fetch()
+        finally:
+            b.free()
+
+
+class Batch:
+    """Staged form: inputs resident in HBM after __init__, `run()` only launches kernels."""
+
+    def __init__(self, lib: GpuLib, calls: Sequence[GibbsCall]):
+        self.lib = lib
+        self.calls = list(calls)
+        n = len(self.calls)
+        self._args = (cabi.QuiltGibbsArgs * n)()
+        for i, c in enumerate(self.calls):
+            c.fill(self._args[i])
+        self._h = C.c_void_p()
+        lib._check(lib.lib.quilt_gpu_batch_stage(n, self._args, C.byref(self._h)), "quilt_gpu_batch_stage")
+
+    def run(self):
+        self.lib._check(self.lib.lib.quilt_gpu_batch_run(self._h), "quilt_gpu_batch_run")
+
+    def sync(self):
+        self.lib._check(self.lib.lib.quilt_gpu_batch_sync(self._h), "quilt_gpu_batch_sync")
+
+    def timing(self):
+        t, s, n = C.c_double(), C.c_double(), C.c_int32()
+        self.lib._check(self.lib.lib.quilt_gpu_batch_timing(self._h, C.byref(t), C.byref(s), C.byref(n)), "quilt_gpu_batch_timing")
+        return {"total_ms": t.value, "sweep_ms": s.value, "n_sweep_launches": n.value}
+
+    def fetch(self) -> List[GibbsResult]:
+        n = len(self.calls)
+        outs = (cabi.QuiltGibbsOut * n)()
+        res = [cabi.alloc_out(c, outs[i]) for i, c in enumerate(self.calls)]
+        self.lib._check(self.lib.lib.quilt_gpu_batch_fetch(self._h, outs), "quilt_gpu_batch_fetch")
+        for i, r in enumerate(res):
+            r.underflow_problem = bool(outs[i].underflow_problem)
+        return res
+
+    def free(self):
+        if self._h:
+            self.lib.lib.quilt_gpu_batch_free(self._h)
+            self._h = C.c_void_p()
+
+
+_LIB: Optional[GpuLib] = None
+
+
+def lib() -> GpuLib:
+    global _LIB
+    if _LIB is None:
+        _LIB = GpuLib()
+    return _LIB
+
+
+def rcpp_forwardBackwardGibbsNIPT(
+    sampleReads: Reads,
+    *,
+    panel: Panel,
+    which_haps_to_use,
+    transMatRate_tc_H,
+    H,
+    runif_reads,
+    runif_block,
+    runif_shard,
+    L_grid,
+    smooth_cm,
+    nGrids: int,
+    nSNPs: int,
+    ff: float = 0.0,
+    n_gibbs_burn_in_its: int = 20,
+    n_gibbs_sample_its: int = 1,
+    block_gibbs_iterations=(3, 6, 9),
+    first_read_for_gibbs_initialization: int = 0,
+    maxDifferenceBetweenReads: float = 1e10,
+    Jmax: int = 10000,
+    class_sum_cutoff: float = 0.06,
+    shuffle_bin_radius: int = 5000,
+    block_gibbs_quantile_prob: float = 0.95,
+    sample_is_diploid: bool = True,
+    gibbs_initialize_iteratively: bool = False,
+    perform_block_gibbs: bool = True,
+    do_shard_block_gibbs: bool = True,
+    shard_check_every_pair: bool = True,
+    disable_read_category_usage: bool = False,
+    force_reset_read_category_zero: bool = False,
+    make_eMatRead_t_rare_common: bool = False,
+    rescale_eMatRead_t: bool = True,
+    record_read_set: bool = True,
+    use_smooth_cm_in_block_gibbs: bool = True,
+    runif_H_class=None,
+) -> GibbsResult:
+    """One Gibbs call on the GPU; argument names follow the reference (functions.R:2614-2678)."""
+    flags = 0
+    for on, bit in (
+        (sample_is_diploid, cabi.F_SAMPLE_IS_DIPLOID),
+        (gibbs_initialize_iteratively, cabi.F_GIBBS_INITIALIZE_ITERATIVELY),
+        (perform_block_gibbs, cabi.F_PERFORM_BLOCK_GIBBS),
+        (do_shard_block_gibbs, cabi.F_DO_SHARD_BLOCK_GIBBS),
+        (shard_check_every_pair, cabi.F_SHARD_CHECK_EVERY_PAIR),
+        (disable_read_category_usage, cabi.F_DISABLE_READ_CATEGORY_USAGE),
+        (force_reset_read_category_zero, cabi.F_FORCE_RESET_READ_CATEGORY_0),
+        (make_eMatRead_t_rare_common, cabi.F_MAKE_EMATREAD_RARE_COMMON),
+        (rescale_eMatRead_t, cabi.F_RESCALE_EMATREAD),
+        (record_read_set, cabi.F_RECORD_READ_SET),
+        (use_smooth_cm_in_block_gibbs, cabi.F_USE_SMOOTH_CM_IN_BLOCK_GIBBS),
+    ):
+        if on:
+            flags |= bit
+    call = GibbsCall(
+        panel=panel,
+        reads=sampleReads,
+        which_haps_to_use=np.asarray(which_haps_to_use, dtype=np.int32),
+        nGrids=nGrids,
+        nSNPs=nSNPs,
+        transMatRate_tc_H=transMatRate_tc_H,
+        L_grid=L_grid,
+        smooth_cm=smooth_cm,
+        H0=np.asarray(H, dtype=np.int32),
+        runif_reads=runif_reads,
+        runif_block=runif_block,
+        runif_shard=runif_shard,
+        runif_H_class=runif_H_class,
+        ff=ff,
+        n_gibbs_burn_in_its=n_gibbs_burn_in_its,
+        n_gibbs_sample_its=n_gibbs_sample_its,
+        block_gibbs_iterations=tuple(block_gibbs_iterations),
+        first_read_for_gibbs_initialization=first_read_for_gibbs_initialization,
+        maxDifferenceBetweenReads=maxDifferenceBetweenReads,
+        Jmax=Jmax,
+        class_sum_cutoff=class_sum_cutoff,
+        shuffle_bin_radius=shuffle_bin_radius,
+        block_gibbs_quantile_prob=block_gibbs_quantile_prob,
+        flags=flags,
+    )
+    return lib().gibbs(call)

@@ -354,7 +354,7 @@ def alloc_out(call: GibbsCall, o: QuiltGibbsOut) -> GibbsResult:
         genProbsF_t=np.zeros((3, nS), order="F"),
         H=np.zeros(R, dtype=np.int32),
         H_class=np.zeros(R, dtype=np.int32),
-        per_it_likelihoods=np.zeros((max(call.n_full_its, 1), 13), order="F"),
+        per_it_likelihoods=np.zeros((1 if call.n_gibbs_sample_its == 0 else call.n_full_its, 13), order="F"),
         read_category=np.zeros(R, dtype=np.int32),
     )
     o.hapProbs_t = _ptr(res.hapProbs_t, _pd)

@@ -1,0 +1,1170 @@
+// quilt_gpu.cu — host side of libquiltgpu.so: the C ABI of include/quilt_b200.h over the sm_100a kernels.
+//
+// Work unit ("job") = one rcpp_forwardBackwardGibbsNIPT call (QUILT/src/gibbs-nipt.cpp:2395-3307).  Jobs of a
+// batch are grouped into buckets of identical shape/flags; each bucket runs in waves of at most
+// (SM count x resident CTAs per SM) jobs, one CTA per job in the sweep kernel.  The K x T state (alpha, beta,
+// eMatGrid, allele words, emission tables) belongs to a wave slot and is reused by the next wave; only the
+// small per-job inputs and outputs stay resident for the whole batch.
+//
+// There is no CPU fallback anywhere in this file: without a CUDA device every entry point returns
+// QUILT_ERR_NO_DEVICE / QUILT_ERR_CUDA.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "../../include/quilt_b200.h"
+#include "passes.cuh"
+#include "prep.cuh"
+#include "sweep.cuh"
+#include "types.h"
+
+using namespace qb;
+
+namespace {
+
+thread_local std::string g_err;
+std::atomic<long long> g_launches{0};
+std::mutex g_mu;
+cudaStream_t g_stream = nullptr;
+int g_device = -1;
+int g_sms = 0;
+
+int set_err(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+#define CK(call)                                                                                          \
+    do {                                                                                                  \
+        cudaError_t e__ = (call);                                                                         \
+        if (e__ != cudaSuccess)                                                                           \
+            return set_err(QUILT_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__) + " @" + std::to_string(__LINE__)); \
+    } while (0)
+#define LAUNCHED() (g_launches.fetch_add(1, std::memory_order_relaxed))
+
+int ensure_device() {
+    if (g_stream) return QUILT_OK;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) return set_err(QUILT_ERR_NO_DEVICE, "no CUDA device: libquiltgpu has no CPU fallback");
+    if (g_device < 0) g_device = 0;
+    CK(cudaSetDevice(g_device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, g_device));
+    if (prop.major < 10) return set_err(QUILT_ERR_NO_DEVICE, "libquiltgpu is built for sm_100a only");
+    g_sms = prop.multiProcessorCount;
+    CK(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
+    return QUILT_OK;
+}
+
+inline size_t al(size_t x) { return (x + 255) & ~(size_t)255; }
+
+struct DBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    DBuf() {}
+    DBuf(const DBuf&) = delete;
+    DBuf& operator=(const DBuf&) = delete;
+    ~DBuf() { release(); }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+    }
+    cudaError_t alloc(size_t n) {
+        release();
+        if (n == 0) n = 256;
+        cudaError_t e = cudaMalloc(&p, n);
+        if (e == cudaSuccess) bytes = n;
+        return e;
+    }
+};
+struct HBuf {  // pinned host
+    void* p = nullptr;
+    size_t bytes = 0;
+    HBuf() {}
+    HBuf(const HBuf&) = delete;
+    HBuf& operator=(const HBuf&) = delete;
+    ~HBuf() { release(); }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        bytes = 0;
+    }
+    cudaError_t alloc(size_t n) {
+        release();
+        if (n == 0) n = 256;
+        cudaError_t e = cudaMallocHost(&p, n);
+        if (e == cudaSuccess) bytes = n;
+        return e;
+    }
+};
+
+// ------------------------------------------------------------------------------------------------ panel cache
+struct PanelEntry {
+    QuiltPanel key;
+    PanelDev dev;
+    DBuf buf;
+};
+std::vector<std::unique_ptr<PanelEntry>> g_panels;
+
+bool same_panel(const QuiltPanel& a, const QuiltPanel& b) {
+    return a.K_full == b.K_full && a.nGrids == b.nGrids && a.nSNPs == b.nSNPs && a.nMaxDH == b.nMaxDH && a.hapMatcherR == b.hapMatcherR &&
+           a.distinctHapsB == b.distinctHapsB && a.distinctHapsIE == b.distinctHapsIE && a.eMatDH_special_matrix == b.eMatDH_special_matrix &&
+           a.n_special == b.n_special && a.eMatDH_special_matrix_helper == b.eMatDH_special_matrix_helper && a.ref_error == b.ref_error &&
+           a.nSNPs_all == b.nSNPs_all && a.snp_is_common == b.snp_is_common && a.common_snp_index == b.common_snp_index &&
+           a.rare_hap_offsets == b.rare_hap_offsets && a.rare_hap_snps == b.rare_hap_snps;
+}
+
+// The kernels derive a haplotype's emission at a SNP from its allele bit: (1 - eps) if set, eps otherwise.  The
+// reference reads the same two numbers from distinctHapsIE (gibbs-small.cpp:208); check that the caller's matrix
+// really is that function of distinctHapsB so the bit form is exact.
+int check_distinctHapsIE(const QuiltPanel* p) {
+    const double eps = p->ref_error, ome = 1 - p->ref_error;
+    std::vector<int> used(p->nGrids, 0);
+    for (int g = 0; g < p->nGrids; g++) {
+        const uint8_t* col = p->hapMatcherR + (size_t)g * p->K_full;
+        int m = 0;
+        for (int k = 0; k < p->K_full; k++) m = std::max<int>(m, col[k]);
+        if (m > p->nMaxDH) return set_err(QUILT_ERR_BAD_ARG, "hapMatcherR refers to a row beyond nMaxDH");
+        used[g] = m;
+    }
+    for (int s = 0; s < p->nSNPs; s++) {
+        const int g = s >> 5, b = s & 31;
+        const double* ie = p->distinctHapsIE + (size_t)s * p->nMaxDH;
+        const int32_t* wb = p->distinctHapsB + (size_t)g * p->nMaxDH;
+        for (int i = 0; i < used[g]; i++) {
+            const double want = (((uint32_t)wb[i] >> b) & 1u) ? ome : eps;
+            if (ie[i] != want) return set_err(QUILT_ERR_UNSUPPORTED, "distinctHapsIE is not (bit ? 1 - ref_error : ref_error) of distinctHapsB");
+        }
+    }
+    return QUILT_OK;
+}
+
+int get_panel(const QuiltPanel* p, PanelDev* out) {
+    for (auto& e : g_panels)
+        if (same_panel(e->key, *p)) {
+            *out = e->dev;
+            return QUILT_OK;
+        }
+    if (p->K_full <= 0 || p->nGrids <= 0 || p->nSNPs <= 0 || p->nMaxDH <= 0 || p->nMaxDH > 255 || !p->hapMatcherR || !p->distinctHapsB ||
+        !p->distinctHapsIE || !p->eMatDH_special_matrix_helper)
+        return set_err(QUILT_ERR_BAD_ARG, "bad panel");
+    if (p->nGrids != (p->nSNPs + 31) / 32) return set_err(QUILT_ERR_UNSUPPORTED, "panel grid must be 32 SNPs per grid");
+    int rc = check_distinctHapsIE(p);
+    if (rc != QUILT_OK) return rc;
+    auto e = std::make_unique<PanelEntry>();
+    e->key = *p;
+    const size_t b_hm = al((size_t)p->K_full * p->nGrids), b_db = al((size_t)p->nMaxDH * p->nGrids * 4);
+    const int nsp = std::max(p->n_special, 1);
+    const size_t b_sp = al((size_t)nsp * 2 * 4), b_he = al((size_t)p->nGrids * 2 * 4);
+    size_t b_ic = 0, b_ci = 0, b_ro = 0, b_rs = 0;
+    int64_t n_rare = 0;
+    if (p->nSNPs_all > 0) {
+        if (!p->snp_is_common || !p->common_snp_index || !p->rare_hap_offsets) return set_err(QUILT_ERR_BAD_ARG, "bad rare/common panel fields");
+        n_rare = p->rare_hap_offsets[p->K_full];
+        b_ic = al(p->nSNPs_all);
+        b_ci = al((size_t)p->nSNPs_all * 4);
+        b_ro = al((size_t)(p->K_full + 1) * 8);
+        b_rs = al((size_t)std::max<int64_t>(n_rare, 1) * 4);
+    }
+    CK(e->buf.alloc(b_hm + b_db + b_sp + b_he + b_ic + b_ci + b_ro + b_rs));
+    char* d = (char*)e->buf.p;
+    PanelDev& D = e->dev;
+    D.K_full = p->K_full;
+    D.Tc = p->nGrids;
+    D.nSNPsC = p->nSNPs;
+    D.nMaxDH = p->nMaxDH;
+    D.n_special = nsp;
+    D.nSNPs_all = p->nSNPs_all;
+    D.ref_error = p->ref_error;
+    D.hapMatcherR = (const uint8_t*)d;
+    CK(cudaMemcpy(d, p->hapMatcherR, (size_t)p->K_full * p->nGrids, cudaMemcpyHostToDevice));
+    d += b_hm;
+    D.distinctHapsB = (const int32_t*)d;
+    CK(cudaMemcpy(d, p->distinctHapsB, (size_t)p->nMaxDH * p->nGrids * 4, cudaMemcpyHostToDevice));
+    d += b_db;
+    D.special = (const int32_t*)d;
+    if (p->n_special > 0)
+        CK(cudaMemcpy(d, p->eMatDH_special_matrix, (size_t)p->n_special * 2 * 4, cudaMemcpyHostToDevice));
+    else
+        CK(cudaMemset(d, 0, b_sp));
+    d += b_sp;
+    D.helper = (const int32_t*)d;
+    CK(cudaMemcpy(d, p->eMatDH_special_matrix_helper, (size_t)p->nGrids * 2 * 4, cudaMemcpyHostToDevice));
+    d += b_he;
+    D.snp_is_common = nullptr;
+    D.common_snp_index = nullptr;
+    D.rare_off = nullptr;
+    D.rare_snps = nullptr;
+    if (p->nSNPs_all > 0) {
+        D.snp_is_common = (const uint8_t*)d;
+        CK(cudaMemcpy(d, p->snp_is_common, p->nSNPs_all, cudaMemcpyHostToDevice));
+        d += b_ic;
+        D.common_snp_index = (const int32_t*)d;
+        CK(cudaMemcpy(d, p->common_snp_index, (size_t)p->nSNPs_all * 4, cudaMemcpyHostToDevice));
+        d += b_ci;
+        D.rare_off = (const int64_t*)d;
+        CK(cudaMemcpy(d, p->rare_hap_offsets, (size_t)(p->K_full + 1) * 8, cudaMemcpyHostToDevice));
+        d += b_ro;
+        D.rare_snps = (const int32_t*)d;
+        if (n_rare > 0) CK(cudaMemcpy(d, p->rare_hap_snps, (size_t)n_rare * 4, cudaMemcpyHostToDevice));
+        d += b_rs;
+    }
+    *out = D;
+    g_panels.push_back(std::move(e));
+    return QUILT_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ geometry
+struct Geo {
+    int NT, EPT;
+};
+bool pick_geo(int K, Geo* g) {
+    if (K <= 512)
+        *g = {128, 4};
+    else if (K <= 1024)
+        *g = {256, 4};
+    else if (K <= 2048)
+        *g = {512, 4};
+    else if (K <= 4096)
+        *g = {512, 8};
+    else
+        return false;
+    return true;
+}
+
+template <typename F>
+int with_geo(const Geo& g, F&& f) {
+    if (g.NT == 128 && g.EPT == 4) return f(std::integral_constant<int, 128>(), std::integral_constant<int, 4>());
+    if (g.NT == 256 && g.EPT == 4) return f(std::integral_constant<int, 256>(), std::integral_constant<int, 4>());
+    if (g.NT == 512 && g.EPT == 4) return f(std::integral_constant<int, 512>(), std::integral_constant<int, 4>());
+    if (g.NT == 512 && g.EPT == 8) return f(std::integral_constant<int, 512>(), std::integral_constant<int, 8>());
+    return set_err(QUILT_ERR_UNSUPPORTED, "no kernel geometry");
+}
+
+// ------------------------------------------------------------------------------------------------ jobs
+struct JobLayoutIn {  // byte offsets inside the job's input region
+    size_t which, rs, roff, u, pRA, wif0, ts, dense_reads, runif_reads, runif_shard, tm, desc, H0, end;
+};
+struct JobLayoutOut {
+    size_t underflow, lik, hap, genM, genF, H, Hclass, cat, end;
+};
+
+struct HostJob {
+    QuiltGibbsArgs a;
+    int R = 0, nU = 0, n_dense = 0, n_tab = 0, n_ep = 0, n_its = 0;
+    int bucket = -1;
+    JobLayoutIn li;
+    JobLayoutOut lo;
+    size_t in_off = 0, out_off = 0;  // offsets of the job's regions in the batch arenas
+    std::vector<ReadDesc> desc;
+    std::vector<int32_t> rs, ts, dense_reads;
+    // debug copies (QUILT_F_RETURN_ALPHA / _EXTRA)
+    std::vector<double> dbg_alpha, dbg_beta, dbg_eG, dbg_c, dbg_eMatRead;
+};
+
+struct Bucket {
+    BatchParams P;
+    Geo geo;
+    std::vector<int> jobs;
+    std::vector<int> block_its;
+    int n_slots = 0;
+    int R_max = 0, n_tab_max = 0, n_dense_max = 0;
+    size_t slot_bytes = 0;
+    // slot layout
+    size_t o_alpha, o_beta, o_eG, o_c, o_W, o_Wc, o_tabs, o_dense, o_xprob, o_snp_type, o_rate, o_hapLocal;
+    DBuf slots;
+    DBuf djobs;
+    HBuf hjobs;
+    bool perform_block = false, do_shard = false, debug = false;
+};
+
+}  // namespace
+
+struct QuiltGpuBatch {
+    int n = 0;
+    std::vector<HostJob> jobs;
+    std::vector<std::unique_ptr<Bucket>> buckets;
+    PanelDev panel;
+    DBuf din, dout;
+    HBuf hin, hout;
+    size_t in_bytes = 0, out_bytes = 0;
+    bool ran = false, fetched_raw = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> sweep_events;
+    double total_ms = 0, sweep_ms = 0;
+    int n_sweep_launches = 0;
+    ~QuiltGpuBatch() {
+        if (ev0) cudaEventDestroy(ev0);
+        if (ev1) cudaEventDestroy(ev1);
+        for (auto& p : sweep_events) {
+            cudaEventDestroy(p.first);
+            cudaEventDestroy(p.second);
+        }
+    }
+};
+
+namespace {
+
+// classify every read and lay out its emission table; host-side, O(sum J)
+int prepare_job(HostJob& j) {
+    const QuiltGibbsArgs& a = j.a;
+    const int R = a.reads.nReads, T = a.nGrids;
+    j.R = R;
+    j.n_its = a.n_gibbs_burn_in_its + a.n_gibbs_sample_its;
+    if (R <= 0) return set_err(QUILT_ERR_BAD_ARG, "no reads");
+    if (!a.reads.offsets || !a.reads.u || !a.reads.bq || !a.reads.wif0 || !a.which_haps_to_use || !a.transMatRate_tc_H || !a.H0)
+        return set_err(QUILT_ERR_BAD_ARG, "null input array");
+    if (j.n_its > 0 && !a.runif_reads) return set_err(QUILT_ERR_BAD_ARG, "runif_reads missing");
+    j.nU = a.reads.offsets[R];
+    j.rs.assign(T + 1, 0);
+    int prev = 0;
+    for (int r = 0; r < R; r++) {
+        const int w = a.reads.wif0[r];
+        if (w < prev || w >= T || w < 0) return set_err(QUILT_ERR_BAD_ARG, "wif0 must be non-decreasing and inside [0, nGrids)");
+        prev = w;
+        j.rs[w + 1]++;
+    }
+    for (int g = 0; g < T; g++) j.rs[g + 1] += j.rs[g];
+    j.desc.assign(R, ReadDesc());
+    j.ts.assign(T + 1, 0);
+    j.dense_reads.clear();
+    int n_tab = 0;
+    int g_cur = 0;
+    for (int r = 0; r < R; r++) {
+        const int w = a.reads.wif0[r];
+        while (g_cur < w) j.ts[++g_cur] = n_tab;
+        ReadDesc& d = j.desc[r];
+        std::memset(&d, 0, sizeof(d));
+        const int o = a.reads.offsets[r];
+        int cnt = a.reads.offsets[r + 1] - o;
+        if (cnt <= 0) return set_err(QUILT_ERR_BAD_ARG, "read without SNPs");
+        if (cnt - 1 >= a.Jmax) cnt = a.Jmax + 1;
+        bool table = cnt <= NBMAX;
+        bool run = true;
+        for (int q = 0; q < cnt && table; q++) {
+            const int s = a.reads.u[o + q];
+            if (s < 0 || s >= a.nSNPs) return set_err(QUILT_ERR_BAD_ARG, "SNP index outside [0, nSNPs)");
+            const int wg = s >> 5;
+            if (wg < w - 1 || wg > w + 1) table = false;
+            if (q > 0 && s != a.reads.u[o + q - 1] + 1) run = false;
+        }
+        if (table) {
+            d.nb = (uint8_t)cnt;
+            d.off = (uint32_t)n_tab;
+            n_tab += 1 << cnt;
+            const int s0 = a.reads.u[o];
+            if (run) {
+                d.mode = MODE_RUN;
+                d.g0rel = (int8_t)((s0 >> 5) - w);
+                d.b0 = (uint8_t)(s0 & 31);
+            } else {
+                d.mode = MODE_GATHER;
+                for (int q = 0; q < cnt; q++) {
+                    const int s = a.reads.u[o + q];
+                    d.sel[q] = (uint8_t)((((s >> 5) - w + 1) << 5) | (s & 31));
+                }
+            }
+        } else {
+            for (int q = 0; q < cnt; q++) {
+                const int s = a.reads.u[o + q];
+                if (s < 0 || s >= a.nSNPs) return set_err(QUILT_ERR_BAD_ARG, "SNP index outside [0, nSNPs)");
+            }
+            d.mode = MODE_DENSE;
+            d.off = (uint32_t)j.dense_reads.size();
+            j.dense_reads.push_back(r);
+        }
+    }
+    while (g_cur < T) j.ts[++g_cur] = n_tab;
+    j.n_tab = n_tab;
+    j.n_dense = (int)j.dense_reads.size();
+    return QUILT_OK;
+}
+
+void layout_in(HostJob& j) {
+    const QuiltGibbsArgs& a = j.a;
+    const int R = j.R, T = a.nGrids;
+    j.n_ep = a.n_block_gibbs_iterations;
+    size_t o = 0;
+    JobLayoutIn& L = j.li;
+    L.which = o, o += al((size_t)a.K * 4);
+    L.rs = o, o += al((size_t)(T + 1) * 4);
+    L.roff = o, o += al((size_t)(R + 1) * 4);
+    L.u = o, o += al((size_t)j.nU * 4);
+    L.pRA = o, o += al((size_t)j.nU * 16);
+    L.wif0 = o, o += al((size_t)R * 4);
+    L.ts = o, o += al((size_t)(T + 1) * 4);
+    L.dense_reads = o, o += al((size_t)std::max(j.n_dense, 1) * 4);
+    L.runif_reads = o, o += al((size_t)std::max(j.n_its, 1) * R * 8);
+    L.runif_shard = o, o += al((size_t)std::max(j.n_ep, 1) * std::max(T - 1, 1) * 8);
+    L.tm = o, o += al((size_t)std::max(T - 1, 1) * 16);
+    L.desc = o, o += al((size_t)R * sizeof(ReadDesc));
+    L.H0 = o, o += al((size_t)R * 4);
+    L.end = o;
+    JobLayoutOut& O = j.lo;
+    o = 0;
+    O.underflow = o, o += 256;
+    O.lik = o, o += al((size_t)std::max(j.n_its, 1) * LIK_N * 8);
+    O.hap = o, o += al((size_t)a.nSNPs * 24);
+    O.genM = o, o += al((size_t)a.nSNPs * 24);
+    O.genF = o, o += al((size_t)a.nSNPs * 24);
+    O.H = o, o += al((size_t)R * 4);
+    O.Hclass = o, o += al((size_t)R * 4);
+    O.cat = o, o += al((size_t)R * 4);
+    O.end = o;
+}
+
+// (pR, pA) per read-SNP exactly as the reference walks them (gibbs-small.cpp:172-181): the pair is only updated
+// for bq != 0 and is carried over from the previous SNP / previous read otherwise.
+void fill_pRA(const HostJob& j, double* pRA) {
+    const QuiltGibbsArgs& a = j.a;
+    double eps, pR = 1, pA = 1;
+    for (int r = 0; r < j.R; r++) {
+        const int o = a.reads.offsets[r];
+        int cnt = a.reads.offsets[r + 1] - o;
+        const int used = std::min(cnt, a.Jmax + 1);
+        for (int q = 0; q < cnt; q++) {
+            if (q < used) {
+                const int bq = a.reads.bq[o + q];
+                if (bq < 0) {
+                    eps = std::pow(10, (double(bq) / 10));
+                    pR = 1 - eps;
+                    pA = eps / 3;
+                }
+                if (bq > 0) {
+                    eps = std::pow(10, (-double(bq) / 10));
+                    pR = eps / 3;
+                    pA = 1 - eps;
+                }
+            }
+            pRA[2 * (size_t)(o + q)] = pR;
+            pRA[2 * (size_t)(o + q) + 1] = pA;
+        }
+    }
+}
+
+void fill_in(const HostJob& j, char* base) {
+    const QuiltGibbsArgs& a = j.a;
+    const JobLayoutIn& L = j.li;
+    const int R = j.R, T = a.nGrids;
+    std::memcpy(base + L.which, a.which_haps_to_use, (size_t)a.K * 4);
+    std::memcpy(base + L.rs, j.rs.data(), (size_t)(T + 1) * 4);
+    std::memcpy(base + L.roff, a.reads.offsets, (size_t)(R + 1) * 4);
+    std::memcpy(base + L.u, a.reads.u, (size_t)j.nU * 4);
+    fill_pRA(j, reinterpret_cast<double*>(base + L.pRA));
+    std::memcpy(base + L.wif0, a.reads.wif0, (size_t)R * 4);
+    std::memcpy(base + L.ts, j.ts.data(), (size_t)(T + 1) * 4);
+    if (j.n_dense) std::memcpy(base + L.dense_reads, j.dense_reads.data(), (size_t)j.n_dense * 4);
+    if (j.n_its > 0) std::memcpy(base + L.runif_reads, a.runif_reads, (size_t)j.n_its * R * 8);
+    if (j.n_ep > 0 && T > 1 && a.runif_shard) std::memcpy(base + L.runif_shard, a.runif_shard, (size_t)j.n_ep * (T - 1) * 8);
+    if (T > 1) std::memcpy(base + L.tm, a.transMatRate_tc_H, (size_t)(T - 1) * 16);
+    std::memcpy(base + L.desc, j.desc.data(), (size_t)R * sizeof(ReadDesc));
+    std::memcpy(base + L.H0, a.H0, (size_t)R * 4);
+}
+
+typedef std::tuple<int, int, int, int, uint32_t, int, int, double, double, double, double, int, std::vector<int>> BucketKey;
+
+BucketKey bucket_key(const QuiltGibbsArgs& a) {
+    std::vector<int> bi(a.block_gibbs_iterations, a.block_gibbs_iterations + a.n_block_gibbs_iterations);
+    return BucketKey(a.K, a.nGrids, a.nSNPs, 0, a.flags, a.n_gibbs_burn_in_its, a.n_gibbs_sample_its, a.ff, a.maxDifferenceBetweenReads,
+                     a.class_sum_cutoff, 0.0, a.Jmax, bi);
+}
+
+int validate(const QuiltGibbsArgs& a) {
+    if (!a.panel) return set_err(QUILT_ERR_BAD_ARG, "panel is NULL");
+    if (a.K <= 0 || a.nGrids <= 0 || a.nSNPs <= 0) return set_err(QUILT_ERR_BAD_ARG, "bad K / nGrids / nSNPs");
+    if (a.nGrids != (a.nSNPs + 31) / 32) return set_err(QUILT_ERR_UNSUPPORTED, "grid must be 32 SNPs per grid (grid32)");
+    if (a.K > 4096) return set_err(QUILT_ERR_UNSUPPORTED, "Ksubset > 4096 not supported yet");
+    const bool diploid = (a.flags & QUILT_F_SAMPLE_IS_DIPLOID) != 0;
+    if (!diploid || a.ff != 0) return set_err(QUILT_ERR_UNSUPPORTED, "NIPT (ff > 0 / three haplotypes) not supported yet");
+    const bool rc = (a.flags & QUILT_F_MAKE_EMATREAD_RARE_COMMON) != 0;
+    if (rc) {
+        if (a.panel->nSNPs_all != a.nSNPs) return set_err(QUILT_ERR_BAD_ARG, "rare/common call: nSNPs must equal panel nSNPs_all");
+    } else {
+        if (a.panel->nSNPs != a.nSNPs) return set_err(QUILT_ERR_BAD_ARG, "common-SNP call: nSNPs must equal panel nSNPs");
+    }
+    if ((a.flags & QUILT_F_PERFORM_BLOCK_GIBBS) && a.n_block_gibbs_iterations > 0) {
+        if ((a.flags & QUILT_F_DO_SHARD_BLOCK_GIBBS) && !(a.flags & QUILT_F_SHARD_CHECK_EVERY_PAIR))
+            return set_err(QUILT_ERR_UNSUPPORTED, "shard pass without shard_check_every_pair not supported yet");
+        if ((a.flags & QUILT_F_DO_SHARD_BLOCK_GIBBS) && !a.runif_shard) return set_err(QUILT_ERR_BAD_ARG, "runif_shard missing");
+    }
+    if (a.Jmax < 0) return set_err(QUILT_ERR_BAD_ARG, "Jmax < 0");
+    for (int k = 0; k < a.K; k++)
+        if (a.which_haps_to_use[k] < 1 || a.which_haps_to_use[k] > a.panel->K_full) return set_err(QUILT_ERR_BAD_ARG, "which_haps_to_use out of range");
+    return QUILT_OK;
+}
+
+void make_params(const QuiltGibbsArgs& a, BatchParams* P) {
+    std::memset(P, 0, sizeof(*P));
+    P->K = a.K;
+    P->Kp = (a.K + 31) & ~31;
+    P->T = a.nGrids;
+    P->NH = (a.flags & QUILT_F_SAMPLE_IS_DIPLOID) ? 2 : 3;
+    P->nSNPs = a.nSNPs;
+    P->n_its = a.n_gibbs_burn_in_its + a.n_gibbs_sample_its;
+    P->n_burn = a.n_gibbs_burn_in_its;
+    P->flags = a.flags;
+    P->ff = a.ff;
+    P->one_over_K = 1 / double(a.K);
+    P->d2 = 1 / a.maxDifferenceBetweenReads;
+    P->class_sum_cutoff = a.class_sum_cutoff;
+    const double pp[3] = {0.5, (1 - a.ff) / 2, (a.ff / 2)};
+    for (int i = 0; i < 3; i++) P->prior[i] = pp[i];
+    const double rlc[7][3] = {{1, 0, 0},
+                              {0, 1, 0},
+                              {0, 0, 1},
+                              {pp[0] / (pp[0] + pp[1]), pp[1] / (pp[0] + pp[1]), 0},
+                              {pp[0] / (pp[0] + pp[2]), 0, pp[2] / (pp[0] + pp[2])},
+                              {0, pp[1] / (pp[1] + pp[2]), pp[2] / (pp[1] + pp[2])},
+                              {pp[0], pp[1], pp[2]}};
+    std::memcpy(P->rlc, rlc, sizeof(rlc));
+    P->ref_error = a.panel->ref_error;
+    P->rare_common = (a.flags & QUILT_F_MAKE_EMATREAD_RARE_COMMON) ? 1 : 0;
+    P->Jmax = a.Jmax;
+}
+
+template <int NT, int EPT>
+int sweep_occupancy(int Kp, int NH, int* occ, int* smem) {
+    const SweepSmemLayout L = sweep_smem_layout(Kp, NH, NT);
+    *smem = L.total;
+    CK(cudaFuncSetAttribute(k_sweep<NT, EPT, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, k_sweep<NT, EPT, 2>, NT, L.total));
+    return QUILT_OK;
+}
+
+int setup_bucket(QuiltGpuBatch* B, Bucket& bk, size_t* mem_budget) {
+    const BatchParams& P = bk.P;
+    if (!pick_geo(P.K, &bk.geo)) return set_err(QUILT_ERR_UNSUPPORTED, "Ksubset too large");
+    int occ = 0, smem = 0;
+    int rc = with_geo(bk.geo, [&](auto nt, auto ept) { return sweep_occupancy<decltype(nt)::value, decltype(ept)::value>(P.Kp, P.NH, &occ, &smem); });
+    if (rc != QUILT_OK) return rc;
+    if (occ < 1) return set_err(QUILT_ERR_UNSUPPORTED, "sweep kernel does not fit on an SM for this K");
+    for (int ji : bk.jobs) {
+        const HostJob& j = B->jobs[ji];
+        bk.R_max = std::max(bk.R_max, j.R);
+        bk.n_tab_max = std::max(bk.n_tab_max, j.n_tab);
+        bk.n_dense_max = std::max(bk.n_dense_max, j.n_dense);
+    }
+    const size_t col = (size_t)P.NH * P.T * P.Kp * 8;
+    size_t o = 0;
+    bk.o_alpha = o, o += al(col);
+    bk.o_beta = o, o += al(col);
+    bk.o_eG = o, o += al(col);
+    bk.o_c = o, o += al((size_t)P.NH * P.T * 8);
+    bk.o_W = o, o += al((size_t)P.T * P.Kp * 4);
+    bk.o_Wc = o, o += al(P.rare_common ? (size_t)B->panel.Tc * P.Kp * 4 : 0);
+    bk.o_tabs = o, o += al((size_t)std::max(bk.n_tab_max, 1) * sizeof(TabEnt));
+    bk.o_dense = o, o += al((size_t)std::max(bk.n_dense_max, 1) * P.Kp * 8);
+    bk.o_xprob = o, o += al((size_t)bk.R_max * 24);
+    bk.o_snp_type = o, o += al(P.nSNPs);
+    bk.o_rate = o, o += al((size_t)P.T * 8);
+    bk.o_hapLocal = o, o += al(P.rare_common ? (size_t)P.nSNPs * 24 : 0);
+    bk.slot_bytes = o;
+    int cap = g_sms * occ;
+    const size_t by_mem = std::max<size_t>(1, *mem_budget / std::max<size_t>(bk.slot_bytes, 1));
+    bk.n_slots = (int)std::min<size_t>(std::min<size_t>(cap, bk.jobs.size()), by_mem);
+    CK(bk.slots.alloc((size_t)bk.n_slots * bk.slot_bytes));
+    CK(cudaMemsetAsync(bk.slots.p, 0, (size_t)bk.n_slots * bk.slot_bytes, g_stream));
+    CK(bk.djobs.alloc((size_t)bk.n_slots * sizeof(JobDev)));
+    CK(bk.hjobs.alloc((size_t)bk.n_slots * sizeof(JobDev)));
+    *mem_budget -= std::min(*mem_budget, (size_t)bk.n_slots * bk.slot_bytes);
+    bk.perform_block = (P.flags & QUILT_F_PERFORM_BLOCK_GIBBS) != 0;
+    bk.do_shard = (P.flags & QUILT_F_DO_SHARD_BLOCK_GIBBS) != 0;
+    bk.debug = (P.flags & (QUILT_F_RETURN_ALPHA | QUILT_F_RETURN_EXTRA)) != 0;
+    return QUILT_OK;
+}
+
+void make_jobdev(const QuiltGpuBatch* B, const Bucket& bk, const HostJob& j, int slot, JobDev* D) {
+    std::memset(D, 0, sizeof(*D));
+    char* s = (char*)bk.slots.p + (size_t)slot * bk.slot_bytes;
+    const char* in = (const char*)B->din.p + j.in_off;
+    char* out = (char*)B->dout.p + j.out_off;
+    D->R = j.R;
+    D->first_read = j.a.first_read_for_gibbs_initialization;
+    D->n_dense = j.n_dense;
+    D->alpha = (double*)(s + bk.o_alpha);
+    D->beta = (double*)(s + bk.o_beta);
+    D->eG = (double*)(s + bk.o_eG);
+    D->c = (double*)(s + bk.o_c);
+    D->W = (uint32_t*)(s + bk.o_W);
+    D->Wc = (uint32_t*)(s + bk.o_Wc);
+    D->desc = (ReadDesc*)(in + j.li.desc);
+    D->tabs = (TabEnt*)(s + bk.o_tabs);
+    D->dense = (double*)(s + bk.o_dense);
+    D->xprob = (double*)(s + bk.o_xprob);
+    D->snp_type = (uint8_t*)(s + bk.o_snp_type);
+    D->rate = (double*)(s + bk.o_rate);
+    D->hapLocal = (double*)(s + bk.o_hapLocal);
+    D->which = (const int32_t*)(in + j.li.which);
+    D->rs = (const int32_t*)(in + j.li.rs);
+    D->roff = (const int32_t*)(in + j.li.roff);
+    D->u = (const int32_t*)(in + j.li.u);
+    D->pRA = (const double*)(in + j.li.pRA);
+    D->wif0 = (const int32_t*)(in + j.li.wif0);
+    D->ts = (const int32_t*)(in + j.li.ts);
+    D->dense_reads = (const int32_t*)(in + j.li.dense_reads);
+    D->runif_reads = (const double*)(in + j.li.runif_reads);
+    D->runif_shard = (const double*)(in + j.li.runif_shard);
+    D->tm = (const double*)(in + j.li.tm);
+    D->H0 = (const int32_t*)(in + j.li.H0);
+    D->H = (int32_t*)(out + j.lo.H);
+    D->Hclass = (int32_t*)(out + j.lo.Hclass);
+    D->lik = (double*)(out + j.lo.lik);
+    D->underflow = (int32_t*)(out + j.lo.underflow);
+    D->hapProbs = (double*)(out + j.lo.hap);
+    D->genM = (double*)(out + j.lo.genM);
+    D->genF = (double*)(out + j.lo.genF);
+    D->cat_out = (int32_t*)(out + j.lo.cat);
+}
+
+// grid = (ceil(R_max / 256), jobs): labels start from H0; read_category export
+__global__ void __launch_bounds__(256) k_copy_H(const JobDev* __restrict__ jobs) {
+    const JobDev& J = jobs[blockIdx.y];
+    const int r = blockIdx.x * 256 + threadIdx.x;
+    if (r < J.R) J.H[r] = J.H0[r];
+}
+__global__ void __launch_bounds__(256) k_export_cat(const JobDev* __restrict__ jobs) {
+    const JobDev& J = jobs[blockIdx.y];
+    const int r = blockIdx.x * 256 + threadIdx.x;
+    if (r < J.R) J.cat_out[r] = J.desc[r].cat;
+}
+
+int run_prep(QuiltGpuBatch* B, Bucket& bk, int n, const JobDev* dj) {
+    const BatchParams& P = bk.P;
+    const int kb = (P.Kp + 255) / 256;
+    if (P.rare_common) {
+        k_unpack_common<<<dim3(kb, B->panel.Tc, n), 256, 0, g_stream>>>(B->panel, dj, P.K, P.Kp, 1);
+        LAUNCHED();
+        k_assemble_all<<<dim3(kb, P.T, n), 256, 0, g_stream>>>(B->panel, dj, P.K, P.Kp);
+        LAUNCHED();
+        k_scatter_rare<<<dim3((P.K + 255) / 256, n), 256, 0, g_stream>>>(B->panel, dj, P.K, P.Kp);
+        LAUNCHED();
+        k_snp_type<<<dim3(P.T, n), 128, 0, g_stream>>>(B->panel, dj, P.K, P.Kp);
+        LAUNCHED();
+    } else {
+        k_unpack_common<<<dim3(kb, P.T, n), 256, 0, g_stream>>>(B->panel, dj, P.K, P.Kp, 0);
+        LAUNCHED();
+    }
+    k_build_tables<<<dim3((bk.R_max + TAB_WARPS - 1) / TAB_WARPS, n), TAB_WARPS * 32, 0, g_stream>>>(P, dj);
+    LAUNCHED();
+    if (bk.n_dense_max > 0) {
+        k_build_dense<<<dim3(bk.n_dense_max, n), 256, 0, g_stream>>>(P, dj);
+        LAUNCHED();
+    }
+    CK(cudaGetLastError());
+    return QUILT_OK;
+}
+
+template <int NT, int EPT>
+int run_wave_t(QuiltGpuBatch* B, Bucket& bk, int n, const JobDev* dj, bool timed) {
+    const BatchParams& P = bk.P;
+    const SweepSmemLayout L = sweep_smem_layout(P.Kp, P.NH, NT);
+    k_copy_H<<<dim3((bk.R_max + 255) / 256, n), 256, 0, g_stream>>>(dj);
+    LAUNCHED();
+    int rc = run_prep(B, bk, n, dj);
+    if (rc != QUILT_OK) return rc;
+    if (P.flags & QUILT_F_GIBBS_INITIALIZE_ITERATIVELY) {
+        k_init_iterative<<<dim3(P.T, n), 256, 0, g_stream>>>(P, dj);
+        LAUNCHED();
+    } else {
+        k_make_eG<<<dim3(P.T, n), 256, 0, g_stream>>>(P, dj);
+        LAUNCHED();
+        k_fb_generic<NT, EPT><<<dim3(n, P.NH), NT, 0, g_stream>>>(P, dj, 1);
+        LAUNCHED();
+    }
+    int episode = 0;
+    const size_t hsm = (size_t)P.NH * P.Kp * 8 + (size_t)P.Kp * 4 + 8 * 3 * 2 * 32 * 8;
+    CK(cudaFuncSetAttribute(k_happrobs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsm));
+    for (int it = 0; it < P.n_its; it++) {
+        cudaEvent_t e0 = nullptr, e1 = nullptr;
+        if (timed) {
+            CK(cudaEventCreate(&e0));
+            CK(cudaEventCreate(&e1));
+            CK(cudaEventRecord(e0, g_stream));
+        }
+        k_sweep<NT, EPT, 2><<<n, NT, L.total, g_stream>>>(P, dj, it);
+        LAUNCHED();
+        if (timed) {
+            CK(cudaEventRecord(e1, g_stream));
+            B->sweep_events.emplace_back(e0, e1);
+        }
+        bool blk = false;
+        if (bk.perform_block)
+            for (int b : bk.block_its) blk = blk || (b == it);
+        if (blk) {
+            // Diploid block resampler (gibbs-nipt-block.cpp:1636-1967): with two haplotypes the third column of the
+            // reference's local matrices is zero, every permutation score is NaN and the identity is always kept
+            // (DESIGN.md "block Gibbs, diploid"); the trailing backward passes reproduce beta unchanged.  Only the
+            // shard pass alters state.
+            if (bk.do_shard && P.T > 1) {
+                k_shard<NT, EPT><<<n, NT, 0, g_stream>>>(P, dj, episode);
+                LAUNCHED();
+            }
+            episode++;
+        }
+        if (it >= P.n_burn) {
+            const int n_sample = P.n_its - P.n_burn;
+            k_happrobs<<<dim3(P.T, n), 256, hsm, g_stream>>>(P, dj, it == P.n_burn, it == P.n_its - 1, 1.0 / double(n_sample));
+            LAUNCHED();
+        }
+    }
+    k_export_cat<<<dim3((bk.R_max + 255) / 256, n), 256, 0, g_stream>>>(dj);
+    LAUNCHED();
+    CK(cudaGetLastError());
+    return QUILT_OK;
+}
+
+int fetch_debug(QuiltGpuBatch* B, Bucket& bk, int w0, int n) {
+    const BatchParams& P = bk.P;
+    CK(cudaStreamSynchronize(g_stream));
+    const size_t cols = (size_t)P.NH * P.T * P.Kp;
+    std::vector<double> tmp(cols);
+    for (int i = 0; i < n; i++) {
+        HostJob& j = B->jobs[bk.jobs[w0 + i]];
+        const char* s = (const char*)bk.slots.p + (size_t)i * bk.slot_bytes;
+        if (P.flags & QUILT_F_RETURN_ALPHA) {
+            auto grab = [&](size_t off, std::vector<double>& dst) -> int {
+                CK(cudaMemcpy(tmp.data(), s + off, cols * 8, cudaMemcpyDeviceToHost));
+                dst.assign((size_t)P.NH * P.T * P.K, 0.0);
+                for (int h = 0; h < P.NH; h++)
+                    for (int g = 0; g < P.T; g++)
+                        std::memcpy(&dst[((size_t)h * P.T + g) * P.K], &tmp[((size_t)h * P.T + g) * P.Kp], (size_t)P.K * 8);
+                return QUILT_OK;
+            };
+            int rc;
+            if ((rc = grab(bk.o_alpha, j.dbg_alpha)) != QUILT_OK) return rc;
+            if ((rc = grab(bk.o_beta, j.dbg_beta)) != QUILT_OK) return rc;
+            if ((rc = grab(bk.o_eG, j.dbg_eG)) != QUILT_OK) return rc;
+            j.dbg_c.assign((size_t)P.NH * P.T, 0.0);
+            CK(cudaMemcpy(j.dbg_c.data(), s + bk.o_c, (size_t)P.NH * P.T * 8, cudaMemcpyDeviceToHost));
+        }
+        if (P.flags & QUILT_F_RETURN_EXTRA) {
+            DBuf d;
+            CK(d.alloc((size_t)P.K * j.R * 8));
+            const JobDev* dj = (const JobDev*)bk.djobs.p + i;
+            k_expand_eMatRead<<<j.R, 256, 0, g_stream>>>(P, dj, (double*)d.p);
+            LAUNCHED();
+            CK(cudaStreamSynchronize(g_stream));
+            j.dbg_eMatRead.assign((size_t)P.K * j.R, 0.0);
+            CK(cudaMemcpy(j.dbg_eMatRead.data(), d.p, (size_t)P.K * j.R * 8, cudaMemcpyDeviceToHost));
+        }
+    }
+    return QUILT_OK;
+}
+
+int run_bucket(QuiltGpuBatch* B, Bucket& bk, bool timed, bool prep_only = false) {
+    const int nj = (int)bk.jobs.size();
+    for (int w0 = 0; w0 < nj; w0 += bk.n_slots) {
+        const int n = std::min(bk.n_slots, nj - w0);
+        JobDev* hj = (JobDev*)bk.hjobs.p;
+        // the previous wave's kernels may still be reading the device copy; the stream orders the upload after them,
+        // but the pinned source must not be rewritten before that upload has been consumed
+        if (w0 > 0) CK(cudaStreamSynchronize(g_stream));
+        for (int i = 0; i < n; i++) make_jobdev(B, bk, B->jobs[bk.jobs[w0 + i]], i, &hj[i]);
+        CK(cudaMemcpyAsync(bk.djobs.p, hj, (size_t)n * sizeof(JobDev), cudaMemcpyHostToDevice, g_stream));
+        if (bk.P.rare_common) {
+            for (int i = 0; i < n; i++)
+                CK(cudaMemsetAsync((char*)bk.slots.p + (size_t)i * bk.slot_bytes + bk.o_hapLocal, 0, (size_t)bk.P.nSNPs * 24, g_stream));
+        }
+        const JobDev* dj = (const JobDev*)bk.djobs.p;
+        int rc;
+        if (prep_only) {
+            k_copy_H<<<dim3((bk.R_max + 255) / 256, n), 256, 0, g_stream>>>(dj);
+            LAUNCHED();
+            rc = run_prep(B, bk, n, dj);
+            if (rc == QUILT_OK) {
+                k_export_cat<<<dim3((bk.R_max + 255) / 256, n), 256, 0, g_stream>>>(dj);
+                LAUNCHED();
+            }
+        } else {
+            rc = with_geo(bk.geo, [&](auto nt, auto ept) { return run_wave_t<decltype(nt)::value, decltype(ept)::value>(B, bk, n, dj, timed); });
+        }
+        if (rc != QUILT_OK) return rc;
+        if (bk.debug) {
+            rc = fetch_debug(B, bk, w0, n);
+            if (rc != QUILT_OK) return rc;
+        }
+    }
+    return QUILT_OK;
+}
+
+// per_it_likelihoods row from the device record (add_to_per_it_likelihoods, gibbs-nipt.cpp:1583-1621;
+// calculate_likelihoods_values :1483-1519; rcpp_get_log_p_H_class gibbs-nipt-block.cpp:146-164)
+void fill_lik_row(const QuiltGibbsArgs& a, const double* rec, int iteration, int n_rows, double* out) {
+    const bool diploid = (a.flags & QUILT_F_SAMPLE_IS_DIPLOID) != 0;
+    const double ff = a.ff;
+    const double inf = std::numeric_limits<double>::infinity();
+    const double d1 = rec[0], d2 = rec[1], d3 = diploid ? inf : rec[2];  // diploid: c3 is all zero -> -log(0)
+    const double prior[3] = {0.5, (1 - ff) / 2, (ff / 2)};
+    double dH = 0;
+    for (int h = 0; h < 3; h++)
+        if (rec[3 + h] > 0) dH += rec[3 + h] * std::log(prior[h]);
+    const int burn = a.n_gibbs_burn_in_its;
+    const int i_result_it = (iteration + 1 > burn) ? iteration - burn : -2;
+    auto at = [&](int col) -> double& { return out[(size_t)col * n_rows + iteration]; };
+    at(0) = 1;
+    at(1) = 1;
+    at(2) = iteration + 1;
+    at(3) = i_result_it + 1;
+    at(4) = d1;
+    at(5) = d2;
+    at(6) = d3;
+    at(7) = d1 + d2 + d3;
+    at(8) = dH;
+    at(9) = at(7) + dH;
+    const double rc[3] = {rec[3], rec[4], rec[5]};
+    const int n = (int)(rc[0] + rc[1] + rc[2]);
+    double r = std::lgamma(1.0 * (n + 1.0));
+    for (int i = 0; i < 3; i++)
+        if (prior[i] > 0) r += rc[i] * std::log(prior[i]) - std::lgamma(1.0 * (rc[i] + 1.0));
+    at(10) = r;
+    at(11) = 1;
+    double lp = 0;
+    if (a.flags & QUILT_F_RECORD_READ_SET) {
+        const double vals[8] = {0, std::log(0.5), std::log(0.5 - ff * 0.5), std::log(ff * 0.5), std::log(1.0 - ff * 0.5), std::log(0.5 + ff * 0.5),
+                                std::log(0.5), 0};
+        for (int q = 0; q < 8; q++)
+            if (rec[6 + q] > 0) lp += rec[6 + q] * vals[q];
+    }
+    at(12) = lp;
+}
+
+}  // namespace
+
+// ================================================================================================== C ABI
+extern "C" {
+
+int quilt_gpu_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+int quilt_gpu_set_device(int32_t device) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_stream && device != g_device) return set_err(QUILT_ERR_BAD_ARG, "device already initialised");
+    g_device = device;
+    return ensure_device();
+}
+
+const char* quilt_gpu_last_error(void) { return g_err.c_str(); }
+
+int64_t quilt_gpu_kernel_launches(void) { return g_launches.load(); }
+
+void quilt_gpu_release_panel_cache(void) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_panels.clear();
+}
+
+int quilt_gpu_batch_free(QuiltGpuBatch* b) {
+    if (b) {
+        if (g_stream) cudaStreamSynchronize(g_stream);
+        delete b;
+    }
+    return QUILT_OK;
+}
+
+int quilt_gpu_batch_stage(int32_t n, const QuiltGibbsArgs* args, QuiltGpuBatch** batch) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (n <= 0 || !args || !batch) return set_err(QUILT_ERR_BAD_ARG, "bad batch arguments");
+    int rc = ensure_device();
+    if (rc != QUILT_OK) return rc;
+    std::unique_ptr<QuiltGpuBatch> B(new QuiltGpuBatch());
+    B->n = n;
+    B->jobs.resize(n);
+    for (int i = 0; i < n; i++) {
+        if ((rc = validate(args[i])) != QUILT_OK) return rc;
+        if (args[i].panel != args[0].panel && !same_panel(*args[i].panel, *args[0].panel))
+            return set_err(QUILT_ERR_UNSUPPORTED, "all calls of a batch must share one panel");
+        B->jobs[i].a = args[i];
+    }
+    if ((rc = get_panel(args[0].panel, &B->panel)) != QUILT_OK) return rc;
+    std::map<BucketKey, int> index;
+    size_t in_total = 0, out_total = 0;
+    for (int i = 0; i < n; i++) {
+        HostJob& j = B->jobs[i];
+        if ((rc = prepare_job(j)) != QUILT_OK) return rc;
+        layout_in(j);
+        j.in_off = in_total;
+        j.out_off = out_total;
+        in_total += j.li.end;
+        out_total += j.lo.end;
+        const BucketKey key = bucket_key(j.a);
+        auto it = index.find(key);
+        if (it == index.end()) {
+            auto bk = std::make_unique<Bucket>();
+            make_params(j.a, &bk->P);
+            bk->block_its.assign(j.a.block_gibbs_iterations, j.a.block_gibbs_iterations + j.a.n_block_gibbs_iterations);
+            index[key] = (int)B->buckets.size();
+            j.bucket = (int)B->buckets.size();
+            B->buckets.push_back(std::move(bk));
+        } else {
+            j.bucket = it->second;
+        }
+        B->buckets[j.bucket]->jobs.push_back(i);
+    }
+    B->in_bytes = in_total;
+    B->out_bytes = out_total;
+    CK(B->din.alloc(in_total));
+    CK(B->dout.alloc(out_total));
+    CK(B->hin.alloc(in_total));
+    CK(B->hout.alloc(out_total));
+    for (int i = 0; i < n; i++) fill_in(B->jobs[i], (char*)B->hin.p + B->jobs[i].in_off);
+    CK(cudaMemcpyAsync(B->din.p, B->hin.p, in_total, cudaMemcpyHostToDevice, g_stream));
+    size_t free_b = 0, total_b = 0;
+    CK(cudaMemGetInfo(&free_b, &total_b));
+    size_t budget = (size_t)(free_b * 0.92);
+    // split the memory budget evenly between buckets (they run one after the other but keep their slots)
+    const size_t per_bucket = budget / std::max<size_t>(1, B->buckets.size());
+    for (auto& bk : B->buckets) {
+        size_t mb = per_bucket;
+        if ((rc = setup_bucket(B.get(), *bk, &mb)) != QUILT_OK) return rc;
+    }
+    CK(cudaEventCreate(&B->ev0));
+    CK(cudaEventCreate(&B->ev1));
+    CK(cudaStreamSynchronize(g_stream));
+    *batch = B.release();
+    return QUILT_OK;
+}
+
+int quilt_gpu_batch_run(QuiltGpuBatch* B) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!B) return set_err(QUILT_ERR_BAD_ARG, "null batch");
+    for (auto& p : B->sweep_events) {
+        cudaEventDestroy(p.first);
+        cudaEventDestroy(p.second);
+    }
+    B->sweep_events.clear();
+    CK(cudaMemsetAsync(B->dout.p, 0, B->out_bytes, g_stream));
+    CK(cudaEventRecord(B->ev0, g_stream));
+    for (auto& bk : B->buckets) {
+        int rc = run_bucket(B, *bk, true);
+        if (rc != QUILT_OK) return rc;
+    }
+    CK(cudaEventRecord(B->ev1, g_stream));
+    B->ran = true;
+    B->fetched_raw = false;
+    return QUILT_OK;
+}
+
+int quilt_gpu_batch_sync(QuiltGpuBatch* B) {
+    if (!B) return set_err(QUILT_ERR_BAD_ARG, "null batch");
+    CK(cudaStreamSynchronize(g_stream));
+    if (B->ran) {
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, B->ev0, B->ev1));
+        B->total_ms = ms;
+        double s = 0;
+        for (auto& p : B->sweep_events) {
+            CK(cudaEventElapsedTime(&ms, p.first, p.second));
+            s += ms;
+        }
+        B->sweep_ms = s;
+        B->n_sweep_launches = (int)B->sweep_events.size();
+    }
+    return QUILT_OK;
+}
+
+int quilt_gpu_batch_timing(QuiltGpuBatch* B, double* total_ms, double* sweep_ms, int32_t* n_sweep_launches) {
+    if (!B) return set_err(QUILT_ERR_BAD_ARG, "null batch");
+    if (total_ms) *total_ms = B->total_ms;
+    if (sweep_ms) *sweep_ms = B->sweep_ms;
+    if (n_sweep_launches) *n_sweep_launches = B->n_sweep_launches;
+    return QUILT_OK;
+}
+
+int quilt_gpu_batch_fetch(QuiltGpuBatch* B, QuiltGibbsOut* out) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!B || !out) return set_err(QUILT_ERR_BAD_ARG, "null batch / out");
+    if (!B->ran) return set_err(QUILT_ERR_BAD_ARG, "batch has not been run");
+    if (!B->fetched_raw) {
+        CK(cudaMemcpyAsync(B->hout.p, B->dout.p, B->out_bytes, cudaMemcpyDeviceToHost, g_stream));
+        CK(cudaStreamSynchronize(g_stream));
+        B->fetched_raw = true;
+    }
+    for (int i = 0; i < B->n; i++) {
+        const HostJob& j = B->jobs[i];
+        const QuiltGibbsArgs& a = j.a;
+        QuiltGibbsOut& o = out[i];
+        const char* base = (const char*)B->hout.p + j.out_off;
+        const int under = *reinterpret_cast<const int32_t*>(base + j.lo.underflow);
+        o.underflow_problem = under ? 1 : 0;
+        const size_t n3 = (size_t)a.nSNPs * 3;
+        if (o.hapProbs_t) std::memcpy(o.hapProbs_t, base + j.lo.hap, n3 * 8);
+        if (o.genProbsM_t) std::memcpy(o.genProbsM_t, base + j.lo.genM, n3 * 8);
+        if (o.genProbsF_t) std::memcpy(o.genProbsF_t, base + j.lo.genF, n3 * 8);
+        if (o.H) std::memcpy(o.H, base + j.lo.H, (size_t)j.R * 4);
+        if (o.H_class && (a.flags & QUILT_F_RECORD_READ_SET)) std::memcpy(o.H_class, base + j.lo.Hclass, (size_t)j.R * 4);
+        if (o.read_category) std::memcpy(o.read_category, base + j.lo.cat, (size_t)j.R * 4);
+        if (o.per_it_likelihoods) {
+            const int n_rows = (a.n_gibbs_sample_its == 0) ? 1 : j.n_its;
+            std::memset(o.per_it_likelihoods, 0, (size_t)n_rows * 13 * 8);
+            const double* lik = reinterpret_cast<const double*>(base + j.lo.lik);
+            for (int it = 0; it < std::min(n_rows, j.n_its); it++) {
+                fill_lik_row(a, lik + (size_t)it * LIK_N, it, n_rows, o.per_it_likelihoods);
+            }
+        }
+        const int NH = (a.flags & QUILT_F_SAMPLE_IS_DIPLOID) ? 2 : 3;
+        if (a.flags & QUILT_F_RETURN_ALPHA) {
+            const size_t per = (size_t)a.nGrids * a.K;
+            for (int h = 0; h < NH; h++) {
+                if (o.alphaHat_t[h] && !j.dbg_alpha.empty()) std::memcpy(o.alphaHat_t[h], &j.dbg_alpha[h * per], per * 8);
+                if (o.betaHat_t[h] && !j.dbg_beta.empty()) std::memcpy(o.betaHat_t[h], &j.dbg_beta[h * per], per * 8);
+                if (o.eMatGrid_t[h] && !j.dbg_eG.empty()) std::memcpy(o.eMatGrid_t[h], &j.dbg_eG[h * per], per * 8);
+                if (o.c[h] && !j.dbg_c.empty()) std::memcpy(o.c[h], &j.dbg_c[(size_t)h * a.nGrids], (size_t)a.nGrids * 8);
+            }
+        }
+        if ((a.flags & QUILT_F_RETURN_EXTRA) && o.eMatRead_t && !j.dbg_eMatRead.empty())
+            std::memcpy(o.eMatRead_t, j.dbg_eMatRead.data(), j.dbg_eMatRead.size() * 8);
+    }
+    return QUILT_OK;
+}
+
+int quilt_gpu_gibbs_batch(int32_t n, const QuiltGibbsArgs* args, QuiltGibbsOut* out) {
+    QuiltGpuBatch* B = nullptr;
+    int rc = quilt_gpu_batch_stage(n, args, &B);
+    if (rc != QUILT_OK) return rc;
+    rc = quilt_gpu_batch_run(B);
+    if (rc == QUILT_OK) rc = quilt_gpu_batch_sync(B);
+    if (rc == QUILT_OK) rc = quilt_gpu_batch_fetch(B, out);
+    quilt_gpu_batch_free(B);
+    return rc;
+}
+
+int quilt_gpu_gibbs(const QuiltGibbsArgs* args, QuiltGibbsOut* out) { return quilt_gpu_gibbs_batch(1, args, out); }
+
+// ---- component entry points (parity tests of the individual reference functions)
+int quilt_gpu_make_eMatRead_t(const QuiltGibbsArgs* args, double* eMatRead_t, int32_t* read_category) {
+    if (!args || !eMatRead_t) return set_err(QUILT_ERR_BAD_ARG, "null argument");
+    QuiltGibbsArgs a = *args;
+    a.flags |= QUILT_F_RETURN_EXTRA;
+    QuiltGpuBatch* B = nullptr;
+    int rc = quilt_gpu_batch_stage(1, &a, &B);
+    if (rc != QUILT_OK) return rc;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        rc = cudaMemsetAsync(B->dout.p, 0, B->out_bytes, g_stream) == cudaSuccess ? QUILT_OK : set_err(QUILT_ERR_CUDA, "memset");
+        if (rc == QUILT_OK) rc = run_bucket(B, *B->buckets[0], false, true);
+        if (rc == QUILT_OK) {
+            const HostJob& j = B->jobs[0];
+            std::memcpy(eMatRead_t, j.dbg_eMatRead.data(), j.dbg_eMatRead.size() * 8);
+            if (read_category) {
+                cudaError_t e = cudaMemcpy(read_category, (const char*)B->dout.p + j.out_off + j.lo.cat, (size_t)j.R * 4, cudaMemcpyDeviceToHost);
+                if (e != cudaSuccess) rc = set_err(QUILT_ERR_CUDA, cudaGetErrorString(e));
+            }
+        }
+    }
+    quilt_gpu_batch_free(B);
+    return rc;
+}
+
+int quilt_gpu_unpack_panel(const QuiltPanel* panel, int32_t K, const int32_t* which, int32_t all_snps, uint32_t* words) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!panel || !which || !words || K <= 0) return set_err(QUILT_ERR_BAD_ARG, "null argument");
+    int rc = ensure_device();
+    if (rc != QUILT_OK) return rc;
+    PanelDev PD;
+    if ((rc = get_panel(panel, &PD)) != QUILT_OK) return rc;
+    if (all_snps && panel->nSNPs_all <= 0) return set_err(QUILT_ERR_BAD_ARG, "panel has no all-SNP axis");
+    for (int k = 0; k < K; k++)
+        if (which[k] < 1 || which[k] > panel->K_full) return set_err(QUILT_ERR_BAD_ARG, "which_haps_to_use out of range");
+    const int Kp = (K + 31) & ~31;
+    const int T = all_snps ? (panel->nSNPs_all + 31) / 32 : panel->nGrids;
+    DBuf dw, dwc, dwhich, dj, dtype;
+    CK(dw.alloc((size_t)T * Kp * 4));
+    CK(dwc.alloc((size_t)panel->nGrids * Kp * 4));
+    CK(dwhich.alloc((size_t)K * 4));
+    CK(dj.alloc(sizeof(JobDev)));
+    CK(dtype.alloc(std::max(panel->nSNPs_all, 1)));
+    CK(cudaMemcpy(dwhich.p, which, (size_t)K * 4, cudaMemcpyHostToDevice));
+    JobDev J;
+    std::memset(&J, 0, sizeof(J));
+    J.W = (uint32_t*)dw.p;
+    J.Wc = (uint32_t*)dwc.p;
+    J.which = (const int32_t*)dwhich.p;
+    J.snp_type = (uint8_t*)dtype.p;
+    CK(cudaMemcpy(dj.p, &J, sizeof(J), cudaMemcpyHostToDevice));
+    const JobDev* d = (const JobDev*)dj.p;
+    const int kb = (Kp + 255) / 256;
+    if (all_snps) {
+        k_unpack_common<<<dim3(kb, PD.Tc, 1), 256, 0, g_stream>>>(PD, d, K, Kp, 1);
+        LAUNCHED();
+        k_assemble_all<<<dim3(kb, T, 1), 256, 0, g_stream>>>(PD, d, K, Kp);
+        LAUNCHED();
+        k_scatter_rare<<<dim3((K + 255) / 256, 1), 256, 0, g_stream>>>(PD, d, K, Kp);
+        LAUNCHED();
+    } else {
+        k_unpack_common<<<dim3(kb, T, 1), 256, 0, g_stream>>>(PD, d, K, Kp, 0);
+        LAUNCHED();
+    }
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(g_stream));
+    std::vector<uint32_t> tmp((size_t)T * Kp);
+    CK(cudaMemcpy(tmp.data(), dw.p, (size_t)T * Kp * 4, cudaMemcpyDeviceToHost));
+    for (int g = 0; g < T; g++) std::memcpy(words + (size_t)g * K, &tmp[(size_t)g * Kp], (size_t)K * 4);
+    return QUILT_OK;
+}
+
+int quilt_gpu_forward_backward(int32_t K, int32_t T, const double* eMatGrid_t, const double* tm, double* alphaHat_t, double* betaHat_t, double* c) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (K <= 0 || T <= 0 || !eMatGrid_t || !tm || !alphaHat_t || !betaHat_t || !c) return set_err(QUILT_ERR_BAD_ARG, "null argument");
+    int rc = ensure_device();
+    if (rc != QUILT_OK) return rc;
+    Geo geo;
+    if (!pick_geo(K, &geo)) return set_err(QUILT_ERR_UNSUPPORTED, "K > 4096 not supported yet");
+    const int Kp = (K + 31) & ~31;
+    const size_t cols = (size_t)T * Kp;
+    DBuf da, db, de, dc, dtm, dj, du;
+    CK(da.alloc(cols * 8));
+    CK(db.alloc(cols * 8));
+    CK(de.alloc(cols * 8));
+    CK(dc.alloc((size_t)T * 8));
+    CK(dtm.alloc((size_t)std::max(T - 1, 1) * 16));
+    CK(dj.alloc(sizeof(JobDev)));
+    CK(du.alloc(256));
+    CK(cudaMemset(du.p, 0, 256));
+    CK(cudaMemset(de.p, 0, cols * 8));
+    CK(cudaMemcpy2D(de.p, (size_t)Kp * 8, eMatGrid_t, (size_t)K * 8, (size_t)K * 8, T, cudaMemcpyHostToDevice));
+    if (T > 1) CK(cudaMemcpy(dtm.p, tm, (size_t)(T - 1) * 16, cudaMemcpyHostToDevice));
+    JobDev J;
+    std::memset(&J, 0, sizeof(J));
+    J.alpha = (double*)da.p;
+    J.beta = (double*)db.p;
+    J.eG = (double*)de.p;
+    J.c = (double*)dc.p;
+    J.tm = (const double*)dtm.p;
+    J.underflow = (int32_t*)du.p;
+    CK(cudaMemcpy(dj.p, &J, sizeof(J), cudaMemcpyHostToDevice));
+    BatchParams P;
+    std::memset(&P, 0, sizeof(P));
+    P.K = K;
+    P.Kp = Kp;
+    P.T = T;
+    P.NH = 1;
+    P.one_over_K = 1 / double(K);
+    rc = with_geo(geo, [&](auto nt, auto ept) {
+        k_fb_generic<decltype(nt)::value, decltype(ept)::value><<<dim3(1, 1), decltype(nt)::value, 0, g_stream>>>(P, (const JobDev*)dj.p, 1);
+        LAUNCHED();
+        return QUILT_OK;
+    });
+    if (rc != QUILT_OK) return rc;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(g_stream));
+    CK(cudaMemcpy2D(alphaHat_t, (size_t)K * 8, da.p, (size_t)Kp * 8, (size_t)K * 8, T, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy2D(betaHat_t, (size_t)K * 8, db.p, (size_t)Kp * 8, (size_t)K * 8, T, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(c, dc.p, (size_t)T * 8, cudaMemcpyDeviceToHost));
+    return QUILT_OK;
+}
+
+}  // extern "C"

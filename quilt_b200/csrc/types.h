@@ -1,0 +1,108 @@
+// types.h — host/device structures of the B200 Gibbs path (internal to libquiltgpu.so).
+#pragma once
+#include <stdint.h>
+
+namespace qb {
+
+// A read's emission column E[k, r] (reference: eMatRead_t, gibbs-small.cpp:116-265) takes one of at
+// most 2^nb values, selected by the alleles of haplotype k at the read's nb SNPs.  For nb <= NBMAX
+// (and SNPs inside grids wif0-1 .. wif0+1) we keep the 2^nb-entry table instead of the K-long fp64
+// column (DESIGN.md "emission tables"); everything else falls back to a dense K-long column.
+constexpr int NBMAX = 10;
+constexpr double ONE_THRESH = 1.0 - 1e-12;  // rcpp_evaluate_read_variability, gibbs-nipt.cpp:349
+
+struct TabEnt {
+    double E;     // rescaled, floored emission value for this allele pattern
+    double invE;  // 1 / E (used only inside K-long sums; stored state is updated with true divisions)
+};
+
+enum ReadMode : uint8_t { MODE_RUN = 0, MODE_GATHER = 1, MODE_DENSE = 2 };
+
+struct ReadDesc {        // 32 bytes, 16-byte aligned (staged to shared memory with cp.async)
+    uint32_t off;        // table modes: first TabEnt in the job's table pool; dense: column index in the dense pool
+    uint8_t cat;         // read_category after the force_reset / disable flags (gibbs-nipt.cpp:338-382, :2816-2827)
+    uint8_t mode;        // ReadMode
+    uint8_t nb;          // pattern bits (SNPs used = min(J + 1, Jmax + 1))
+    int8_t g0rel;        // MODE_RUN: word index of the first SNP minus wif0 (-1, 0, +1)
+    uint8_t b0;          // MODE_RUN: bit of the first SNP inside that word
+    uint8_t sel[NBMAX];  // MODE_GATHER: per SNP ((word - wif0 + 1) << 5) | bit
+    uint8_t pad[13];
+};
+static_assert(sizeof(ReadDesc) == 32, "ReadDesc must be 32 bytes");
+
+constexpr int LIK_N = 16;  // per-sweep bookkeeping record written by the sweep epilogue
+// lik[0..2] = -sum_g log c_h[g] ; lik[3..5] = #reads with label h ; lik[6..13] = #reads with H_class 0..7 ;
+// lik[14] = 1 if a non-finite sum(c_h) was seen (reference underflow check, gibbs-nipt.cpp:2959-2969)
+
+// one Gibbs call in flight on the device ("job"); pointers are device pointers
+struct JobDev {
+    int32_t R;           // reads
+    int32_t first_read;  // first_read_for_gibbs_initialization
+    int32_t n_dense;     // reads stored as dense columns
+    int32_t pad0;
+    // big state, owned by the slot the job runs in
+    double* alpha;  // [NH][T][Kp]
+    double* beta;   // [NH][T][Kp]
+    double* eG;     // [NH][T][Kp]   eMatGrid_t
+    double* c;      // [NH][T]
+    uint32_t* W;    // [T][Kp]       32-SNP allele words of the selected haplotypes on this call's SNP axis
+    uint32_t* Wc;   // [Tc][Kp]      scratch: words on the panel's common-SNP axis (all-SNP calls only)
+    ReadDesc* desc;  // [R]
+    TabEnt* tabs;    // table pool
+    double* dense;   // [n_dense][Kp]
+    double* xprob;   // [R][3] label probabilities of the last visit (H_class is derived from them)
+    uint8_t* snp_type;  // [nSNPs] all-SNP calls: 0 common, 1 rare without carrier, 2 rare with carrier(s)
+    double* rate;       // [T] scratch (block definition)
+    // inputs
+    const int32_t* which;  // [K] 1-based
+    const int32_t* rs;     // [T + 1] first read of each grid (reads are sorted by wif0)
+    const int32_t* roff;   // [R + 1]
+    const int32_t* u;      // [nU] 0-based SNP index on this call's axis
+    const double* pRA;     // [nU][2] (pR, pA) running values per read-SNP, computed on the host with libm pow()
+    const int32_t* wif0;   // [R]
+    const int32_t* ts;     // [T + 1] first table-pool entry of each grid's reads (table-mode reads only)
+    const int32_t* dense_reads;  // [n_dense] read indices stored as dense columns
+    const double* runif_reads;  // [n_its][R]
+    const double* runif_shard;  // [n_ep][T - 1]
+    const double* tm;           // [T - 1][2] (sigma, 1 - sigma)
+    const int32_t* H0;          // [R] starting labels
+    // outputs / evolving small state
+    int32_t* H;       // [R] 1-based labels
+    int32_t* Hclass;  // [R]
+    double* lik;      // [max(n_its,1)][LIK_N]
+    int32_t* underflow;  // [1]
+    double* hapProbs;    // [3][nSNPs] running sums over sampling sweeps, scaled at the end
+    double* genM;        // [3][nSNPs]
+    double* genF;        // [3][nSNPs]
+    double* hapLocal;    // [3][nSNPs] rare/common calls: the reference's never re-zeroed hapProbs_t_local (gibbs-small.cpp:711-867)
+    int32_t* cat_out;    // [R] read_category export
+};
+
+struct PanelDev {
+    int32_t K_full, Tc, nSNPsC, nMaxDH, n_special, nSNPs_all;
+    const uint8_t* hapMatcherR;    // [Tc][K_full]
+    const int32_t* distinctHapsB;  // [Tc][nMaxDH]
+    const int32_t* special;        // [2][n_special] column-major
+    const int32_t* helper;         // [2][Tc] column-major
+    const uint8_t* snp_is_common;
+    const int32_t* common_snp_index;
+    const int64_t* rare_off;
+    const int32_t* rare_snps;
+    double ref_error;
+};
+
+struct BatchParams {
+    int32_t K, Kp, T, NH, nSNPs, n_its, n_burn;
+    uint32_t flags;
+    double ff;
+    double one_over_K;
+    double d2;  // 1 / maxDifferenceBetweenReads
+    double class_sum_cutoff;
+    double prior[3];
+    double rlc[7][3];
+    double ref_error;
+    int32_t rare_common;
+    int32_t Jmax;
+};
+
+}  // namespace qb

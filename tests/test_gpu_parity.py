@@ -1,0 +1,224 @@
+"""GPU parity tests: the CUDA path through the C ABI vs the CPU oracle on identical seeded inputs.
+
+Bars (BASELINE.json north_star): integer outputs (labels H, H_class, read categories, allele words) bit-exact;
+floating point within the tolerance written next to each assert.  K-long sums are reduced in a different order on
+the GPU (tree vs Armadillo's two accumulators), so state arrays agree to ~1e-12 relative, not bitwise.
+"""
+import numpy as np
+import pytest
+
+from quilt_b200 import cabi, synth
+
+pytestmark = pytest.mark.gpu
+
+RTOL_STATE = 1e-9   # alpha / beta / c / eMatGrid after many sweeps (sum-order noise accumulates ~1e-13)
+ATOL_DS = 1e-4      # north_star: DS / GP within 1e-4
+
+
+def _rel(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    den = np.maximum(np.abs(b), 1e-300)
+    return float(np.max(np.abs(a - b) / den)) if a.size else 0.0
+
+
+def _compare(tag, g, o, state=True):
+    """print + assert the whole result of one call"""
+    msgs = []
+    assert g.underflow_problem == o.underflow_problem, f"{tag}: underflow {g.underflow_problem} vs {o.underflow_problem}"
+    nH = int(np.sum(g.H != o.H))
+    nC = int(np.sum(g.H_class != o.H_class))
+    nK = int(np.sum(g.read_category != o.read_category))
+    dhp = float(np.max(np.abs(g.hapProbs_t - o.hapProbs_t)))
+    dgm = float(np.max(np.abs(g.genProbsM_t - o.genProbsM_t)))
+    dgf = float(np.max(np.abs(g.genProbsF_t - o.genProbsF_t)))
+    msgs.append(f"H mismatches {nH}/{g.H.size}, H_class {nC}, category {nK}, |dhap| {dhp:.3e} |dgenM| {dgm:.3e} |dgenF| {dgf:.3e}")
+    if state and g.alphaHat_t is not None:
+        for h in range(len(g.alphaHat_t)):
+            msgs.append(
+                f"  hap{h}: alpha rel {_rel(g.alphaHat_t[h], o.alphaHat_t[h]):.3e} beta rel {_rel(g.betaHat_t[h], o.betaHat_t[h]):.3e} "
+                f"eG rel {_rel(g.eMatGrid_t[h], o.eMatGrid_t[h]):.3e} c rel {_rel(g.c[h], o.c[h]):.3e}"
+            )
+    fin = np.isfinite(o.per_it_likelihoods)
+    same_inf = np.array_equal(fin, np.isfinite(g.per_it_likelihoods))
+    dl = _rel(g.per_it_likelihoods[fin], o.per_it_likelihoods[fin]) if same_inf else np.inf
+    msgs.append(f"  per_it_likelihoods rel {dl:.3e} (inf pattern equal: {same_inf})")
+    print(f"[{tag}] " + "\n".join(msgs))
+    assert nK == 0, f"{tag}: read categories differ"
+    assert nH == 0, f"{tag}: read labels differ"
+    assert nC == 0, f"{tag}: H_class differs"
+    assert dhp <= ATOL_DS and dgm <= ATOL_DS and dgf <= ATOL_DS, f"{tag}: dosage-level outputs differ"
+    # GT = argmax of the genotype probabilities must be identical
+    assert np.array_equal(np.argmax(g.genProbsM_t, axis=0), np.argmax(o.genProbsM_t, axis=0)), f"{tag}: GT differs"
+    if state and g.alphaHat_t is not None:
+        for h in range(len(g.alphaHat_t)):
+            assert _rel(g.c[h], o.c[h]) < RTOL_STATE, f"{tag}: c[{h}]"
+            assert _rel(g.eMatGrid_t[h], o.eMatGrid_t[h]) < RTOL_STATE, f"{tag}: eMatGrid[{h}]"
+            assert _rel(g.alphaHat_t[h], o.alphaHat_t[h]) < RTOL_STATE, f"{tag}: alpha[{h}]"
+            assert _rel(g.betaHat_t[h], o.betaHat_t[h]) < RTOL_STATE, f"{tag}: beta[{h}]"
+    assert same_inf and dl < 1e-8, f"{tag}: per_it_likelihoods"
+
+
+# ---------------------------------------------------------------------------------------------- components
+@pytest.mark.parametrize("K", [64, 200, 600])
+def test_unpack_panel_common(gpu, oracle, small_world, K):
+    rng = np.random.default_rng(K)
+    which = rng.choice(small_world.panel.K_full, size=K, replace=False) + 1  # unsorted on purpose (Appendix D.10)
+    wg = gpu.unpack_panel(small_world.panel, which, all_snps=False)
+    wo = oracle.unpack_panel(small_world.panel, which, all_snps=False)
+    assert np.array_equal(wg, wo)
+
+
+def test_unpack_panel_all_snps(gpu, oracle, small_world):
+    which = np.sort(np.random.default_rng(5).choice(small_world.panel.K_full, size=300, replace=False)) + 1
+    wg = gpu.unpack_panel(small_world.panel, which, all_snps=True)
+    wo = oracle.unpack_panel(small_world.panel, which, all_snps=True)
+    assert np.array_equal(wg, wo)
+    # and they are the truth alleles of the synthetic panel
+    bits = synth.unpack_words(wg, small_world.nSNPs_all)
+    assert np.array_equal(bits, small_world.bits_all[which - 1])
+
+
+@pytest.mark.parametrize("K", [100, 600])
+@pytest.mark.parametrize("all_snps", [False, True])
+def test_make_eMatRead_t(gpu, oracle, small_world, small_reads, K, all_snps):
+    reads = small_reads.all if all_snps else small_reads.common
+    call = synth.make_call(small_world, reads, 11, K=K, all_snps=all_snps, first_iteration=False)
+    if all_snps:
+        call.flags &= ~cabi.F_DISABLE_READ_CATEGORY_USAGE  # look at the real categories as well
+    eg, cg = gpu.make_eMatRead_t(call)
+    eo, co = oracle.make_eMatRead_t(call)
+    print(f"eMatRead K={K} all={all_snps}: max abs diff {np.max(np.abs(eg - eo)):.3e}, categories {np.bincount(co, minlength=4)}")
+    assert np.array_equal(cg, co)
+    assert np.array_equal(eg, eo), "emission table arithmetic is element-wise identical to the reference order -> bit-exact"
+
+
+def test_make_eMatRead_t_dense_and_gather(gpu, oracle, small_world):
+    """reads with > NBMAX SNPs (dense columns), with gaps (gather mode) and spanning > 3 grids"""
+    rng = np.random.default_rng(3)
+    nS = small_world.nSNPs
+    offs, u, bq, wif = [0], [], [], []
+    for g in range(0, small_world.nGrids, 3):
+        base = 32 * g
+        kinds = [np.arange(base + 3, base + 3 + 14), np.array([base + 1, base + 4, base + 30, base + 33]), np.array([base + 31, base + 32]),
+                 np.arange(base + 20, min(base + 20 + 80, nS), 9)]
+        for idx in kinds:
+            idx = idx[idx < nS]
+            if idx.size == 0:
+                continue
+            q = rng.integers(20, 41, size=idx.size) * rng.choice([-1, 1], size=idx.size)
+            u += list(idx)
+            bq += list(q)
+            offs.append(len(u))
+            wif.append(int(idx[idx.size // 2] // 32))
+    order = np.argsort(wif, kind="stable")
+    offs = np.asarray(offs)
+    gather = np.concatenate([np.arange(offs[i], offs[i + 1]) for i in order])
+    new_offs = np.concatenate([[0], np.cumsum(np.diff(offs)[order])])
+    reads = cabi.Reads(offsets=new_offs, u=np.asarray(u)[gather], bq=np.asarray(bq)[gather], wif0=np.asarray(wif)[order])
+    call = synth.make_call(small_world, reads, 12, K=300, first_iteration=False)
+    eg, cg = gpu.make_eMatRead_t(call)
+    eo, co = oracle.make_eMatRead_t(call)
+    assert np.array_equal(cg, co)
+    assert np.array_equal(eg, eo)
+    # Jmax truncation
+    call.Jmax = 2
+    eg, cg = gpu.make_eMatRead_t(call)
+    eo, co = oracle.make_eMatRead_t(call)
+    assert np.array_equal(cg, co) and np.array_equal(eg, eo)
+
+
+@pytest.mark.parametrize("K,T", [(37, 5), (512, 64), (600, 33), (1500, 20), (3000, 12)])
+def test_forward_backward(gpu, oracle, K, T):
+    rng = np.random.default_rng(K + T)
+    e = np.asfortranarray(rng.uniform(0.05, 1.0, size=(K, T)))
+    sig = rng.uniform(0.9, 0.9999, size=T - 1)
+    tm = np.asfortranarray(np.stack([sig, 1 - sig]))
+    ag, bg, cg = gpu.forward_backward(e, tm)
+    ao, bo, co = oracle.forward_backward(e, tm)
+    print(f"fb K={K} T={T}: alpha {_rel(ag, ao):.2e} beta {_rel(bg, bo):.2e} c {_rel(cg, co):.2e}")
+    assert _rel(cg, co) < 1e-12 and _rel(ag, ao) < 1e-11 and _rel(bg, bo) < 1e-11
+
+
+# ---------------------------------------------------------------------------------------------- whole calls
+def _run_both(gpu, oracle, call):
+    call.flags |= cabi.F_RETURN_ALPHA
+    return gpu.gibbs(call), oracle.gibbs(call)
+
+
+@pytest.mark.parametrize("K", [200, 600])
+@pytest.mark.parametrize("iterative", [False, True])
+@pytest.mark.parametrize("its", [(0, 0), (1, 0), (2, 0), (3, 1)])
+def test_gibbs_short(gpu, oracle, small_world, small_reads, K, iterative, its):
+    """init only / one sweep / two sweeps / 3 + 1 sampling sweep, no block Gibbs: bisects the sweep kernel"""
+    call = synth.make_call(small_world, small_reads.common, 21, K=K, first_iteration=iterative, n_burn_in=its[0], n_sample=its[1], block_its=())
+    g, o = _run_both(gpu, oracle, call)
+    _compare(f"short K={K} iterative={iterative} its={its}", g, o)
+
+
+@pytest.mark.parametrize("K", [200, 600])
+def test_gibbs_shard(gpu, oracle, small_world, small_reads, K):
+    call = synth.make_call(small_world, small_reads.common, 22, K=K, first_iteration=False, n_burn_in=3, n_sample=1, block_its=(1,))
+    g, o = _run_both(gpu, oracle, call)
+    _compare(f"shard K={K}", g, o)
+
+
+@pytest.mark.parametrize("K", [200, 600, 1500, 3000])
+@pytest.mark.parametrize("iterative", [False, True])
+def test_gibbs_production_common(gpu, oracle, K, iterative):
+    """the production common-SNP call: 20 + 1 sweeps, block Gibbs at 3/6/9 (functions.R:620-706)"""
+    w = synth.make_world(99 + K, K_full=max(K + 100, 700), nSNPs=2240, region_bp=210_000)
+    sr = synth.make_sample_reads(w, K, coverage=1.0, region_bp=210_000)
+    call = synth.make_call(w, sr.common, 23, K=K, first_iteration=iterative)
+    g, o = _run_both(gpu, oracle, call)
+    _compare(f"production K={K} iterative={iterative}", g, o)
+
+
+@pytest.mark.parametrize("K", [200, 600])
+def test_gibbs_production_all_snps(gpu, oracle, small_world, small_reads, K):
+    """the final all-SNP (rare/common) call (rare_common.R:325-391)"""
+    call = synth.make_call(small_world, small_reads.all, 24, K=K, all_snps=True)
+    g, o = _run_both(gpu, oracle, call)
+    _compare(f"all-SNP K={K}", g, o)
+
+
+def test_gibbs_unsorted_haps_and_sampling_its(gpu, oracle, small_world, small_reads):
+    """which_haps_to_use unsorted (after mspbwt selection, Appendix D.10), 3 sampling sweeps averaged"""
+    call = synth.make_call(small_world, small_reads.common, 25, K=300, sort_haps=False, first_iteration=False, n_burn_in=5, n_sample=3, block_its=(2,))
+    g, o = _run_both(gpu, oracle, call)
+    _compare("unsorted / 3 sampling its", g, o)
+
+
+def test_gibbs_batch_mixed(gpu, oracle, small_world):
+    """a batch mixing shapes and flags: every job must match its own oracle run"""
+    calls = []
+    for s in range(6):
+        sr = synth.make_sample_reads(small_world, 100 + s, coverage=0.5 + 0.25 * s, region_bp=300_000)
+        calls.append(synth.make_call(small_world, sr.common, 200 + s, K=200 if s % 2 else 333, first_iteration=(s % 3 == 0)))
+        calls.append(synth.make_call(small_world, sr.all, 300 + s, K=200, all_snps=True))
+    res = gpu.gibbs_batch(calls)
+    for i, (c, g) in enumerate(zip(calls, res)):
+        _compare(f"batch job {i}", g, oracle.gibbs(c), state=False)
+
+
+def test_underflow_reported(gpu, oracle, small_world, small_reads):
+    """maxDifferenceBetweenReads huge + many reads per grid -> the reference reports underflow instead of failing"""
+    sr = synth.make_sample_reads(small_world, 9, coverage=60.0, region_bp=300_000)
+    call = synth.make_call(small_world, sr.common, 26, K=100, first_iteration=False, maxDifferenceBetweenReads=1e300)
+    g, o = gpu.gibbs(call), oracle.gibbs(call)
+    print("underflow:", g.underflow_problem, o.underflow_problem)
+    assert g.underflow_problem == o.underflow_problem
+
+
+def test_bad_arguments(gpu, small_world, small_reads):
+    from quilt_b200.api import QuiltGpuError
+
+    call = synth.make_call(small_world, small_reads.common, 27, K=50)
+    call.which_haps_to_use = call.which_haps_to_use.copy()
+    call.which_haps_to_use[3] = small_world.panel.K_full + 5
+    with pytest.raises(QuiltGpuError):
+        gpu.gibbs(call)
+    call = synth.make_call(small_world, small_reads.common, 27, K=50)
+    call.reads = cabi.Reads(offsets=call.reads.offsets, u=call.reads.u, bq=call.reads.bq, wif0=call.reads.wif0[::-1].copy())
+    with pytest.raises(QuiltGpuError):
+        gpu.gibbs(call)
