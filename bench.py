@@ -1,0 +1,346 @@
+#!/usr/bin/env python
+"""bench.py — diploid samples/second of the QUILT2 per-sample Gibbs hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W            (N > 1: launched by torchrun, one rank per GPU)
+    python bench.py --impl reference --gpus N --steps K --warmup W
+
+A "step" = every Gibbs call of one batch of synthetic samples at QUILT2 defaults: per sample 8 chains x
+(3 calls on the common SNPs + 1 call on all SNPs) = 32 calls, each 20 burn-in + 1 sampling sweep with shard
+passes after sweeps 3/6/9.  Workload at N = 1 = the configuration the metric is quoted on:
+chr20 2 Mb (+2x0.5 Mb buffer) at 1x, K = 4096 of a 5008-haplotype panel, 32 000 common / 96 000 total SNPs.
+Samples shard across ranks (weak scaling: the per-GPU batch is fixed); the only collectives are the one-time
+NCCL broadcast of the prepared reference and the max-reduction of the timed region.
+
+value      device-timed (CUDA events on the library stream), inputs resident in HBM before the timed region
+e2e        the same batch through quilt_gpu_gibbs_batch with HOST buffers: host preparation, H2D, kernels, D2H
+roofline   the sweep kernel: algorithmic bytes (8 K (5 nHap T + R) per job and sweep) / event time
+cpu_baseline / --impl reference
+           the reference cannot be compiled in this image (needs R / Rcpp / RcppArmadillo), so the CPU arm is the
+           statement-order C++ oracle (kind "port"), one call per thread on all host cores, like the reference's
+           one-forked-worker-per-core model (QUILT/R/quilt.R:690-692)
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: K, K_full, nSNPs (common), all-SNP factor, region bp, coverage, samples per GPU per step
+    "chr20_2Mb_1x_K4096": dict(K=4096, K_full=5008, nSNPs=32000, factor=3, region_bp=3_000_000, coverage=1.0, samples=37),
+    "chr20_2Mb_1x_K512": dict(K=512, K_full=5008, nSNPs=32000, factor=3, region_bp=3_000_000, coverage=1.0, samples=64),
+    "tiny": dict(K=256, K_full=600, nSNPs=3200, factor=3, region_bp=300_000, coverage=1.0, samples=4),
+}
+METRIC = "diploid samples/sec, chr20 2Mb @1x cov, K=4096, 5008-hap panel; 1/2/4/8 GPU"
+WORLD_SEED = 20260118
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic():
+    """dram bytes per sweep launch from the committed ncu capture (profiles/), or None"""
+    try:
+        with open(os.path.join(ROOT, "profiles", "sweep_traffic.json")) as fh:
+            return json.load(fh)
+    except Exception:
+        return None
+
+
+class ClockSampler:
+    QUERY = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(self.index)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_inputs(wl, rank, world_obj, log):
+    from quilt_b200 import schedule, synth
+
+    t0 = time.time()
+    calls = []
+    n_samples = wl["samples"]
+    for s in range(n_samples):
+        seed = 1000 * (rank + 1) + s
+        sr = synth.make_sample_reads(world_obj, seed, coverage=wl["coverage"], region_bp=wl["region_bp"])
+        calls += schedule.sample_calls(world_obj, sr, seed + 7, K=wl["K"])
+    log(f"inputs: {n_samples} samples -> {len(calls)} Gibbs calls in {time.time() - t0:.1f}s")
+    return calls
+
+
+def cpu_arm(wl, world_obj, log, budget_calls_per_thread=1):
+    """Oracle timed on the host cores: each thread runs one common-SNP call and one all-SNP call of its own sample
+    concurrently with all the others; per-sample time = 8 t_iterative + 16 t_normal + 8 t_all (the QUILT2 schedule)."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    import psutil
+
+    from oracle.oracle_py import Oracle
+    from quilt_b200 import synth
+
+    orc = Oracle()
+    cores = os.cpu_count() or 1
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except Exception:
+        pass
+    K = wl["K"]
+    per_thread_gb = (8.0 * K * 20000 + 4.0 * K * 20000 + 3 * 2 * 8.0 * K * 3000) / 1e9 * 1.3 + 0.3
+    mem_cap = max(1, int(psutil.virtual_memory().available / 1e9 / per_thread_gb))
+    threads = max(1, min(cores, mem_cap))
+    jobs = []
+    for t in range(threads):
+        sr = synth.make_sample_reads(world_obj, 777000 + t, coverage=wl["coverage"], region_bp=wl["region_bp"])
+        kind = "iterative" if t % 3 == 0 else "normal"
+        jobs.append((kind, synth.make_call(world_obj, sr.common, 5000 + t, K=K, first_iteration=(kind == "iterative"))))
+        jobs.append(("all", synth.make_call(world_obj, sr.all, 6000 + t, K=K, all_snps=True, sort_haps=False)))
+
+    def run(job):
+        t0 = time.perf_counter()
+        orc.gibbs(job[1])
+        return job[0], time.perf_counter() - t0
+
+    t0 = time.perf_counter()
+    # two phases so that every core is busy with the same kind of call while it is being timed
+    with ThreadPoolExecutor(max_workers=threads) as ex:
+        r1 = list(ex.map(run, [j for j in jobs if j[0] != "all"]))
+        r2 = list(ex.map(run, [j for j in jobs if j[0] == "all"]))
+    wall = time.perf_counter() - t0
+    tt = {"iterative": [], "normal": [], "all": []}
+    for k, v in r1 + r2:
+        tt[k].append(v)
+    t_it = statistics.mean(tt["iterative"]) if tt["iterative"] else statistics.mean(tt["normal"])
+    t_no = statistics.mean(tt["normal"]) if tt["normal"] else t_it
+    t_all = statistics.mean(tt["all"])
+    per_sample = 8 * t_it + 16 * t_no + 8 * t_all
+    value = threads / per_sample
+    log(f"cpu arm: {threads} threads ({cores} cores), t_iterative {t_it:.2f}s t_normal {t_no:.2f}s t_all {t_all:.2f}s -> {value:.4f} samples/s (wall {wall:.1f}s)")
+    return {
+        "value": value,
+        "unit": "samples/s",
+        "cores": threads,
+        "kind": "port",
+        "sample": f"{threads} concurrent threads x (1 common-SNP call + 1 all-SNP call) of the same workload; per-sample time = 8*t_iterative + 16*t_normal + 8*t_all",
+        "seconds_per_call": {"iterative": t_it, "normal": t_no, "all_snps": t_all},
+        "host_cores": cores,
+    }, wall
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="chr20_2Mb_1x_K4096", choices=sorted(WORKLOADS))
+    ap.add_argument("--samples", type=int, default=0, help="samples per GPU per step (default: workload's)")
+    ap.add_argument("--e2e-steps", type=int, default=1)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    wl = dict(WORKLOADS[args.workload])
+    if args.samples > 0:
+        wl["samples"] = args.samples
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    def log(msg):
+        print(f"[bench r{rank}] {msg}", file=sys.stderr, flush=True)
+
+    from quilt_b200 import synth
+
+    config = {
+        "workload": args.workload,
+        "K": wl["K"], "K_full": wl["K_full"], "nSNPs_common": wl["nSNPs"], "nSNPs_all": wl["nSNPs"] * wl["factor"],
+        "nGrids": (wl["nSNPs"] + 31) // 32, "nGrids_all": (wl["nSNPs"] * wl["factor"] + 31) // 32,
+        "coverage": wl["coverage"], "samples_per_gpu_per_step": wl["samples"], "calls_per_sample": 32,
+        "schedule": "8 chains x (3 common-SNP calls + 1 all-SNP call), 20+1 sweeps, shard passes at sweeps 3/6/9",
+        "parallelism": f"samples sharded over {args.gpus} GPU(s), no data-path collective",
+        "l2": "per-wave working set (>= 29 GB of alpha/beta/eMatGrid columns) is far larger than the 126 MB L2",
+    }
+
+    # ------------------------------------------------------------------------------------------ reference arm
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        w = synth.make_world(WORLD_SEED, K_full=wl["K_full"], nSNPs=wl["nSNPs"], region_bp=wl["region_bp"], all_snps_factor=wl["factor"])
+        vals, walls = [], []
+        cb = None
+        # each "step" is the bounded sample; warm-up steps would only repeat ~25 s of CPU work, one is enough for page-in
+        for i in range(max(1, min(args.steps, 2))):
+            cb, wall = cpu_arm(wl, w, log)
+            vals.append(cb["value"])
+            walls.append(wall)
+        v = statistics.mean(vals)
+        cb["value"] = v
+        line = {
+            "impl": "reference", "metric": METRIC, "value": v, "unit": "samples/s", "n_gpus": args.gpus, "steps": len(vals), "warmup": 0,
+            "ms_per_step": 1e3 * statistics.mean(walls), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": config, "cpu_baseline": cb,
+            "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "note": "the reference needs R/Rcpp/RcppArmadillo (absent): CPU arm = statement-order C++ oracle, one call per thread on all host cores",
+        }
+        print(json.dumps(line), flush=True)
+        return 0
+
+    # ------------------------------------------------------------------------------------------ B200 arm
+    import torch
+
+    from quilt_b200 import api, dist
+
+    rank, local_rank, world, dev = dist.init()
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device (no CPU fallback)")
+    lib = api.GpuLib()
+    lib.set_device(local_rank)
+    t0 = time.time()
+    w = None
+    if rank == 0:
+        w = synth.make_world(WORLD_SEED, K_full=wl["K_full"], nSNPs=wl["nSNPs"], region_bp=wl["region_bp"], all_snps_factor=wl["factor"])
+    w = dist.broadcast_world(w, src=0)
+    log(f"world ready in {time.time() - t0:.1f}s")
+    calls = build_inputs(wl, rank, w, log)
+    n_samples = wl["samples"]
+
+    # ---- staged batch: inputs resident in HBM
+    t0 = time.time()
+    batch = api.Batch(lib, calls)
+    nbytes = batch.bytes()
+    log(f"staged {len(calls)} calls: h2d {nbytes['h2d_bytes'] / 1e9:.2f} GB in {time.time() - t0:.1f}s")
+    for i in range(args.warmup):
+        batch.run()
+        batch.sync()
+        log(f"warmup {i}: {batch.timing()['total_ms']:.1f} ms")
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    dist.barrier()
+    torch.cuda.synchronize()
+    n0 = lib.kernel_launches()
+    wall0 = time.perf_counter()
+    dev_ms, sweep_ms, sweep_launches = 0.0, 0.0, 0
+    for i in range(args.steps):
+        batch.run()
+        batch.sync()
+        tm = batch.timing()
+        dev_ms += tm["total_ms"]
+        sweep_ms += tm["sweep_ms"]
+        sweep_launches += tm["n_sweep_launches"]
+    torch.cuda.synchronize()
+    dist.barrier()
+    wall_ms = 1e3 * (time.perf_counter() - wall0)
+    launches = lib.kernel_launches() - n0
+    clocks = sampler.stop()
+    ms_per_step_local = dev_ms / args.steps
+    ms_per_step = dist.max_over_ranks(ms_per_step_local)
+    wall_per_step = dist.max_over_ranks(wall_ms / args.steps)
+    total_samples = n_samples * world
+    value = total_samples / (ms_per_step / 1e3)
+    log(f"timed: {ms_per_step_local:.1f} ms/step device, {wall_ms / args.steps:.1f} ms/step wall, sweep share {sweep_ms / dev_ms:.3f}")
+
+    # ---- roofline of the dominant kernel (rank 0's launches)
+    peak, peak_src = measured_peak()
+    alg_bytes_per_run = nbytes["sweep_algorithmic_bytes"]
+    launches_per_run = sweep_launches / args.steps
+    avg_launch_s = (sweep_ms / 1e3) / max(sweep_launches, 1)
+    achieved = (alg_bytes_per_run / max(launches_per_run, 1)) / avg_launch_s / 1e9
+    tr = ncu_traffic()
+    roofline = {
+        "bound": "hbm", "kernel": "k_sweep", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+        "traffic": (tr or {}).get("dram_bytes_per_launch"),
+        "peak_source": peak_src,
+        "algorithmic_bytes_per_launch": alg_bytes_per_run / max(launches_per_run, 1),
+        "avg_launch_ms": 1e3 * avg_launch_s, "launches_per_step": launches_per_run, "share_of_step": sweep_ms / dev_ms,
+        "note": "algorithmic bytes follow SURVEY.md §8(d) (dense fp64 eMatRead columns counted); the kernel moves fewer bytes "
+                "because emission columns are rebuilt from 2^nb-entry tables + bit-packed alleles, see DESIGN.md",
+    }
+    batch.free()
+
+    # ---- e2e: host buffers in, host buffers out, every step
+    e2e_s = []
+    for i in range(max(1, args.e2e_steps)):
+        dist.barrier()
+        t0 = time.perf_counter()
+        res = lib.gibbs_batch(calls)
+        e2e_s.append(time.perf_counter() - t0)
+    e2e_step = dist.max_over_ranks(statistics.mean(e2e_s))
+    n_under = sum(int(r.underflow_problem) for r in res)
+    e2e = {"value": total_samples / e2e_step, "unit": "samples/s", "h2d_bytes_per_step": nbytes["h2d_bytes"], "d2h_bytes_per_step": nbytes["d2h_bytes"],
+           "ms_per_step": 1e3 * e2e_step, "steps": len(e2e_s), "underflow_calls": n_under}
+    log(f"e2e: {1e3 * e2e_step:.1f} ms/step")
+
+    cb = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cb, _ = cpu_arm(wl, w, log)
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": config, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cb,
+            "wall_ms_per_step": wall_per_step,
+        }
+        print(json.dumps(line), flush=True)
+    dist.barrier()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -165,6 +165,9 @@ int quilt_gpu_batch_free(QuiltGpuBatch* batch);
 /* device time of the last quilt_gpu_batch_run in ms, measured with CUDA events on the library stream;
  * sweep_ms = time inside the dominant (sweep) kernel launches, n_sweep_launches their count */
 int quilt_gpu_batch_timing(QuiltGpuBatch* batch, double* total_ms, double* sweep_ms, int32_t* n_sweep_launches);
+/* bytes moved by quilt_gpu_batch_stage (host -> device) and quilt_gpu_batch_fetch (device -> host), and the ALGORITHMIC bytes of
+ * the sweep kernel launches of one run: sum over launches and jobs of 8 * K * (5 * nHap * nGrids + nReads) */
+int quilt_gpu_batch_bytes(QuiltGpuBatch* batch, int64_t* h2d_bytes, int64_t* d2h_bytes, double* sweep_algorithmic_bytes);
 
 /* component entry points (parity tests of the individual reference functions) */
 int quilt_gpu_make_eMatRead_t(const QuiltGibbsArgs* args, double* eMatRead_t /*[K x nReads]*/,

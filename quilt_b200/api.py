@@ -52,6 +52,8 @@ class GpuLib(cabi._LibAPI):
         L.quilt_gpu_batch_fetch.restype = C.c_int
         L.quilt_gpu_batch_timing.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int32)]
         L.quilt_gpu_batch_timing.restype = C.c_int
+        L.quilt_gpu_batch_bytes.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_double)]
+        L.quilt_gpu_batch_bytes.restype = C.c_int
         L.quilt_gpu_device_count.restype = C.c_int
         L.quilt_gpu_set_device.argtypes = [C.c_int32]
         L.quilt_gpu_set_device.restype = C.c_int
@@ -114,6 +116,11 @@ class Batch:
         t, s, n = C.c_double(), C.c_double(), C.c_int32()
         self.lib._check(self.lib.lib.quilt_gpu_batch_timing(self._h, C.byref(t), C.byref(s), C.byref(n)), "quilt_gpu_batch_timing")
         return {"total_ms": t.value, "sweep_ms": s.value, "n_sweep_launches": n.value}
+
+    def bytes(self):
+        a, b, c = C.c_int64(), C.c_int64(), C.c_double()
+        self.lib._check(self.lib.lib.quilt_gpu_batch_bytes(self._h, C.byref(a), C.byref(b), C.byref(c)), "quilt_gpu_batch_bytes")
+        return {"h2d_bytes": a.value, "d2h_bytes": b.value, "sweep_algorithmic_bytes": c.value}
 
     def fetch(self) -> List[GibbsResult]:
         n = len(self.calls)

@@ -670,6 +670,8 @@ template <int NT, int EPT>
 int run_wave_t(QuiltGpuBatch* B, Bucket& bk, int n, const JobDev* dj, bool timed) {
     const BatchParams& P = bk.P;
     const SweepSmemLayout L = sweep_smem_layout(P.Kp, P.NH, NT);
+    // (buckets of different K share a template instance: re-arm the opt-in shared-memory size for this one)
+    CK(cudaFuncSetAttribute(k_sweep<NT, EPT, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
     k_copy_H<<<dim3((bk.R_max + 255) / 256, n), 256, 0, g_stream>>>(dj);
     LAUNCHED();
     int rc = run_prep(B, bk, n, dj);
@@ -981,6 +983,21 @@ int quilt_gpu_batch_timing(QuiltGpuBatch* B, double* total_ms, double* sweep_ms,
     if (total_ms) *total_ms = B->total_ms;
     if (sweep_ms) *sweep_ms = B->sweep_ms;
     if (n_sweep_launches) *n_sweep_launches = B->n_sweep_launches;
+    return QUILT_OK;
+}
+
+int quilt_gpu_batch_bytes(QuiltGpuBatch* B, int64_t* h2d, int64_t* d2h, double* sweep_alg) {
+    if (!B) return set_err(QUILT_ERR_BAD_ARG, "null batch");
+    if (h2d) *h2d = (int64_t)B->in_bytes;
+    if (d2h) *d2h = (int64_t)B->out_bytes;
+    if (sweep_alg) {
+        double s = 0;
+        for (const HostJob& j : B->jobs) {
+            const int NH = (j.a.flags & QUILT_F_SAMPLE_IS_DIPLOID) ? 2 : 3;
+            s += (double)j.n_its * 8.0 * j.a.K * (5.0 * NH * j.a.nGrids + j.R);
+        }
+        *sweep_alg = s;
+    }
     return QUILT_OK;
 }
 
