@@ -22,12 +22,12 @@
 
 namespace qb {
 
-constexpr int SW_MAXR = 64;     // reads of one grid staged in shared memory (more: read from global)
-constexpr int SW_MAXTAB = 256;  // table entries of one grid staged in shared memory
+constexpr int SW_MAXR = 48;     // reads of one grid staged in shared memory (more: read from global)
+constexpr int SW_MAXTAB = 384;  // table entries of one grid staged in shared memory
 constexpr int SW_VMAX = 4;
 
 struct SweepSmemLayout {
-    int off_bar, off_red, off_cnt, off_small[2], off_W, off_eG, total;
+    int off_bar, off_red, off_cnt, off_small[2], off_pat, off_W, off_eG, total;
     int small_desc, small_tab, small_U, small_H;
 };
 __host__ __device__ inline SweepSmemLayout sweep_smem_layout(int Kp, int NH, int NT) {
@@ -49,6 +49,8 @@ __host__ __device__ inline SweepSmemLayout sweep_smem_layout(int Kp, int NH, int
     o += small_total;
     L.off_small[1] = o;
     o += small_total;
+    L.off_pat = o;
+    o += Kp * 2;
     L.off_W = o;
     o += 4 * Kp * 4;
     L.off_eG = o;
@@ -59,10 +61,13 @@ __host__ __device__ inline SweepSmemLayout sweep_smem_layout(int Kp, int NH, int
 
 template <int NT>
 struct BlockSumV {
-    static constexpr int NW = NT / 32;
-    double* scratch;  // [2][SW_VMAX][NW]
+    static constexpr int NW = NT / 32;  // power of two (4, 8, 16)
+    double* scratch;                    // [2][SW_VMAX][NW]
     int phase;
     __device__ __forceinline__ BlockSumV(double* s) : scratch(s), phase(0) {}
+    // Every thread returns the same, bit-identical totals: xor butterfly inside each warp, one shared-memory slot per
+    // warp, then every warp butterflies the NW partials again (same operation order in all warps).  Two alternating
+    // scratch buffers make one __syncthreads per call enough.
     template <int V>
     __device__ __forceinline__ void run(double (&v)[V]) {
 #pragma unroll
@@ -81,9 +86,9 @@ struct BlockSumV {
         __syncthreads();
 #pragma unroll
         for (int i = 0; i < V; i++) {
-            double s = buf[i * NW];
+            double s = buf[i * NW + (lane & (NW - 1))];
 #pragma unroll
-            for (int w = 1; w < NW; w++) s += buf[i * NW + w];
+            for (int d = NW / 2; d >= 1; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
             v[i] = s;
         }
     }
@@ -102,6 +107,29 @@ __device__ __forceinline__ int classify_H(const BatchParams& P, double x0, doubl
         }
     }
     return (local_min < P.class_sum_cutoff) ? which + 1 : 0;
+}
+
+// three label-indexed doubles kept in registers (dynamic indexing of a local array would go to local memory)
+struct P3 {
+    double a, b, c;
+    __device__ __forceinline__ double get(int i) const { return i == 0 ? a : (i == 1 ? b : c); }
+    __device__ __forceinline__ void set(int i, double v) {
+        if (i == 0)
+            a = v;
+        else if (i == 1)
+            b = v;
+        else
+            c = v;
+    }
+    __device__ __forceinline__ double prod() const { return (a * b) * c; }
+};
+
+// a / e from e and inv = RN(1 / e): q = RN(a * inv) is within 2 ulp, the fma residual r = a - q e is exact and
+// RN(q + r inv) is the correctly rounded quotient (Markstein); 10x cheaper than the IEEE division sequence.
+__device__ __forceinline__ double div_by(double a, double e, double inv) {
+    const double q = a * inv;
+    const double r = fma(-q, e, a);
+    return fma(r, inv, q);
 }
 
 __device__ __forceinline__ uint32_t read_pattern_smem(const ReadDesc& d, const uint32_t* Wr, int Kp, int g, int k) {
@@ -134,6 +162,7 @@ __global__ void __launch_bounds__(NT, (NT <= 128 ? 5 : (NT <= 256 ? 2 : 1))) k_s
     BlockSumV<NT> bsum(reinterpret_cast<double*>(smem + L.off_red));
     int* cnt = reinterpret_cast<int*>(smem + L.off_cnt);
     uint32_t* Wr = reinterpret_cast<uint32_t*>(smem + L.off_W);
+    uint16_t* spat = reinterpret_cast<uint16_t*>(smem + L.off_pat);  // [Kp] allele patterns of reads that leave the fast path
     double* eGs = reinterpret_cast<double*>(smem + L.off_eG);  // [2][NH][Kp]
     const bool iterative = (P.flags & QUILT_F_GIBBS_INITIALIZE_ITERATIVELY) != 0;
     const bool record = (P.flags & QUILT_F_RECORD_READ_SET) != 0;
@@ -148,7 +177,7 @@ __global__ void __launch_bounds__(NT, (NT <= 128 ? 5 : (NT <= 256 ? 2 : 1))) k_s
     }
     if (tid < 16) cnt[tid] = 0;
     __syncthreads();
-    uint32_t n_use[2] = {0, 0};  // completed uses of each stage barrier -> wait parity
+    uint32_t n_use0 = 0, n_use1 = 0;  // completed uses of each stage barrier -> wait parity
 
     // ---- one package = everything grid g needs: eMatGrid columns, the allele words of grid g+1 (ring of 4:
     //      grid g uses words g-1 .. g+1 while package g+1 is already filling word g+2), and the read
@@ -192,12 +221,17 @@ __global__ void __launch_bounds__(NT, (NT <= 128 ? 5 : (NT <= 256 ? 2 : 1))) k_s
     auto wait_pkg = [&](int g) {
         const int s = g & 1;
         cp_async_wait_all();
-        mbar_wait(&bar[s], n_use[s] & 1);
-        n_use[s]++;
+        if (s == 0) {
+            mbar_wait(&bar[0], n_use0 & 1);
+            n_use0++;
+        } else {
+            mbar_wait(&bar[1], n_use1 & 1);
+            n_use1++;
+        }
         __syncthreads();
     };
 
-    double ap[NH][EPT];  // alpha of the previous grid (normalised)
+    double am[NH][EPT];  // alpha of the previous grid (normalised) on entry to a grid, alphaHat_m / alpha of this grid afterwards
     double cfin[NH];     // c of the last grid processed
 #pragma unroll
     for (int h = 0; h < NH; h++) cfin[h] = 1;
@@ -215,7 +249,7 @@ __global__ void __launch_bounds__(NT, (NT <= 128 ? 5 : (NT <= 256 ? 2 : 1))) k_s
         double c_old[NH];
 #pragma unroll
         for (int h = 0; h < NH; h++) c_old[h] = ld_cg(J.c + h * T + g);
-        double am[NH][EPT], ab[NH][EPT];
+        double ab[NH][EPT];
         // beta of this grid goes straight into the ab registers (consumed after the forward step)
         if (has) {
 #pragma unroll
@@ -245,7 +279,7 @@ __global__ void __launch_bounds__(NT, (NT <= 128 ? 5 : (NT <= 256 ? 2 : 1))) k_s
             // rcpp_alpha_forward_one_QUILT_faster
             double sp[NH];
 #pragma unroll
-            for (int h = 0; h < NH; h++) sp[h] = Col<NT, EPT>::sum(ap[h]);
+            for (int h = 0; h < NH; h++) sp[h] = Col<NT, EPT>::sum(am[h]);
             bsum.run(sp);
             const double x = J.tm[2 * (g - 1)], t1 = J.tm[2 * (g - 1) + 1];
             double sv[NH];
@@ -258,7 +292,7 @@ __global__ void __launch_bounds__(NT, (NT <= 128 ? 5 : (NT <= 256 ? 2 : 1))) k_s
                     const int k = tid + i * NT;
                     double v = 0.0;
                     if (k < K) {
-                        v = x * ap[h][i] + jump;
+                        v = x * am[h][i] + jump;
                         if (has) v = eg[h * Kp + k] * v;
                     }
                     am[h][i] = v;
@@ -285,11 +319,16 @@ __global__ void __launch_bounds__(NT, (NT <= 128 ? 5 : (NT <= 256 ? 2 : 1))) k_s
             const double* Up = staged ? reinterpret_cast<const double*>(sm + L.small_U) : U + r0;
             const int32_t* Hp = staged ? reinterpret_cast<const int32_t*>(sm + L.small_H) : J.H + r0;
             const uint32_t tab_base = (uint32_t)J.ts[g];
+            const uint32_t* wg = Wr + (g & 3) * Kp;  // this grid's allele words: most reads lie inside one 32-SNP word
             bool inited = false;
-            double pC[3] = {1, 1, 1};
+            P3 pC = {1, 1, 1};
+            const P3 prior = {P.prior[0], P.prior[1], P.prior[2]};
             for (int ir = 0; ir < n_g; ir++) {
-                const ReadDesc d = descp[ir];
-                if (NH == 2 && d.cat == 1) continue;  // diploid: uninformative reads are never visited (gibbs-nipt.cpp:815)
+                // descriptor as two 16-byte words (no local-memory copy): off | cat,mode,nb,g0rel | b0,sel0..2 | ...
+                const uint4 dq = *reinterpret_cast<const uint4*>(descp + ir);
+                const int cat = dq.y & 0xff, mode = (dq.y >> 8) & 0xff, nb = (dq.y >> 16) & 0xff;
+                if (NH == 2 && cat == 1) continue;  // diploid: uninformative reads are never visited (gibbs-nipt.cpp:815)
+                const int g0rel = (int)(int8_t)(dq.y >> 24), b0 = dq.z & 0xff;
                 const int r = r0 + ir;
                 // which of the three regimes (gibbs-nipt.cpp:816-834)
                 bool normal = true, init_mode = false, pass = false;
@@ -315,133 +354,178 @@ __global__ void __launch_bounds__(NT, (NT <= 128 ? 5 : (NT <= 256 ? 2 : 1))) k_s
                         sv[h] = Col<NT, EPT>::sum(ab[h]);
                     }
                     bsum.run(sv);
-#pragma unroll
-                    for (int h = 0; h < NH; h++) pC[h] = sv[h];
+                    pC.a = sv[0];
+                    pC.b = sv[1];
+                    if (NH == 3) pC.c = sv[NH - 1];
                     inited = true;
                 }
                 int hC = 0, hA1 = 1, hA2 = 2;
-                double pA1[3] = {pC[0], pC[1], pC[2]}, pA2[3] = {pC[0], pC[1], pC[2]};
-                const TabEnt* tab = tabp + (d.off - tab_base);
-                const double* dcol = J.dense + (size_t)d.off * Kp;
+                P3 pA1 = pC, pA2 = pC;
+                const TabEnt* tab = tabp + (dq.x - tab_base);
+                const double* dcol = J.dense + (size_t)dq.x * Kp;
+                // allele pattern of every haplotype over the read's SNPs (index into the read's emission table).
+                // fast path: all SNPs inside this grid's word -> (word >> b0) & mask inline; otherwise the patterns
+                // are materialised once into spat[] (each thread writes and later reads only its own elements)
+                const bool fast = (mode == MODE_RUN) && g0rel == 0 && (b0 + nb <= 32);
+                const uint32_t mask = (1u << nb) - 1u;
+                if (!fast && !pass) {
+                    if (mode == MODE_RUN) {
+                        const uint32_t* wlo = Wr + ((g + g0rel) & 3) * Kp;
+                        const uint32_t* whi = Wr + ((g + g0rel + 1) & 3) * Kp;
+                        const bool cross = b0 + nb > 32;
+#pragma unroll
+                        for (int i = 0; i < EPT; i++) {
+                            const int k = tid + i * NT;
+                            if (k < K) {
+                                const uint32_t lo = wlo[k];
+                                const uint32_t hi = cross ? whi[k] : 0u;
+                                spat[k] = (uint16_t)(__funnelshift_r(lo, hi, b0) & mask);
+                            }
+                        }
+                    } else if (mode == MODE_GATHER) {
+                        const uint8_t* sel = reinterpret_cast<const uint8_t*>(descp + ir) + 9;
+#pragma unroll
+                        for (int i = 0; i < EPT; i++) {
+                            const int k = tid + i * NT;
+                            if (k < K) {
+                                uint32_t pt = 0;
+                                for (int j = 0; j < nb; j++) {
+                                    const int sj = sel[j];
+                                    pt |= ((Wr[((g + (sj >> 5) - 1) & 3) * Kp + k] >> (sj & 31)) & 1u) << j;
+                                }
+                                spat[k] = (uint16_t)pt;
+                            }
+                        }
+                    }
+                }
+#define QB_PAT(k) (fast ? ((wg[k] >> b0) & mask) : (uint32_t)spat[k])
                 if (!pass) {
                     if (normal) {
                         hC = Hp[ir] - 1;
-                        if (hC == 0) {
-                            hA1 = 1;
-                            hA2 = 2;
-                        } else if (hC == 1) {
-                            hA1 = 0;
-                            hA2 = 2;
-                        } else {
-                            hA1 = 0;
-                            hA2 = 1;
-                        }
+                        hA1 = (hC == 0) ? 1 : 0;
+                        hA2 = (hC == 2) ? 1 : 2;
                     }
                     // K-long sums: normal  -> sum ab_C / e, sum ab_A1 * e, (sum ab_A2 * e)
                     //              init    -> sum ab_0 * e, sum ab_1 * e, (sum ab_2 * e)
                     double sv[NH];
 #pragma unroll
                     for (int h = 0; h < NH; h++) sv[h] = 0;
-#pragma unroll
-                    for (int i = 0; i < EPT; i++) {
-                        const int k = tid + i * NT;
-                        if (k < K) {
-                            double E, invE;
-                            if (d.mode == MODE_DENSE) {
-                                E = dcol[k];
-                                invE = 0;  // unused: dense columns divide
-                            } else {
-                                const double2 te = *reinterpret_cast<const double2*>(tab + read_pattern_smem(d, Wr, Kp, g, k));
-                                E = te.x;
-                                invE = te.y;
-                            }
-                            // operands picked by label (uniform across the CTA)
-                            double aC, aA1, aA2 = 0;
-                            if (NH == 2) {
-                                aC = hC == 0 ? ab[0][i] : ab[1][i];
-                                aA1 = hA1 == 0 ? ab[0][i] : ab[1][i];
-                            } else {
-                                aC = hC == 0 ? ab[0][i] : (hC == 1 ? ab[1][i] : ab[NH - 1][i]);
-                                aA1 = hA1 == 0 ? ab[0][i] : ab[1][i];
-                                aA2 = hA2 == 1 ? ab[1][i] : ab[NH - 1][i];
-                            }
-                            if (normal) {
-                                sv[0] += (d.mode == MODE_DENSE) ? aC / E : aC * invE;
-                            } else {
-                                sv[0] += aC * E;
-                            }
-                            sv[1] += aA1 * E;
-                            if (NH == 3) sv[NH - 1] += aA2 * E;
-                        }
+#define QB_SUM_LOOP(XC, XA1, XA2, CMUL)                                                                  \
+    _Pragma("unroll") for (int i = 0; i < EPT; i++) {                                                     \
+        const int k = tid + i * NT;                                                                       \
+        if (k < K) {                                                                                      \
+            if (mode == MODE_DENSE) {                                                                     \
+                const double E = dcol[k];                                                                 \
+                sv[0] += CMUL ? XC[i] * E : XC[i] / E;                                                    \
+                sv[1] += XA1[i] * E;                                                                      \
+                if (NH == 3) sv[NH - 1] += XA2[i] * E;                                                    \
+            } else {                                                                                      \
+                const double2 te = *reinterpret_cast<const double2*>(tab + QB_PAT(k));                   \
+                sv[0] = fma(XC[i], CMUL ? te.x : te.y, sv[0]);                                            \
+                sv[1] = fma(XA1[i], te.x, sv[1]);                                                         \
+                if (NH == 3) sv[NH - 1] = fma(XA2[i], te.x, sv[NH - 1]);                                  \
+            }                                                                                             \
+        }                                                                                                 \
+    }
+                    if (!normal) {
+                        QB_SUM_LOOP(ab[0], ab[1], ab[NH - 1], true)
+                    } else if (hC == 0) {
+                        QB_SUM_LOOP(ab[0], ab[1], ab[NH - 1], false)
+                    } else if (hC == 1) {
+                        QB_SUM_LOOP(ab[1], ab[0], ab[NH - 1], false)
+                    } else {
+                        QB_SUM_LOOP(ab[NH - 1], ab[0], ab[1], false)
                     }
+#undef QB_SUM_LOOP
                     bsum.run(sv);
                     if (normal) {
-                        pA1[hC] = sv[0];
-                        pA1[hA1] = sv[1];
-                        if (NH == 3) pA2[hA2] = sv[NH - 1];
-                        pA2[hA1] = pC[hA1];
-                        pA2[hC] = pA1[hC];
+                        pA1.set(hC, sv[0]);
+                        pA1.set(hA1, sv[1]);
+                        if (NH == 3) pA2.set(hA2, sv[NH - 1]);
+                        pA2.set(hC, sv[0]);
                     } else {
-                        pC[0] = sv[0];
-                        pA1[1] = sv[1];
-                        if (NH == 3) pA2[2] = sv[NH - 1];
+                        pC.a = sv[0];
+                        pA1.b = sv[1];
+                        if (NH == 3) pA2.c = sv[NH - 1];
                     }
                 }
-                const double prod_pC = (pC[0] * pC[1] * pC[2]) * P.prior[hC];
-                const double prod_pA1 = (pA1[0] * pA1[1] * pA1[2]) * P.prior[hA1];
-                const double prod_pA2 = (pA2[0] * pA2[1] * pA2[2]) * P.prior[hA2];
+                const double prod_pC = pC.prod() * prior.get(hC);
+                const double prod_pA1 = pA1.prod() * prior.get(hA1);
+                const double prod_pA2 = pA2.prod() * prior.get(hA2);
                 const double denom = prod_pC + prod_pA1 + prod_pA2;
                 const double norm_pC = prod_pC / denom, norm_pA1 = prod_pA1 / denom, norm_pA2 = prod_pA2 / denom;
                 const double chance = Up[ir];
-                double cum[3] = {0, 0, 0};
-                cum[hC] = norm_pC;
-                cum[hA1] = norm_pA1;
-                cum[hA2] = norm_pA2;
-                const double x0 = cum[0], x1 = cum[1], x2 = cum[2];
-                cum[1] += cum[0];
-                cum[2] += cum[1];
+                P3 cum = {0, 0, 0};
+                cum.set(hC, norm_pC);
+                cum.set(hA1, norm_pA1);
+                cum.set(hA2, norm_pA2);
+                const double x0 = cum.a, x1 = cum.b, x2 = cum.c;
+                cum.b += cum.a;
+                cum.c += cum.b;
                 int hN = 0;
-                if (chance < cum[2]) hN = 2;
-                if (chance < cum[1]) hN = 1;
-                if (chance < cum[0]) hN = 0;
+                if (chance < cum.c) hN = 2;
+                if (chance < cum.b) hN = 1;
+                if (chance < cum.a) hN = 0;
                 if (((hN != hC) || init_mode) && !pass) {
                     changed = true;
                     if (tid == 0) J.H[r] = hN + 1;
-                    const bool upd_eC = normal && (hC < 2 || NH == 3);
-                    const bool upd_eN = (hN < 2 || NH == 3);
-#pragma unroll
-                    for (int i = 0; i < EPT; i++) {
-                        const int k = tid + i * NT;
-                        if (k < K) {
-                            const double E = (d.mode == MODE_DENSE) ? dcol[k] : tab[read_pattern_smem(d, Wr, Kp, g, k)].E;
-#pragma unroll
-                            for (int h = 0; h < NH; h++) {
-                                if (normal && h == hC) {
-                                    am[h][i] /= E;
-                                    ab[h][i] /= E;
-                                }
-                                if (h == hN) {
-                                    am[h][i] *= E;
-                                    ab[h][i] *= E;
-                                }
-                            }
-                            if (upd_eC) eg[hC * Kp + k] /= E;
-                            if (upd_eN) eg[hN * Kp + k] *= E;
-                        }
-                    }
+                    // alphaHat_m / ab_m / eMatGrid of the old label are divided by the read's column, those of the new
+                    // label multiplied (gibbs-nipt.cpp:1092-1110).  Divisions: q = a * (1/e) corrected by one fma
+                    // residual step = the correctly rounded a / e (DESIGN.md "arithmetic"); dense columns divide.
+#define QB_UPD_LOOP(HC, HN, DODIV)                                                                        \
+    _Pragma("unroll") for (int i = 0; i < EPT; i++) {                                                     \
+        const int k = tid + i * NT;                                                                       \
+        if (k < K) {                                                                                      \
+            double E, invE;                                                                               \
+            if (mode == MODE_DENSE) {                                                                     \
+                E = dcol[k];                                                                              \
+                invE = 1 / E;                                                                             \
+            } else {                                                                                      \
+                const double2 te = *reinterpret_cast<const double2*>(tab + QB_PAT(k));                   \
+                E = te.x;                                                                                 \
+                invE = te.y;                                                                              \
+            }                                                                                             \
+            if (DODIV) {                                                                                  \
+                am[HC][i] = div_by(am[HC][i], E, invE);                                                   \
+                ab[HC][i] = div_by(ab[HC][i], E, invE);                                                   \
+                if (HC < 2 || NH == 3) eg[HC * Kp + k] = div_by(eg[HC * Kp + k], E, invE);                \
+            }                                                                                             \
+            am[HN][i] *= E;                                                                               \
+            ab[HN][i] *= E;                                                                               \
+            if (HN < 2 || NH == 3) eg[HN * Kp + k] *= E;                                                  \
+        }                                                                                                 \
+    }
                     if (normal) {
+                        if (hC == 0 && hN == 1) {
+                            QB_UPD_LOOP(0, 1, true)
+                        } else if (hC == 1 && hN == 0) {
+                            QB_UPD_LOOP(1, 0, true)
+                        } else if (NH == 3) {
+                            if (hC == 0 && hN == 2) {
+                                QB_UPD_LOOP(0, NH - 1, true)
+                            } else if (hC == 1 && hN == 2) {
+                                QB_UPD_LOOP(1, NH - 1, true)
+                            } else if (hC == 2 && hN == 0) {
+                                QB_UPD_LOOP(NH - 1, 0, true)
+                            } else if (hC == 2 && hN == 1) {
+                                QB_UPD_LOOP(NH - 1, 1, true)
+                            }
+                        }
                         const bool useA1 = (hN == hA1);
-#pragma unroll
-                        for (int j = 0; j < 3; j++) pC[j] = useA1 ? pA1[j] : pA2[j];
+                        pC = useA1 ? pA1 : pA2;
                     } else {
-                        if (hN == 1) {
-#pragma unroll
-                            for (int j = 0; j < 3; j++) pC[j] = pA1[j];
-                        } else if (hN == 2) {
-#pragma unroll
-                            for (int j = 0; j < 3; j++) pC[j] = pA2[j];
+                        if (hN == 0) {
+                            QB_UPD_LOOP(0, 0, false)
+                        } else if (hN == 1) {
+                            QB_UPD_LOOP(0, 1, false)
+                            pC = pA1;
+                        } else if (NH == 3) {
+                            QB_UPD_LOOP(0, NH - 1, false)
+                            pC = pA2;
                         }
                     }
+#undef QB_UPD_LOOP
+#undef QB_PAT
                 }
                 if (record && tid == 0) {
                     J.xprob[3 * (size_t)r + 0] = x0;
@@ -476,8 +560,6 @@ __global__ void __launch_bounds__(NT, (NT <= 128 ? 5 : (NT <= 256 ? 2 : 1))) k_s
             }
             if (tid == 0) J.c[h * T + g] = cnew[h];
             cfin[h] = cnew[h];
-#pragma unroll
-            for (int i = 0; i < EPT; i++) ap[h][i] = am[h][i];
         }
     }
 
@@ -512,8 +594,13 @@ __global__ void __launch_bounds__(NT, (NT <= 128 ? 5 : (NT <= 256 ? 2 : 1))) k_s
         if (T >= 2) issue_b(T - 2);
         for (int g = T - 2; g >= 0; g--) {
             const int s = g & 1;
-            mbar_wait(&bar[s], n_use[s] & 1);
-            n_use[s]++;
+            if (s == 0) {
+                mbar_wait(&bar[0], n_use0 & 1);
+                n_use0++;
+            } else {
+                mbar_wait(&bar[1], n_use1 & 1);
+                n_use1++;
+            }
             __syncthreads();  // everyone is done with the other stage (step g + 1) before it is refilled
             if (g >= 1) issue_b(g - 1);
             const bool has1 = rs[g + 2] > rs[g + 1];
