@@ -14,6 +14,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <map>
@@ -364,6 +365,7 @@ int prepare_job(HostJob& j) {
             d.nb = (uint8_t)cnt;
             d.off = (uint32_t)n_tab;
             n_tab += 1 << cnt;
+            d.tnext = (uint32_t)n_tab;
             const int s0 = a.reads.u[o];
             if (run) {
                 d.mode = MODE_RUN;
@@ -382,6 +384,7 @@ int prepare_job(HostJob& j) {
                 if (s < 0 || s >= a.nSNPs) return set_err(QUILT_ERR_BAD_ARG, "SNP index outside [0, nSNPs)");
             }
             d.mode = MODE_DENSE;
+            d.tnext = (uint32_t)n_tab;
             d.off = (uint32_t)j.dense_reads.size();
             j.dense_reads.push_back(r);
         }
@@ -532,11 +535,14 @@ void make_params(const QuiltGibbsArgs& a, BatchParams* P) {
     P->ref_error = a.panel->ref_error;
     P->rare_common = (a.flags & QUILT_F_MAKE_EMATREAD_RARE_COMMON) ? 1 : 0;
     P->Jmax = a.Jmax;
+    const char* bm = std::getenv("QUILT_B200_BMAX");
+    P->bmax = bm ? std::atoi(bm) : 0;
+    if (P->bmax > SW_BMAX) P->bmax = SW_BMAX;
 }
 
 template <int NT, int EPT>
 int sweep_occupancy(int Kp, int NH, int* occ, int* smem) {
-    const SweepSmemLayout L = sweep_smem_layout(Kp, NH, NT);
+    const SweepSmemLayout L = sweep_smem_layout(NT * EPT, NH, NT);
     *smem = L.total;
     CK(cudaFuncSetAttribute(k_sweep<NT, EPT, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, k_sweep<NT, EPT, 2>, NT, L.total));
@@ -669,7 +675,7 @@ int run_prep(QuiltGpuBatch* B, Bucket& bk, int n, const JobDev* dj) {
 template <int NT, int EPT>
 int run_wave_t(QuiltGpuBatch* B, Bucket& bk, int n, const JobDev* dj, bool timed) {
     const BatchParams& P = bk.P;
-    const SweepSmemLayout L = sweep_smem_layout(P.Kp, P.NH, NT);
+    const SweepSmemLayout L = sweep_smem_layout(NT * EPT, P.NH, NT);
     // (buckets of different K share a template instance: re-arm the opt-in shared-memory size for this one)
     CK(cudaFuncSetAttribute(k_sweep<NT, EPT, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
     k_copy_H<<<dim3((bk.R_max + 255) / 256, n), 256, 0, g_stream>>>(dj);

@@ -8,13 +8,14 @@
 //   add_to_per_it_likelihoods             :1583-1621 (device part: -sum log c, label / H_class counts)
 //
 // Layout: the K states of a column are spread over the CTA (k = tid + i * NT, EPT elements per thread, in
-// registers); alpha_{g-1}, the working copies alphaHat_m / ab_m of the current grid live in registers for
-// the whole grid.  eMatGrid columns (both stages of a 2-deep ring) and the 32-SNP allele words of grids
-// g-1 .. g+2 are staged in shared memory by 1-D bulk async copies (TMA engine, mbarrier completion); the
-// small per-grid read metadata (descriptors, emission tables, labels, uniforms) by cp.async.  beta columns
-// are streamed with L1-bypassing loads, alpha / beta / changed eMatGrid columns leave with streaming stores.
-// Per-read K-long sums use a shuffle butterfly + one shared-memory exchange (device_common.cuh BlockSum),
-// every thread ends with bit-identical totals and takes the label decision redundantly.
+// registers); alpha of the previous grid and the working copies alphaHat_m / ab_m of the current grid live in
+// registers for the whole grid.  eMatGrid columns (a 2-deep ring) and the 32-SNP allele words of grids g-1 .. g+2
+// are staged in shared memory by 1-D bulk async copies (TMA engine, mbarrier completion); the small per-grid read
+// metadata (descriptors, emission tables, labels, uniforms) by cp.async.  beta columns are streamed with
+// L1-bypassing loads, alpha / beta / changed eMatGrid columns leave with streaming stores.  Per-read K-long sums
+// use a shuffle butterfly + one shared-memory exchange; every thread ends with bit-identical totals and takes the
+// label decision redundantly.  Shared-memory columns have stride KA = NT * EPT >= K so the per-read loops need no
+// bounds checks (padding elements carry alpha = ab = 0).
 #pragma once
 
 #include "device_common.cuh"
@@ -22,15 +23,17 @@
 
 namespace qb {
 
-constexpr int SW_MAXR = 48;     // reads of one grid staged in shared memory (more: read from global)
-constexpr int SW_MAXTAB = 384;  // table entries of one grid staged in shared memory
+constexpr int SW_MAXR = 48;     // reads staged in shared memory at a time (longer grids are processed in chunks)
+constexpr int SW_MAXTAB = 384;  // table entries staged at a time (>= 2^NBMAX, so any table-mode read fits)
 constexpr int SW_VMAX = 4;
+constexpr int SW_BMAX = 16;  // reads decided per round of the batched resampler
+static_assert(SW_MAXTAB >= (1 << NBMAX), "a single emission table must fit the staging buffer");
 
 struct SweepSmemLayout {
-    int off_bar, off_red, off_cnt, off_small[2], off_pat, off_W, off_eG, total;
+    int off_bar, off_red, off_cnt, off_small[2], off_pat, off_part, off_rec, off_W, off_eG, total;
     int small_desc, small_tab, small_U, small_H;
 };
-__host__ __device__ inline SweepSmemLayout sweep_smem_layout(int Kp, int NH, int NT) {
+__host__ __device__ inline SweepSmemLayout sweep_smem_layout(int KA, int NH, int NT) {
     SweepSmemLayout L;
     int o = 0;
     L.off_bar = o;
@@ -50,11 +53,16 @@ __host__ __device__ inline SweepSmemLayout sweep_smem_layout(int Kp, int NH, int
     L.off_small[1] = o;
     o += small_total;
     L.off_pat = o;
-    o += Kp * 2;
+    o += KA * 2;
+    L.off_part = o;
+    o += SW_BMAX * (NH == 2 ? 2 : 4) * (NT / 32) * 8;
+    L.off_rec = o;
+    o += SW_BMAX * 32 + 64;
+    o = (o + 127) & ~127;
     L.off_W = o;
-    o += 4 * Kp * 4;
+    o += 4 * KA * 4;
     L.off_eG = o;
-    o += 2 * NH * Kp * 8;
+    o += 2 * NH * KA * 8;
     L.total = o;
     return L;
 }
@@ -132,38 +140,146 @@ __device__ __forceinline__ double div_by(double a, double e, double inv) {
     return fma(r, inv, q);
 }
 
-__device__ __forceinline__ uint32_t read_pattern_smem(const ReadDesc& d, const uint32_t* Wr, int Kp, int g, int k) {
-    if (d.mode == MODE_RUN) {
-        const int w0 = g + d.g0rel;
-        const uint32_t lo = Wr[(w0 & 3) * Kp + k];
-        const uint32_t hi = (d.b0 + d.nb > 32) ? Wr[((w0 + 1) & 3) * Kp + k] : 0u;
-        return __funnelshift_r(lo, hi, d.b0) & ((1u << d.nb) - 1u);
+
+enum ReadKind : int { KIND_NORMAL = 0, KIND_INIT = 1, KIND_PASS = 2 };
+
+struct Decision {
+    int hN;
+    bool change;
+    P3 x;      // label probabilities placed by label (H_class is derived from them)
+    P3 pCnew;  // column sums of ab_m after the decision
+};
+
+// the scalar part of sample_reads_in_grid for one read (gibbs-nipt.cpp:998-1046, :1112-1134):
+// sv = {sum ab_C / e, sum ab_A1 * e, sum ab_A2 * e} (normal) or {sum ab_0 * e, sum ab_1 * e, sum ab_2 * e} (initialisation)
+template <int NH>
+__device__ __forceinline__ Decision decide_read(const P3& pC_in, const double (&sv)[NH], int hC_in, int kind, double chance, const P3& prior) {
+    int hC = 0, hA1 = 1, hA2 = 2;
+    P3 pC = pC_in, pA1 = pC_in, pA2 = pC_in;
+    if (kind == KIND_NORMAL) {
+        hC = hC_in;
+        hA1 = (hC == 0) ? 1 : 0;
+        hA2 = (hC == 2) ? 1 : 2;
+        pA1.set(hC, sv[0]);
+        pA1.set(hA1, sv[1]);
+        if (NH == 3) pA2.set(hA2, sv[NH - 1]);
+        pA2.set(hC, sv[0]);
+    } else if (kind == KIND_INIT) {
+        pC.a = sv[0];
+        pA1.b = sv[1];
+        if (NH == 3) pA2.c = sv[NH - 1];
     }
-    uint32_t pat = 0;
-    for (int j = 0; j < d.nb; j++) {
-        const int wr = d.sel[j] >> 5, b = d.sel[j] & 31;
-        pat |= ((Wr[((g + wr - 1) & 3) * Kp + k] >> b) & 1u) << j;
+    const double prod_pC = pC.prod() * prior.get(hC);
+    const double prod_pA1 = pA1.prod() * prior.get(hA1);
+    const double prod_pA2 = pA2.prod() * prior.get(hA2);
+    const double denom = prod_pC + prod_pA1 + prod_pA2;
+    const double norm_pC = prod_pC / denom, norm_pA1 = prod_pA1 / denom, norm_pA2 = prod_pA2 / denom;
+    P3 cum = {0, 0, 0};
+    cum.set(hC, norm_pC);
+    cum.set(hA1, norm_pA1);
+    cum.set(hA2, norm_pA2);
+    Decision D;
+    D.x = cum;
+    cum.b += cum.a;
+    cum.c += cum.b;
+    int hN = 0;
+    if (chance < cum.c) hN = 2;
+    if (chance < cum.b) hN = 1;
+    if (chance < cum.a) hN = 0;
+    D.hN = hN;
+    D.change = ((hN != hC) || kind == KIND_INIT) && kind != KIND_PASS;
+    D.pCnew = pC;
+    if (D.change) {
+        if (kind == KIND_NORMAL)
+            D.pCnew = (hN == hA1) ? pA1 : pA2;
+        else if (hN == 1)
+            D.pCnew = pA1;
+        else if (hN == 2)
+            D.pCnew = pA2;
     }
-    return pat;
+    return D;
+}
+
+// N values per lane -> after the call v[0] of lane L holds the 32-lane total of value index
+// wtr_index<N>(L); 4 (N = 8) or 2 (N = 16) lanes hold each value.  31/N as many shuffles as N butterflies.
+template <int N>
+__device__ __forceinline__ void warp_transpose_reduce(double (&v)[N], int lane) {
+    int n = N;
+#pragma unroll
+    for (int d = 16; n > 1; d >>= 1, n >>= 1) {
+        const bool upper = (lane & d) != 0;
+#pragma unroll
+        for (int i = 0; i < n / 2; i++) {
+            const double send = upper ? v[i] : v[i + n / 2];
+            const double keep = upper ? v[i + n / 2] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, d);
+        }
+    }
+#pragma unroll
+    for (int d = 16 / N; d >= 1; d >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], d);
+}
+template <int N>
+__device__ __forceinline__ int wtr_index(int lane) {
+    return N == 8 ? (lane >> 2) : (lane >> 1);
+}
+
+// where a read's emission value comes from, per haplotype k (uniform over the CTA for a given read)
+struct ESrc {
+    const uint32_t* wlo;   // RUN: word holding the first SNP
+    const uint32_t* whi;   // RUN: next word (only read when the run crosses)
+    const uint16_t* spat;  // GATHER: materialised patterns
+    const TabEnt* tab;     // table (shared memory)
+    const double* dcol;    // DENSE: K-long column (global memory)
+    uint32_t b0, mask;
+    bool cross;
+};
+struct EV {
+    double E, invE;
+};
+template <int SRC>  // 0: run inside one word, 1: run crossing into the next word, 2: materialised patterns, 3: dense column
+__device__ __forceinline__ EV emission_at(const ESrc& S, int k) {
+    EV r;
+    if (SRC == 3) {
+        r.E = S.dcol[k];
+        r.invE = 1 / r.E;
+        return r;
+    }
+    uint32_t pat;
+    if (SRC == 0)
+        pat = (S.wlo[k] >> S.b0) & S.mask;
+    else if (SRC == 1)
+        pat = __funnelshift_r(S.wlo[k], S.whi[k], S.b0) & S.mask;
+    else
+        pat = S.spat[k];
+    const double2 te = *reinterpret_cast<const double2*>(S.tab + pat);
+    r.E = te.x;
+    r.invE = te.y;
+    return r;
 }
 
 template <int NT, int EPT, int NH>
-__global__ void __launch_bounds__(NT, (NT <= 128 ? 5 : (NT <= 256 ? 2 : 1))) k_sweep(BatchParams P, const JobDev* __restrict__ jobs, int iteration) {
+__global__ void __launch_bounds__(NT, (NT <= 128 ? 4 : (NT <= 256 ? 2 : 1))) k_sweep(BatchParams P, const JobDev* __restrict__ jobs, int iteration) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ JobDev Js;
+    constexpr int KA = NT * EPT;
+    constexpr int NW = NT / 32;
     const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
     if (tid == 0) Js = jobs[blockIdx.x];
     __syncthreads();
     const JobDev& J = Js;
     if (*J.underflow) return;
     const int K = P.K, Kp = P.Kp, T = P.T, R = J.R;
-    const SweepSmemLayout L = sweep_smem_layout(Kp, NH, NT);
+    const SweepSmemLayout L = sweep_smem_layout(KA, NH, NT);
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L.off_bar);
     BlockSumV<NT> bsum(reinterpret_cast<double*>(smem + L.off_red));
     int* cnt = reinterpret_cast<int*>(smem + L.off_cnt);
-    uint32_t* Wr = reinterpret_cast<uint32_t*>(smem + L.off_W);
-    uint16_t* spat = reinterpret_cast<uint16_t*>(smem + L.off_pat);  // [Kp] allele patterns of reads that leave the fast path
-    double* eGs = reinterpret_cast<double*>(smem + L.off_eG);  // [2][NH][Kp]
+    uint32_t* Wr = reinterpret_cast<uint32_t*>(smem + L.off_W);          // [4][KA] ring of allele words
+    uint16_t* spat = reinterpret_cast<uint16_t*>(smem + L.off_pat);      // [KA] allele patterns of gather-mode reads
+    double* eGs = reinterpret_cast<double*>(smem + L.off_eG);            // [2][NH][KA]
+    double* part = reinterpret_cast<double*>(smem + L.off_part);         // batched resampler: [chunk * VC + value][NW]
+    unsigned char* recb = smem + L.off_rec;                              // batched resampler: [SW_BMAX] x {int hN; double pCnew[3]}
+    uint32_t* rmask = reinterpret_cast<uint32_t*>(recb + SW_BMAX * 32);  // [0..1] active, [2..3] batchable, [4..5] change masks, [6..7] chunk
     const bool iterative = (P.flags & QUILT_F_GIBBS_INITIALIZE_ITERATIVELY) != 0;
     const bool record = (P.flags & QUILT_F_RECORD_READ_SET) != 0;
     const double one_over_K = P.one_over_K;
@@ -179,9 +295,26 @@ __global__ void __launch_bounds__(NT, (NT <= 128 ? 5 : (NT <= 256 ? 2 : 1))) k_s
     __syncthreads();
     uint32_t n_use0 = 0, n_use1 = 0;  // completed uses of each stage barrier -> wait parity
 
+    // staging of reads [ra, ra + n) with table entries [ta, ta + nt) into stage buffer s
+    auto stage_small = [&](int s, int ra, int n, int ta, int nt, bool async) {
+        unsigned char* sm = smem + L.off_small[s];
+        const unsigned char* gd = reinterpret_cast<const unsigned char*>(J.desc + ra);
+        for (int i = tid; i < n * 2; i += NT) cp_async16(sm + L.small_desc + i * 16, gd + i * 16);
+        const unsigned char* gt = reinterpret_cast<const unsigned char*>(J.tabs + ta);
+        for (int i = tid; i < nt; i += NT) cp_async16(sm + L.small_tab + i * 16, gt + i * 16);
+        for (int i = tid; i < n; i += NT) {
+            cp_async8(sm + L.small_U + i * 8, U + ra + i);
+            cp_async4(sm + L.small_H + i * 4, J.H + ra + i);
+        }
+        cp_async_commit();
+        if (!async) {
+            cp_async_wait_all();
+            __syncthreads();
+        }
+    };
     // ---- one package = everything grid g needs: eMatGrid columns, the allele words of grid g+1 (ring of 4:
     //      grid g uses words g-1 .. g+1 while package g+1 is already filling word g+2), and the read
-    //      metadata of the grid
+    //      metadata of the grid when it fits one staging buffer
     auto issue_pkg = [&](int g) {
         const int s = g & 1;
         const int r0 = rs[g], r1 = rs[g + 1];
@@ -197,26 +330,20 @@ __global__ void __launch_bounds__(NT, (NT <= 128 ? 5 : (NT <= 256 ? 2 : 1))) k_s
                 mbar_arrive(&bar[s]);
             if (n_g > 0 || g == 0) {
 #pragma unroll
-                for (int h = 0; h < NH; h++) bulk_g2s(eGs + (size_t)(s * NH + h) * Kp, J.eG + ((size_t)h * T + g) * Kp, Kp * 8, &bar[s]);
+                for (int h = 0; h < NH; h++) bulk_g2s(eGs + (size_t)(s * NH + h) * KA, J.eG + ((size_t)h * T + g) * Kp, Kp * 8, &bar[s]);
             }
             if (g == 0) bulk_g2s(Wr, J.W, Kp * 4, &bar[s]);
-            if (g + 1 < T) bulk_g2s(Wr + ((g + 1) & 3) * Kp, J.W + (size_t)(g + 1) * Kp, Kp * 4, &bar[s]);
+            if (g + 1 < T) bulk_g2s(Wr + ((g + 1) & 3) * KA, J.W + (size_t)(g + 1) * Kp, Kp * 4, &bar[s]);
         }
+        bool small_done = false;
         if (n_g > 0) {
             const int t0 = J.ts[g], nt = J.ts[g + 1] - t0;
             if (n_g <= SW_MAXR && nt <= SW_MAXTAB) {
-                unsigned char* sm = smem + L.off_small[s];
-                const unsigned char* gd = reinterpret_cast<const unsigned char*>(J.desc + r0);
-                for (int i = tid; i < n_g * 2; i += NT) cp_async16(sm + L.small_desc + i * 16, gd + i * 16);
-                const unsigned char* gt = reinterpret_cast<const unsigned char*>(J.tabs + t0);
-                for (int i = tid; i < nt; i += NT) cp_async16(sm + L.small_tab + i * 16, gt + i * 16);
-                for (int i = tid; i < n_g; i += NT) {
-                    cp_async8(sm + L.small_U + i * 8, U + r0 + i);
-                    cp_async4(sm + L.small_H + i * 4, J.H + r0 + i);
-                }
+                stage_small(s, r0, n_g, t0, nt, true);
+                small_done = true;
             }
         }
-        cp_async_commit();
+        if (!small_done) cp_async_commit();
     };
     auto wait_pkg = [&](int g) {
         const int s = g & 1;
@@ -245,7 +372,7 @@ __global__ void __launch_bounds__(NT, (NT <= 128 ? 5 : (NT <= 256 ? 2 : 1))) k_s
         const int r0 = rs[g], r1 = rs[g + 1];
         const int n_g = r1 - r0;
         const bool has = n_g > 0;
-        double* eg = eGs + (size_t)(s * NH) * Kp;
+        double* eg = eGs + (size_t)(s * NH) * KA;
         double c_old[NH];
 #pragma unroll
         for (int h = 0; h < NH; h++) c_old[h] = ld_cg(J.c + h * T + g);
@@ -264,7 +391,7 @@ __global__ void __launch_bounds__(NT, (NT <= 128 ? 5 : (NT <= 256 ? 2 : 1))) k_s
 #pragma unroll
                 for (int i = 0; i < EPT; i++) {
                     const int k = tid + i * NT;
-                    am[h][i] = (k < K) ? one_over_K * eg[h * Kp + k] : 0.0;
+                    am[h][i] = (k < K) ? one_over_K * eg[h * KA + k] : 0.0;
                 }
                 sv[h] = Col<NT, EPT>::sum(am[h]);
             }
@@ -293,7 +420,7 @@ __global__ void __launch_bounds__(NT, (NT <= 128 ? 5 : (NT <= 256 ? 2 : 1))) k_s
                     double v = 0.0;
                     if (k < K) {
                         v = x * am[h][i] + jump;
-                        if (has) v = eg[h * Kp + k] * v;
+                        if (has) v = eg[h * KA + k] * v;
                     }
                     am[h][i] = v;
                 }
@@ -309,230 +436,403 @@ __global__ void __launch_bounds__(NT, (NT <= 128 ? 5 : (NT <= 256 ? 2 : 1))) k_s
                 for (int i = 0; i < EPT; i++) am[h][i] *= sc;
             }
         }
-        // am now holds alphaHat_t[:, g]; keep it as `ap` for the next grid unless reads change it
+        // am now holds alphaHat_t[:, g]; it stays in registers as the previous column of the next grid
         bool changed = false;
         if (has) {
-            const bool staged = (n_g <= SW_MAXR) && (J.ts[g + 1] - J.ts[g] <= SW_MAXTAB);
             const unsigned char* sm = smem + L.off_small[s];
-            const ReadDesc* descp = staged ? reinterpret_cast<const ReadDesc*>(sm + L.small_desc) : J.desc + r0;
-            const TabEnt* tabp = staged ? reinterpret_cast<const TabEnt*>(sm + L.small_tab) : J.tabs + J.ts[g];
-            const double* Up = staged ? reinterpret_cast<const double*>(sm + L.small_U) : U + r0;
-            const int32_t* Hp = staged ? reinterpret_cast<const int32_t*>(sm + L.small_H) : J.H + r0;
-            const uint32_t tab_base = (uint32_t)J.ts[g];
-            const uint32_t* wg = Wr + (g & 3) * Kp;  // this grid's allele words: most reads lie inside one 32-SNP word
-            bool inited = false;
-            P3 pC = {1, 1, 1};
+            const ReadDesc* descs = reinterpret_cast<const ReadDesc*>(sm + L.small_desc);
+            const TabEnt* tabs = reinterpret_cast<const TabEnt*>(sm + L.small_tab);
+            const double* Us = reinterpret_cast<const double*>(sm + L.small_U);
+            const int32_t* Hs = reinterpret_cast<const int32_t*>(sm + L.small_H);
             const P3 prior = {P.prior[0], P.prior[1], P.prior[2]};
-            for (int ir = 0; ir < n_g; ir++) {
-                // descriptor as two 16-byte words (no local-memory copy): off | cat,mode,nb,g0rel | b0,sel0..2 | ...
-                const uint4 dq = *reinterpret_cast<const uint4*>(descp + ir);
-                const int cat = dq.y & 0xff, mode = (dq.y >> 8) & 0xff, nb = (dq.y >> 16) & 0xff;
-                if (NH == 2 && cat == 1) continue;  // diploid: uninformative reads are never visited (gibbs-nipt.cpp:815)
-                const int g0rel = (int)(int8_t)(dq.y >> 24), b0 = dq.z & 0xff;
-                const int r = r0 + ir;
+            P3 pC = {1, 1, 1};
+            bool inited = false;
+
+            auto kind_of = [&](int r) -> int {
                 // which of the three regimes (gibbs-nipt.cpp:816-834)
-                bool normal = true, init_mode = false, pass = false;
                 if (iterative) {
-                    if (iteration == 0) {
-                        normal = false;
-                        if (r < J.first_read)
-                            pass = true;
-                        else
-                            init_mode = true;
-                    } else if (iteration == 1 && r < J.first_read) {
-                        normal = false;
-                        init_mode = true;
-                    }
+                    if (iteration == 0) return (r < J.first_read) ? KIND_PASS : KIND_INIT;
+                    if (iteration == 1 && r < J.first_read) return KIND_INIT;
                 }
-                if (!inited) {
-                    // alphaHat_m = alpha, betaHat_m = beta, ab_m = alpha * beta ; pC = colsums
-                    double sv[NH];
+                return KIND_NORMAL;
+            };
+            auto init_ab = [&]() {
+                // alphaHat_m = alpha, betaHat_m = beta, ab_m = alpha * beta ; pC = colsums (gibbs-nipt.cpp:836-858)
+                double sv[NH];
 #pragma unroll
-                    for (int h = 0; h < NH; h++) {
+                for (int h = 0; h < NH; h++) {
 #pragma unroll
-                        for (int i = 0; i < EPT; i++) ab[h][i] = am[h][i] * ab[h][i];
-                        sv[h] = Col<NT, EPT>::sum(ab[h]);
-                    }
-                    bsum.run(sv);
-                    pC.a = sv[0];
-                    pC.b = sv[1];
-                    if (NH == 3) pC.c = sv[NH - 1];
-                    inited = true;
+                    for (int i = 0; i < EPT; i++) ab[h][i] = am[h][i] * ab[h][i];
+                    sv[h] = Col<NT, EPT>::sum(ab[h]);
                 }
-                int hC = 0, hA1 = 1, hA2 = 2;
-                P3 pA1 = pC, pA2 = pC;
-                const TabEnt* tab = tabp + (dq.x - tab_base);
-                const double* dcol = J.dense + (size_t)dq.x * Kp;
-                // allele pattern of every haplotype over the read's SNPs (index into the read's emission table).
-                // fast path: all SNPs inside this grid's word -> (word >> b0) & mask inline; otherwise the patterns
-                // are materialised once into spat[] (each thread writes and later reads only its own elements)
-                const bool fast = (mode == MODE_RUN) && g0rel == 0 && (b0 + nb <= 32);
-                const uint32_t mask = (1u << nb) - 1u;
-                if (!fast && !pass) {
-                    if (mode == MODE_RUN) {
-                        const uint32_t* wlo = Wr + ((g + g0rel) & 3) * Kp;
-                        const uint32_t* whi = Wr + ((g + g0rel + 1) & 3) * Kp;
-                        const bool cross = b0 + nb > 32;
-#pragma unroll
-                        for (int i = 0; i < EPT; i++) {
-                            const int k = tid + i * NT;
-                            if (k < K) {
-                                const uint32_t lo = wlo[k];
-                                const uint32_t hi = cross ? whi[k] : 0u;
-                                spat[k] = (uint16_t)(__funnelshift_r(lo, hi, b0) & mask);
-                            }
-                        }
-                    } else if (mode == MODE_GATHER) {
-                        const uint8_t* sel = reinterpret_cast<const uint8_t*>(descp + ir) + 9;
-#pragma unroll
-                        for (int i = 0; i < EPT; i++) {
-                            const int k = tid + i * NT;
-                            if (k < K) {
-                                uint32_t pt = 0;
-                                for (int j = 0; j < nb; j++) {
-                                    const int sj = sel[j];
-                                    pt |= ((Wr[((g + (sj >> 5) - 1) & 3) * Kp + k] >> (sj & 31)) & 1u) << j;
-                                }
-                                spat[k] = (uint16_t)pt;
-                            }
-                        }
-                    }
-                }
-#define QB_PAT(k) (fast ? ((wg[k] >> b0) & mask) : (uint32_t)spat[k])
-                if (!pass) {
-                    if (normal) {
-                        hC = Hp[ir] - 1;
-                        hA1 = (hC == 0) ? 1 : 0;
-                        hA2 = (hC == 2) ? 1 : 2;
-                    }
-                    // K-long sums: normal  -> sum ab_C / e, sum ab_A1 * e, (sum ab_A2 * e)
-                    //              init    -> sum ab_0 * e, sum ab_1 * e, (sum ab_2 * e)
-                    double sv[NH];
-#pragma unroll
-                    for (int h = 0; h < NH; h++) sv[h] = 0;
-#define QB_SUM_LOOP(XC, XA1, XA2, CMUL)                                                                  \
+                bsum.run(sv);
+                pC.a = sv[0];
+                pC.b = sv[1];
+                if (NH == 3) pC.c = sv[NH - 1];
+                inited = true;
+            };
+            // ESrc of chunk-local read ir; returns the source kind (0..3)
+            auto make_src = [&](int ir, uint32_t tab0, ESrc& S) -> int {
+                // descriptor as one 16-byte word (no local-memory copy): off | cat,mode,nb,g0rel | b0,sel0..2 | ...
+                const uint4 dq = *reinterpret_cast<const uint4*>(descs + ir);
+                const int mode = (dq.y >> 8) & 0xff, nb = (dq.y >> 16) & 0xff;
+                const int g0rel = (int)(int8_t)(dq.y >> 24);
+                S.b0 = dq.z & 0xff;
+                S.mask = (1u << nb) - 1u;
+                S.wlo = Wr + ((g + g0rel) & 3) * KA;
+                S.whi = Wr + ((g + g0rel + 1) & 3) * KA;
+                S.cross = S.b0 + nb > 32;
+                S.tab = tabs + (dq.x - tab0);
+                S.spat = spat;
+                S.dcol = J.dense + (size_t)dq.x * Kp;
+                if (mode == MODE_DENSE) return 3;
+                if (mode == MODE_GATHER) return 2;
+                return S.cross ? 1 : 0;
+            };
+            // divide the old label's alphaHat_m / ab_m / eMatGrid by the read's column, multiply the new label's
+            // (gibbs-nipt.cpp:1092-1110).  Divisions: q = a * (1/e) corrected by one fma residual step = the correctly
+            // rounded a / e (DESIGN.md "arithmetic"); dense columns divide.
+#define QB_UPD_LOOP(SRC, HC, HN, DODIV)                                                                   \
     _Pragma("unroll") for (int i = 0; i < EPT; i++) {                                                     \
         const int k = tid + i * NT;                                                                       \
-        if (k < K) {                                                                                      \
-            if (mode == MODE_DENSE) {                                                                     \
-                const double E = dcol[k];                                                                 \
-                sv[0] += CMUL ? XC[i] * E : XC[i] / E;                                                    \
-                sv[1] += XA1[i] * E;                                                                      \
-                if (NH == 3) sv[NH - 1] += XA2[i] * E;                                                    \
-            } else {                                                                                      \
-                const double2 te = *reinterpret_cast<const double2*>(tab + QB_PAT(k));                   \
-                sv[0] = fma(XC[i], CMUL ? te.x : te.y, sv[0]);                                            \
-                sv[1] = fma(XA1[i], te.x, sv[1]);                                                         \
-                if (NH == 3) sv[NH - 1] = fma(XA2[i], te.x, sv[NH - 1]);                                  \
-            }                                                                                             \
-        }                                                                                                 \
-    }
-                    if (!normal) {
-                        QB_SUM_LOOP(ab[0], ab[1], ab[NH - 1], true)
-                    } else if (hC == 0) {
-                        QB_SUM_LOOP(ab[0], ab[1], ab[NH - 1], false)
-                    } else if (hC == 1) {
-                        QB_SUM_LOOP(ab[1], ab[0], ab[NH - 1], false)
-                    } else {
-                        QB_SUM_LOOP(ab[NH - 1], ab[0], ab[1], false)
-                    }
-#undef QB_SUM_LOOP
-                    bsum.run(sv);
-                    if (normal) {
-                        pA1.set(hC, sv[0]);
-                        pA1.set(hA1, sv[1]);
-                        if (NH == 3) pA2.set(hA2, sv[NH - 1]);
-                        pA2.set(hC, sv[0]);
-                    } else {
-                        pC.a = sv[0];
-                        pA1.b = sv[1];
-                        if (NH == 3) pA2.c = sv[NH - 1];
-                    }
-                }
-                const double prod_pC = pC.prod() * prior.get(hC);
-                const double prod_pA1 = pA1.prod() * prior.get(hA1);
-                const double prod_pA2 = pA2.prod() * prior.get(hA2);
-                const double denom = prod_pC + prod_pA1 + prod_pA2;
-                const double norm_pC = prod_pC / denom, norm_pA1 = prod_pA1 / denom, norm_pA2 = prod_pA2 / denom;
-                const double chance = Up[ir];
-                P3 cum = {0, 0, 0};
-                cum.set(hC, norm_pC);
-                cum.set(hA1, norm_pA1);
-                cum.set(hA2, norm_pA2);
-                const double x0 = cum.a, x1 = cum.b, x2 = cum.c;
-                cum.b += cum.a;
-                cum.c += cum.b;
-                int hN = 0;
-                if (chance < cum.c) hN = 2;
-                if (chance < cum.b) hN = 1;
-                if (chance < cum.a) hN = 0;
-                if (((hN != hC) || init_mode) && !pass) {
-                    changed = true;
-                    if (tid == 0) J.H[r] = hN + 1;
-                    // alphaHat_m / ab_m / eMatGrid of the old label are divided by the read's column, those of the new
-                    // label multiplied (gibbs-nipt.cpp:1092-1110).  Divisions: q = a * (1/e) corrected by one fma
-                    // residual step = the correctly rounded a / e (DESIGN.md "arithmetic"); dense columns divide.
-#define QB_UPD_LOOP(HC, HN, DODIV)                                                                        \
-    _Pragma("unroll") for (int i = 0; i < EPT; i++) {                                                     \
-        const int k = tid + i * NT;                                                                       \
-        if (k < K) {                                                                                      \
-            double E, invE;                                                                               \
-            if (mode == MODE_DENSE) {                                                                     \
-                E = dcol[k];                                                                              \
-                invE = 1 / E;                                                                             \
-            } else {                                                                                      \
-                const double2 te = *reinterpret_cast<const double2*>(tab + QB_PAT(k));                   \
-                E = te.x;                                                                                 \
-                invE = te.y;                                                                              \
-            }                                                                                             \
+        if (SRC != 3 || k < K) {                                                                          \
+            const EV ev = emission_at<SRC>(S, k);                                                         \
             if (DODIV) {                                                                                  \
-                am[HC][i] = div_by(am[HC][i], E, invE);                                                   \
-                ab[HC][i] = div_by(ab[HC][i], E, invE);                                                   \
-                if (HC < 2 || NH == 3) eg[HC * Kp + k] = div_by(eg[HC * Kp + k], E, invE);                \
+                am[HC][i] = (SRC == 3) ? am[HC][i] / ev.E : div_by(am[HC][i], ev.E, ev.invE);             \
+                ab[HC][i] = (SRC == 3) ? ab[HC][i] / ev.E : div_by(ab[HC][i], ev.E, ev.invE);             \
+                if (HC < 2 || NH == 3)                                                                    \
+                    eg[HC * KA + k] = (SRC == 3) ? eg[HC * KA + k] / ev.E : div_by(eg[HC * KA + k], ev.E, ev.invE); \
             }                                                                                             \
-            am[HN][i] *= E;                                                                               \
-            ab[HN][i] *= E;                                                                               \
-            if (HN < 2 || NH == 3) eg[HN * Kp + k] *= E;                                                  \
+            am[HN][i] *= ev.E;                                                                            \
+            ab[HN][i] *= ev.E;                                                                            \
+            if (HN < 2 || NH == 3) eg[HN * KA + k] *= ev.E;                                               \
         }                                                                                                 \
     }
-                    if (normal) {
-                        if (hC == 0 && hN == 1) {
-                            QB_UPD_LOOP(0, 1, true)
-                        } else if (hC == 1 && hN == 0) {
-                            QB_UPD_LOOP(1, 0, true)
-                        } else if (NH == 3) {
-                            if (hC == 0 && hN == 2) {
-                                QB_UPD_LOOP(0, NH - 1, true)
-                            } else if (hC == 1 && hN == 2) {
-                                QB_UPD_LOOP(1, NH - 1, true)
-                            } else if (hC == 2 && hN == 0) {
-                                QB_UPD_LOOP(NH - 1, 0, true)
-                            } else if (hC == 2 && hN == 1) {
-                                QB_UPD_LOOP(NH - 1, 1, true)
-                            }
+#define QB_UPD_LABELS(SRC, normal, hC, hN)                                                                \
+    if (normal) {                                                                                         \
+        if (hC == 0 && hN == 1) {                                                                         \
+            QB_UPD_LOOP(SRC, 0, 1, true)                                                                  \
+        } else if (hC == 1 && hN == 0) {                                                                  \
+            QB_UPD_LOOP(SRC, 1, 0, true)                                                                  \
+        } else if (NH == 3) {                                                                             \
+            if (hC == 0 && hN == 2) {                                                                     \
+                QB_UPD_LOOP(SRC, 0, NH - 1, true)                                                         \
+            } else if (hC == 1 && hN == 2) {                                                              \
+                QB_UPD_LOOP(SRC, 1, NH - 1, true)                                                         \
+            } else if (hC == 2 && hN == 0) {                                                              \
+                QB_UPD_LOOP(SRC, NH - 1, 0, true)                                                         \
+            } else if (hC == 2 && hN == 1) {                                                              \
+                QB_UPD_LOOP(SRC, NH - 1, 1, true)                                                         \
+            }                                                                                             \
+        }                                                                                                 \
+    } else {                                                                                              \
+        if (hN == 0) {                                                                                    \
+            QB_UPD_LOOP(SRC, 0, 0, false)                                                                 \
+        } else if (hN == 1) {                                                                             \
+            QB_UPD_LOOP(SRC, 0, 1, false)                                                                 \
+        } else if (NH == 3) {                                                                             \
+            QB_UPD_LOOP(SRC, 0, NH - 1, false)                                                            \
+        }                                                                                                 \
+    }
+#define QB_UPD(src, normal, hC, hN)                                                                       \
+    if (src == 0) {                                                                                       \
+        QB_UPD_LABELS(0, normal, hC, hN)                                                                  \
+    } else if (src == 1) {                                                                                \
+        QB_UPD_LABELS(1, normal, hC, hN)                                                                  \
+    } else if (src == 2) {                                                                                \
+        QB_UPD_LABELS(2, normal, hC, hN)                                                                  \
+    } else {                                                                                              \
+        QB_UPD_LABELS(3, normal, hC, hN)                                                                  \
+    }
+            // K-long sums: normal -> sum ab_C / e, sum ab_A1 * e, (sum ab_A2 * e) ; init -> every label times e
+#define QB_SUM_LOOP(SRC, XC, XA1, XA2, CMUL)                                                              \
+    _Pragma("unroll") for (int i = 0; i < EPT; i++) {                                                     \
+        const int k = tid + i * NT;                                                                       \
+        if (SRC != 3 || k < K) {                                                                          \
+            const EV ev = emission_at<SRC>(S, k);                                                         \
+            if (SRC == 3) {                                                                               \
+                s0 += CMUL ? XC[i] * ev.E : XC[i] / ev.E;                                                 \
+                s1 += XA1[i] * ev.E;                                                                      \
+                if (NH == 3) s2 += XA2[i] * ev.E;                                                         \
+            } else {                                                                                      \
+                s0 = fma(XC[i], CMUL ? ev.E : ev.invE, s0);                                               \
+                s1 = fma(XA1[i], ev.E, s1);                                                               \
+                if (NH == 3) s2 = fma(XA2[i], ev.E, s2);                                                  \
+            }                                                                                             \
+        }                                                                                                 \
+    }
+#define QB_SUM_LABELS(SRC, normal, hC)                                                                    \
+    if (!(normal)) {                                                                                      \
+        QB_SUM_LOOP(SRC, ab[0], ab[1], ab[NH - 1], true)                                                  \
+    } else if (hC == 0) {                                                                                 \
+        QB_SUM_LOOP(SRC, ab[0], ab[1], ab[NH - 1], false)                                                 \
+    } else if (hC == 1) {                                                                                 \
+        QB_SUM_LOOP(SRC, ab[1], ab[0], ab[NH - 1], false)                                                 \
+    } else {                                                                                              \
+        QB_SUM_LOOP(SRC, ab[NH - 1], ab[0], ab[1], false)                                                 \
+    }
+#define QB_SUM(src, normal, hC)                                                                           \
+    if (src == 0) {                                                                                       \
+        QB_SUM_LABELS(0, normal, hC)                                                                      \
+    } else if (src == 1) {                                                                                \
+        QB_SUM_LABELS(1, normal, hC)                                                                      \
+    } else if (src == 2) {                                                                                \
+        QB_SUM_LABELS(2, normal, hC)                                                                      \
+    } else {                                                                                              \
+        QB_SUM_LABELS(3, normal, hC)                                                                      \
+    }
+
+            // ---------------------------------------------------------------- one read at a time (any mode / regime)
+            // ir = index inside the staged chunk, r = read index, tab0 = table-pool offset of the chunk
+            auto single = [&](int ir, int r, uint32_t tab0) {
+                const int kind = kind_of(r);
+                if (!inited) init_ab();
+                ESrc S;
+                const int src = make_src(ir, tab0, S);
+                if (src == 2 && kind != KIND_PASS) {
+                    // gather mode: materialise the patterns once (each thread writes and later reads only its own elements)
+                    const uint4 dq = *reinterpret_cast<const uint4*>(descs + ir);
+                    const int nb = (dq.y >> 16) & 0xff;
+                    const uint8_t* sel = reinterpret_cast<const uint8_t*>(descs + ir) + 9;
+#pragma unroll
+                    for (int i = 0; i < EPT; i++) {
+                        const int k = tid + i * NT;
+                        uint32_t pt = 0;
+                        for (int j = 0; j < nb; j++) {
+                            const int sj = sel[j];
+                            pt |= ((Wr[((g + (sj >> 5) - 1) & 3) * KA + k] >> (sj & 31)) & 1u) << j;
                         }
-                        const bool useA1 = (hN == hA1);
-                        pC = useA1 ? pA1 : pA2;
-                    } else {
-                        if (hN == 0) {
-                            QB_UPD_LOOP(0, 0, false)
-                        } else if (hN == 1) {
-                            QB_UPD_LOOP(0, 1, false)
-                            pC = pA1;
-                        } else if (NH == 3) {
-                            QB_UPD_LOOP(0, NH - 1, false)
-                            pC = pA2;
-                        }
+                        spat[k] = (uint16_t)pt;
                     }
-#undef QB_UPD_LOOP
-#undef QB_PAT
+                }
+                int hC = 0;
+                double sv[NH];
+#pragma unroll
+                for (int h = 0; h < NH; h++) sv[h] = 0;
+                if (kind != KIND_PASS) {
+                    const bool normal = kind == KIND_NORMAL;
+                    if (normal) hC = Hs[ir] - 1;
+                    double s0 = 0, s1 = 0, s2 = 0;
+                    QB_SUM(src, normal, hC)
+                    sv[0] = s0;
+                    sv[1] = s1;
+                    if (NH == 3) sv[NH - 1] = s2;
+                    bsum.run(sv);
+                }
+                const Decision D = decide_read<NH>(pC, sv, hC, kind, Us[ir], prior);
+                pC = D.pCnew;
+                if (D.change) {
+                    changed = true;
+                    if (tid == 0) J.H[r] = D.hN + 1;
+                    const int hN = D.hN;
+                    const bool normal = kind == KIND_NORMAL;
+                    QB_UPD(src, normal, hC, hN)
                 }
                 if (record && tid == 0) {
-                    J.xprob[3 * (size_t)r + 0] = x0;
-                    J.xprob[3 * (size_t)r + 1] = x1;
-                    J.xprob[3 * (size_t)r + 2] = x2;
+                    J.xprob[3 * (size_t)r + 0] = D.x.a;
+                    J.xprob[3 * (size_t)r + 1] = D.x.b;
+                    J.xprob[3 * (size_t)r + 2] = D.x.c;
                 }
+            };
+
+            // ---------------------------------------------------------------- the grid's reads, chunk by chunk
+            const bool prestaged = (n_g <= SW_MAXR) && (J.ts[g + 1] - J.ts[g] <= SW_MAXTAB);
+            int c0 = 0;
+            uint32_t tab0 = (uint32_t)J.ts[g];
+            while (c0 < n_g) {
+                int cn = n_g;
+                if (!prestaged) {
+                    // rare: a grid with more reads / table entries than one staging buffer holds
+                    __syncthreads();
+                    if (tid == 0) {
+                        int n = 0;
+                        uint32_t tend = tab0;
+                        while (c0 + n < n_g && n < SW_MAXR) {
+                            const uint32_t tn = J.desc[r0 + c0 + n].tnext;
+                            if (tn - tab0 > (uint32_t)SW_MAXTAB) break;
+                            tend = tn;
+                            n++;
+                        }
+                        rmask[6] = (uint32_t)n;
+                        rmask[7] = tend;
+                    }
+                    __syncthreads();
+                    cn = (int)rmask[6];
+                    stage_small(s, r0 + c0, cn, (int)tab0, (int)(rmask[7] - tab0), false);
+                }
+                if (P.bmax <= 1) {
+                    for (int ir = 0; ir < cn; ir++) {
+                        const uint32_t dy = reinterpret_cast<const uint32_t*>(descs + ir)[1];
+                        if (NH == 2 && (dy & 0xff) == 1) continue;  // diploid: uninformative reads are never visited (gibbs-nipt.cpp:815)
+                        single(ir, r0 + c0 + ir, tab0);
+                    }
+                } else {
+                    // -------------------------------------------------------- batched resampler
+                    // Reads are resampled strictly in order, but a read whose label does not change leaves every column
+                    // untouched, so the K-long sums of the next reads are unaffected.  A round evaluates up to bmax
+                    // consecutive reads against the current state in one pass (one reduction for all of them), takes
+                    // their decisions in parallel (one warp per read) and commits them up to and including the first
+                    // label change; the reads after it are re-evaluated in the next round.  Same arithmetic per read
+                    // as the one-at-a-time path, same order of label changes.
+                    constexpr int VC = (NH == 2) ? 8 : 16;  // values per chunk of 4 reads (padded)
+                    if (warp == 0) {
+                        uint32_t ma[2], mb[2];
+#pragma unroll
+                        for (int q = 0; q < 2; q++) {
+                            const int ir = lane + 32 * q;
+                            bool act = false, bat = false;
+                            if (ir < cn) {
+                                const uint32_t dy = reinterpret_cast<const uint32_t*>(descs + ir)[1];
+                                act = !(NH == 2 && (dy & 0xff) == 1);
+                                bat = act && ((dy >> 8) & 0xff) == MODE_RUN && kind_of(r0 + c0 + ir) == KIND_NORMAL;
+                            }
+                            ma[q] = __ballot_sync(0xffffffffu, act);
+                            mb[q] = __ballot_sync(0xffffffffu, bat);
+                        }
+                        if (lane == 0) {
+                            rmask[0] = ma[0];
+                            rmask[1] = ma[1];
+                            rmask[2] = mb[0];
+                            rmask[3] = mb[1];
+                            rmask[4] = 0;
+                            rmask[5] = 0;
+                        }
+                    }
+                    __syncthreads();
+                    uint64_t rem = (uint64_t)rmask[0] | ((uint64_t)rmask[1] << 32);
+                    const uint64_t mbat = (uint64_t)rmask[2] | ((uint64_t)rmask[3] << 32);
+                    int round = 0;
+                    while (rem) {
+                        const int ir0 = __ffsll((long long)rem) - 1;
+                        if (!((mbat >> ir0) & 1)) {
+                            single(ir0, r0 + c0 + ir0, tab0);
+                            rem &= rem - 1;
+                            continue;
+                        }
+                        if (!inited) init_ab();
+                        // the batch: leading run of batchable reads among the remaining active ones
+                        int nbatch = 0;
+                        uint64_t bsel = 0;
+                        {
+                            uint64_t t = rem;
+                            while (t && nbatch < P.bmax) {
+                                const int j = __ffsll((long long)t) - 1;
+                                if (!((mbat >> j) & 1)) break;
+                                bsel |= 1ull << j;
+                                nbatch++;
+                                t &= t - 1;
+                            }
+                        }
+                        uint32_t* chg = rmask + 4 + (round & 1);
+                        // ---- phase A: sums of every read of the batch against the current ab_m
+                        {
+                            uint64_t t = bsel;
+                            for (int b0_ = 0; b0_ < nbatch; b0_ += 4) {
+                                double cv[VC];
+#pragma unroll
+                                for (int q = 0; q < VC; q++) cv[q] = 0;
+#pragma unroll
+                                for (int jj = 0; jj < 4; jj++) {
+                                    if (b0_ + jj < nbatch) {
+                                        const int ir = __ffsll((long long)t) - 1;
+                                        t &= t - 1;
+                                        ESrc S;
+                                        const int src = make_src(ir, tab0, S);
+                                        const int hC = Hs[ir] - 1;
+                                        double s0 = 0, s1 = 0, s2 = 0;
+                                        if (src == 0) {
+                                            QB_SUM_LABELS(0, true, hC)
+                                        } else {
+                                            QB_SUM_LABELS(1, true, hC)
+                                        }
+                                        cv[jj * NH] = s0;
+                                        cv[jj * NH + 1] = s1;
+                                        if (NH == 3) cv[jj * NH + NH - 1] = s2;
+                                    }
+                                }
+                                warp_transpose_reduce<VC>(cv, lane);
+                                if ((lane & (32 / VC - 1)) == 0) part[((b0_ / 4) * VC + wtr_index<VC>(lane)) * NW + warp] = cv[0];
+                            }
+                            if (tid == 0) *chg = 0;
+                        }
+                        __syncthreads();
+                        // ---- phase B: one warp per read: totals over the warps, the decision, its record
+                        for (int j = warp; j < nbatch; j += NW) {
+                            uint64_t t = bsel;
+                            for (int q = 0; q < j; q++) t &= t - 1;
+                            const int ir = __ffsll((long long)t) - 1;
+                            double sv[NH];
+#pragma unroll
+                            for (int h = 0; h < NH; h++) {
+                                double x = part[((j / 4) * VC + (j & 3) * NH + h) * NW + (lane & (NW - 1))];
+#pragma unroll
+                                for (int d = NW / 2; d >= 1; d >>= 1) x += __shfl_xor_sync(0xffffffffu, x, d);
+                                sv[h] = x;
+                            }
+                            const int hC = Hs[ir] - 1;
+                            const Decision D = decide_read<NH>(pC, sv, hC, KIND_NORMAL, Us[ir], prior);
+                            if (lane == 0) {
+                                int* ri = reinterpret_cast<int*>(recb + j * 32);
+                                double* rd = reinterpret_cast<double*>(recb + j * 32 + 8);
+                                ri[0] = D.hN;
+                                rd[0] = D.pCnew.a;
+                                rd[1] = D.pCnew.b;
+                                rd[2] = D.pCnew.c;
+                                if (D.change) atomicOr(chg, 1u << j);
+                                if (record) {
+                                    const int r = r0 + c0 + ir;
+                                    J.xprob[3 * (size_t)r + 0] = D.x.a;
+                                    J.xprob[3 * (size_t)r + 1] = D.x.b;
+                                    J.xprob[3 * (size_t)r + 2] = D.x.c;
+                                }
+                            }
+                        }
+                        __syncthreads();
+                        // ---- phase C: commit up to and including the first label change
+                        const uint32_t cm = *chg;
+                        int consumed = nbatch;
+                        if (cm) {
+                            const int f = __ffs((int)cm) - 1;
+                            consumed = f + 1;
+                            uint64_t t = bsel;
+                            for (int q = 0; q < f; q++) t &= t - 1;
+                            const int ir = __ffsll((long long)t) - 1;
+                            const int hN = *reinterpret_cast<const int*>(recb + f * 32);
+                            const double* rd = reinterpret_cast<const double*>(recb + f * 32 + 8);
+                            pC.a = rd[0];
+                            pC.b = rd[1];
+                            pC.c = rd[2];
+                            const int hC = Hs[ir] - 1;
+                            changed = true;
+                            if (tid == 0) J.H[r0 + c0 + ir] = hN + 1;
+                            ESrc S;
+                            const int src = make_src(ir, tab0, S);
+                            if (src == 0) {
+                                QB_UPD_LABELS(0, true, hC, hN)
+                            } else {
+                                QB_UPD_LABELS(1, true, hC, hN)
+                            }
+                        }
+                        // drop the consumed reads from the remaining set
+                        {
+                            uint64_t t = bsel;
+                            for (int q = 0; q < consumed; q++) {
+                                rem &= ~(t & (~t + 1));
+                                t &= t - 1;
+                            }
+                        }
+                        round++;
+                    }
+                }
+                if (!prestaged) tab0 = rmask[7];
+                c0 += cn;
             }
+#undef QB_SUM
+#undef QB_SUM_LABELS
+#undef QB_SUM_LOOP
+#undef QB_UPD
+#undef QB_UPD_LABELS
+#undef QB_UPD_LOOP
             if (changed) {
                 // gibbs-nipt.cpp:1262-1292: renormalise every haplotype's column and fold into c
                 double sv[NH];
@@ -555,7 +855,7 @@ __global__ void __launch_bounds__(NT, (NT <= 128 ? 5 : (NT <= 256 ? 2 : 1))) k_s
 #pragma unroll
                 for (int i = 0; i < EPT; i++) {
                     const int k = tid + i * NT;
-                    if (k < K) st_stream(J.eG + ((size_t)h * T + g) * Kp + k, eg[h * Kp + k]);
+                    if (k < K) st_stream(J.eG + ((size_t)h * T + g) * Kp + k, eg[h * KA + k]);
                 }
             }
             if (tid == 0) J.c[h * T + g] = cnew[h];
@@ -585,7 +885,7 @@ __global__ void __launch_bounds__(NT, (NT <= 128 ? 5 : (NT <= 256 ? 2 : 1))) k_s
                 if (has1) {
                     mbar_arrive_expect_tx(&bar[s], NH * Kp * 8);
 #pragma unroll
-                    for (int h = 0; h < NH; h++) bulk_g2s(eGs + (size_t)(s * NH + h) * Kp, J.eG + ((size_t)h * T + g + 1) * Kp, Kp * 8, &bar[s]);
+                    for (int h = 0; h < NH; h++) bulk_g2s(eGs + (size_t)(s * NH + h) * KA, J.eG + ((size_t)h * T + g + 1) * Kp, Kp * 8, &bar[s]);
                 } else {
                     mbar_arrive(&bar[s]);
                 }
@@ -604,7 +904,7 @@ __global__ void __launch_bounds__(NT, (NT <= 128 ? 5 : (NT <= 256 ? 2 : 1))) k_s
             __syncthreads();  // everyone is done with the other stage (step g + 1) before it is refilled
             if (g >= 1) issue_b(g - 1);
             const bool has1 = rs[g + 2] > rs[g + 1];
-            const double* eg = eGs + (size_t)(s * NH) * Kp;
+            const double* eg = eGs + (size_t)(s * NH) * KA;
             const double t0 = J.tm[2 * g], t1 = J.tm[2 * g + 1];
             double cg[NH], sv[NH];
 #pragma unroll
@@ -614,7 +914,7 @@ __global__ void __launch_bounds__(NT, (NT <= 128 ? 5 : (NT <= 256 ? 2 : 1))) k_s
 #pragma unroll
                     for (int i = 0; i < EPT; i++) {
                         const int k = tid + i * NT;
-                        if (k < K) b[h][i] = eg[h * Kp + k] * b[h][i];
+                        if (k < K) b[h][i] = eg[h * KA + k] * b[h][i];
                     }
                 }
                 sv[h] = Col<NT, EPT>::sum(b[h]);
