@@ -78,6 +78,26 @@ struct BlockSumV {
     // scratch buffers make one __syncthreads per call enough.
     template <int V>
     __device__ __forceinline__ void run(double (&v)[V]) {
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        if (V == 2 && NW > 1) {
+            // two values: the lower half-warp reduces v[0], the upper half v[1] (half the shuffles of two butterflies)
+            const bool upper = (lane & 16) != 0;
+            const double send = upper ? v[0] : v[1];
+            double x = (upper ? v[1] : v[0]) + __shfl_xor_sync(0xffffffffu, send, 16);
+#pragma unroll
+            for (int d = 8; d >= 1; d >>= 1) x += __shfl_xor_sync(0xffffffffu, x, d);
+            double* buf = scratch + phase * (SW_VMAX * NW);
+            phase ^= 1;
+            if ((lane & 15) == 0) buf[(lane >> 4) * NW + warp] = x;
+            __syncthreads();
+            double s = buf[(lane >> 4) * NW + (lane & (NW - 1))];
+#pragma unroll
+            for (int d = NW / 2; d >= 1; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+            const double o = __shfl_xor_sync(0xffffffffu, s, 16);
+            v[0] = upper ? o : s;
+            v[1] = upper ? s : o;
+            return;
+        }
 #pragma unroll
         for (int i = 0; i < V; i++) {
 #pragma unroll
@@ -86,7 +106,6 @@ struct BlockSumV {
         if (NW == 1) return;
         double* buf = scratch + phase * (SW_VMAX * NW);
         phase ^= 1;
-        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
         if (lane == 0) {
 #pragma unroll
             for (int i = 0; i < V; i++) buf[i * NW + warp] = v[i];
@@ -152,8 +171,48 @@ struct Decision {
 
 // the scalar part of sample_reads_in_grid for one read (gibbs-nipt.cpp:998-1046, :1112-1134):
 // sv = {sum ab_C / e, sum ab_A1 * e, sum ab_A2 * e} (normal) or {sum ab_0 * e, sum ab_1 * e, sum ab_2 * e} (initialisation)
+// a / b from rb = RN(1 / b): same correction step as div_by, i.e. the correctly rounded quotient
+__device__ __forceinline__ double quot(double a, double b, double rb) {
+    const double q = a * rb;
+    return fma(fma(-q, b, a), rb, q);
+}
+
 template <int NH>
 __device__ __forceinline__ Decision decide_read(const P3& pC_in, const double (&sv)[NH], int hC_in, int kind, double chance, const P3& prior) {
+    Decision D;
+    if (NH == 2 && kind == KIND_NORMAL) {
+        // diploid fast path, same values as the general code below: label 2 has prior 0 and pC.c stays 1
+        const bool c0 = hC_in == 0;
+        const double pc = c0 ? pC_in.a : pC_in.b, pa = c0 ? pC_in.b : pC_in.a;  // current / alternative column sums
+        const double prod_pC = ((pC_in.a * pC_in.b) * pC_in.c) * (c0 ? prior.a : prior.b);
+        const double prod_pA1 = ((c0 ? sv[0] * sv[1] : sv[1] * sv[0]) * pC_in.c) * (c0 ? prior.b : prior.a);
+        const double prod_pA2 = ((c0 ? sv[0] * pa : pa * sv[0]) * pC_in.c) * prior.c;
+        (void)pc;
+        const double denom = prod_pC + prod_pA1 + prod_pA2;
+        const double rd = 1 / denom;
+        const double norm_pC = quot(prod_pC, denom, rd), norm_pA1 = quot(prod_pA1, denom, rd), norm_pA2 = quot(prod_pA2, denom, rd);
+        D.x.a = c0 ? norm_pC : norm_pA1;
+        D.x.b = c0 ? norm_pA1 : norm_pC;
+        D.x.c = norm_pA2;
+        const double cb = D.x.b + D.x.a, cc = D.x.c + cb;
+        int hN = 0;
+        if (chance < cc) hN = 2;
+        if (chance < cb) hN = 1;
+        if (chance < D.x.a) hN = 0;
+        D.hN = hN;
+        D.change = hN != hC_in;
+        D.pCnew = pC_in;
+        if (D.change) {
+            if (hN == (c0 ? 1 : 0)) {
+                D.pCnew.a = c0 ? sv[0] : sv[1];
+                D.pCnew.b = c0 ? sv[1] : sv[0];
+            } else {
+                D.pCnew.a = c0 ? sv[0] : pC_in.a;
+                D.pCnew.b = c0 ? pC_in.b : sv[0];
+            }
+        }
+        return D;
+    }
     int hC = 0, hA1 = 1, hA2 = 2;
     P3 pC = pC_in, pA1 = pC_in, pA2 = pC_in;
     if (kind == KIND_NORMAL) {
@@ -178,7 +237,6 @@ __device__ __forceinline__ Decision decide_read(const P3& pC_in, const double (&
     cum.set(hC, norm_pC);
     cum.set(hA1, norm_pA1);
     cum.set(hA2, norm_pA2);
-    Decision D;
     D.x = cum;
     cum.b += cum.a;
     cum.c += cum.b;
