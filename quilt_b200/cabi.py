@@ -349,9 +349,9 @@ def alloc_out(call: GibbsCall, o: QuiltGibbsOut) -> GibbsResult:
     nh = 2 if (call.flags & F_SAMPLE_IS_DIPLOID) else 3
     res = GibbsResult(
         underflow_problem=False,
-        hapProbs_t=np.zeros((3, nS), order="F"),
-        genProbsM_t=np.zeros((3, nS), order="F"),
-        genProbsF_t=np.zeros((3, nS), order="F"),
+        hapProbs_t=np.empty((3, nS), order="F"),
+        genProbsM_t=np.empty((3, nS), order="F"),
+        genProbsF_t=np.empty((3, nS), order="F"),
         H=np.zeros(R, dtype=np.int32),
         H_class=np.zeros(R, dtype=np.int32),
         per_it_likelihoods=np.zeros((1 if call.n_gibbs_sample_its == 0 else call.n_full_its, 13), order="F"),

@@ -21,6 +21,7 @@
 #include <memory>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <tuple>
 #include <vector>
 
@@ -110,6 +111,67 @@ struct HBuf {  // pinned host
         return e;
     }
 };
+
+// Staging buffers are expensive to create (cudaMallocHost / cudaMalloc of several GB): batches hand them back to a
+// small cache on quilt_gpu_batch_free and the next batch reuses them.
+template <class B>
+struct BufCache {
+    std::vector<std::unique_ptr<B>> free_;
+    std::unique_ptr<B> acquire(size_t n, cudaError_t* err) {
+        *err = cudaSuccess;
+        int best = -1;
+        for (int i = 0; i < (int)free_.size(); i++)
+            if (free_[i]->bytes >= n && (best < 0 || free_[i]->bytes < free_[best]->bytes)) best = i;
+        if (best >= 0) {
+            std::unique_ptr<B> b = std::move(free_[best]);
+            free_.erase(free_.begin() + best);
+            return b;
+        }
+        free_.clear();  // nothing fits: drop the cached ones before growing
+        std::unique_ptr<B> b(new B());
+        *err = b->alloc(n);
+        return b;
+    }
+    void release(std::unique_ptr<B> b) {
+        if (b && b->p) free_.push_back(std::move(b));
+        while (free_.size() > 3) free_.erase(free_.begin());
+    }
+    void clear() { free_.clear(); }
+};
+BufCache<DBuf> g_dcache_in, g_dcache_out, g_dcache_slots;
+BufCache<HBuf> g_hcache_in, g_hcache_out;
+
+int host_threads() {
+    static int n = 0;
+    if (n == 0) {
+        n = (int)std::thread::hardware_concurrency();
+        const char* e = std::getenv("QUILT_B200_HOST_THREADS");
+        if (e) n = std::atoi(e);
+        if (n < 1) n = 1;
+        if (n > 16) n = 16;
+    }
+    return n;
+}
+// run f(i) for i in [0, n) on the host threads (staging copies are memory-bound: a few threads saturate DRAM)
+template <class F>
+void parallel_for(int n, F&& f) {
+    const int nt = std::min(host_threads(), n);
+    if (nt <= 1) {
+        for (int i = 0; i < n; i++) f(i);
+        return;
+    }
+    std::atomic<int> next{0};
+    std::vector<std::thread> th;
+    for (int t = 0; t < nt; t++)
+        th.emplace_back([&]() {
+            for (;;) {
+                const int i = next.fetch_add(1);
+                if (i >= n) break;
+                f(i);
+            }
+        });
+    for (auto& t : th) t.join();
+}
 
 // ------------------------------------------------------------------------------------------------ panel cache
 struct PanelEntry {
@@ -285,7 +347,7 @@ struct Bucket {
     size_t slot_bytes = 0;
     // slot layout
     size_t o_alpha, o_beta, o_eG, o_c, o_W, o_Wc, o_tabs, o_dense, o_xprob, o_snp_type, o_rate, o_hapLocal;
-    DBuf slots;
+    char* slots = nullptr;  // into the batch's slot arena (buckets run one after the other and share it)
     DBuf djobs;
     HBuf hjobs;
     bool perform_block = false, do_shard = false, debug = false;
@@ -298,8 +360,12 @@ struct QuiltGpuBatch {
     std::vector<HostJob> jobs;
     std::vector<std::unique_ptr<Bucket>> buckets;
     PanelDev panel;
-    DBuf din, dout;
-    HBuf hin, hout;
+    std::unique_ptr<DBuf> din_, dout_, slots_;
+    std::unique_ptr<HBuf> hin_, hout_;
+    DBuf& din() const { return *din_; }
+    DBuf& dout() const { return *dout_; }
+    HBuf& hin() const { return *hin_; }
+    HBuf& hout() const { return *hout_; }
     size_t in_bytes = 0, out_bytes = 0;
     bool ran = false, fetched_raw = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -307,6 +373,11 @@ struct QuiltGpuBatch {
     double total_ms = 0, sweep_ms = 0;
     int n_sweep_launches = 0;
     ~QuiltGpuBatch() {
+        g_dcache_in.release(std::move(din_));
+        g_dcache_out.release(std::move(dout_));
+        g_dcache_slots.release(std::move(slots_));
+        g_hcache_in.release(std::move(hin_));
+        g_hcache_out.release(std::move(hout_));
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
         for (auto& p : sweep_events) {
@@ -580,11 +651,8 @@ int setup_bucket(QuiltGpuBatch* B, Bucket& bk, size_t* mem_budget) {
     int cap = g_sms * occ;
     const size_t by_mem = std::max<size_t>(1, *mem_budget / std::max<size_t>(bk.slot_bytes, 1));
     bk.n_slots = (int)std::min<size_t>(std::min<size_t>(cap, bk.jobs.size()), by_mem);
-    CK(bk.slots.alloc((size_t)bk.n_slots * bk.slot_bytes));
-    CK(cudaMemsetAsync(bk.slots.p, 0, (size_t)bk.n_slots * bk.slot_bytes, g_stream));
     CK(bk.djobs.alloc((size_t)bk.n_slots * sizeof(JobDev)));
     CK(bk.hjobs.alloc((size_t)bk.n_slots * sizeof(JobDev)));
-    *mem_budget -= std::min(*mem_budget, (size_t)bk.n_slots * bk.slot_bytes);
     bk.perform_block = (P.flags & QUILT_F_PERFORM_BLOCK_GIBBS) != 0;
     bk.do_shard = (P.flags & QUILT_F_DO_SHARD_BLOCK_GIBBS) != 0;
     bk.debug = (P.flags & (QUILT_F_RETURN_ALPHA | QUILT_F_RETURN_EXTRA)) != 0;
@@ -593,9 +661,9 @@ int setup_bucket(QuiltGpuBatch* B, Bucket& bk, size_t* mem_budget) {
 
 void make_jobdev(const QuiltGpuBatch* B, const Bucket& bk, const HostJob& j, int slot, JobDev* D) {
     std::memset(D, 0, sizeof(*D));
-    char* s = (char*)bk.slots.p + (size_t)slot * bk.slot_bytes;
-    const char* in = (const char*)B->din.p + j.in_off;
-    char* out = (char*)B->dout.p + j.out_off;
+    char* s = (char*)bk.slots + (size_t)slot * bk.slot_bytes;
+    const char* in = (const char*)B->din().p + j.in_off;
+    char* out = (char*)B->dout().p + j.out_off;
     D->R = j.R;
     D->first_read = j.a.first_read_for_gibbs_initialization;
     D->n_dense = j.n_dense;
@@ -740,7 +808,7 @@ int fetch_debug(QuiltGpuBatch* B, Bucket& bk, int w0, int n) {
     std::vector<double> tmp(cols);
     for (int i = 0; i < n; i++) {
         HostJob& j = B->jobs[bk.jobs[w0 + i]];
-        const char* s = (const char*)bk.slots.p + (size_t)i * bk.slot_bytes;
+        const char* s = (const char*)bk.slots + (size_t)i * bk.slot_bytes;
         if (P.flags & QUILT_F_RETURN_ALPHA) {
             auto grab = [&](size_t off, std::vector<double>& dst) -> int {
                 CK(cudaMemcpy(tmp.data(), s + off, cols * 8, cudaMemcpyDeviceToHost));
@@ -783,7 +851,7 @@ int run_bucket(QuiltGpuBatch* B, Bucket& bk, bool timed, bool prep_only = false)
         CK(cudaMemcpyAsync(bk.djobs.p, hj, (size_t)n * sizeof(JobDev), cudaMemcpyHostToDevice, g_stream));
         if (bk.P.rare_common) {
             for (int i = 0; i < n; i++)
-                CK(cudaMemsetAsync((char*)bk.slots.p + (size_t)i * bk.slot_bytes + bk.o_hapLocal, 0, (size_t)bk.P.nSNPs * 24, g_stream));
+                CK(cudaMemsetAsync((char*)bk.slots + (size_t)i * bk.slot_bytes + bk.o_hapLocal, 0, (size_t)bk.P.nSNPs * 24, g_stream));
         }
         const JobDev* dj = (const JobDev*)bk.djobs.p;
         int rc;
@@ -873,6 +941,11 @@ int64_t quilt_gpu_kernel_launches(void) { return g_launches.load(); }
 void quilt_gpu_release_panel_cache(void) {
     std::lock_guard<std::mutex> lk(g_mu);
     g_panels.clear();
+    g_dcache_in.clear();
+    g_dcache_out.clear();
+    g_dcache_slots.clear();
+    g_hcache_in.clear();
+    g_hcache_out.clear();
 }
 
 int quilt_gpu_batch_free(QuiltGpuBatch* b) {
@@ -924,20 +997,38 @@ int quilt_gpu_batch_stage(int32_t n, const QuiltGibbsArgs* args, QuiltGpuBatch**
     }
     B->in_bytes = in_total;
     B->out_bytes = out_total;
-    CK(B->din.alloc(in_total));
-    CK(B->dout.alloc(out_total));
-    CK(B->hin.alloc(in_total));
-    CK(B->hout.alloc(out_total));
-    for (int i = 0; i < n; i++) fill_in(B->jobs[i], (char*)B->hin.p + B->jobs[i].in_off);
-    CK(cudaMemcpyAsync(B->din.p, B->hin.p, in_total, cudaMemcpyHostToDevice, g_stream));
+    {
+        cudaError_t e;
+        B->din_ = g_dcache_in.acquire(in_total, &e);
+        CK(e);
+        B->dout_ = g_dcache_out.acquire(out_total, &e);
+        CK(e);
+        B->hin_ = g_hcache_in.acquire(in_total, &e);
+        CK(e);
+        B->hout_ = g_hcache_out.acquire(out_total, &e);
+        CK(e);
+    }
+    {
+        QuiltGpuBatch* Bp = B.get();
+        char* hin = (char*)Bp->hin().p;
+        parallel_for(n, [&](int i) { fill_in(Bp->jobs[i], hin + Bp->jobs[i].in_off); });
+    }
+    CK(cudaMemcpyAsync(B->din().p, B->hin().p, in_total, cudaMemcpyHostToDevice, g_stream));
     size_t free_b = 0, total_b = 0;
     CK(cudaMemGetInfo(&free_b, &total_b));
-    size_t budget = (size_t)(free_b * 0.92);
-    // split the memory budget evenly between buckets (they run one after the other but keep their slots)
-    const size_t per_bucket = budget / std::max<size_t>(1, B->buckets.size());
+    for (auto& c : g_dcache_slots.free_) free_b += c->bytes;  // a cached arena will be reused or dropped
+    size_t budget = (size_t)(free_b * 0.94);
+    size_t arena = 0;
     for (auto& bk : B->buckets) {
-        size_t mb = per_bucket;
+        size_t mb = budget;
         if ((rc = setup_bucket(B.get(), *bk, &mb)) != QUILT_OK) return rc;
+        arena = std::max(arena, (size_t)bk->n_slots * bk->slot_bytes);
+    }
+    {
+        cudaError_t e;
+        B->slots_ = g_dcache_slots.acquire(arena, &e);
+        CK(e);
+        for (auto& bk : B->buckets) bk->slots = (char*)B->slots_->p;
     }
     CK(cudaEventCreate(&B->ev0));
     CK(cudaEventCreate(&B->ev1));
@@ -954,7 +1045,7 @@ int quilt_gpu_batch_run(QuiltGpuBatch* B) {
         cudaEventDestroy(p.second);
     }
     B->sweep_events.clear();
-    CK(cudaMemsetAsync(B->dout.p, 0, B->out_bytes, g_stream));
+    CK(cudaMemsetAsync(B->dout().p, 0, B->out_bytes, g_stream));
     CK(cudaEventRecord(B->ev0, g_stream));
     for (auto& bk : B->buckets) {
         int rc = run_bucket(B, *bk, true);
@@ -1012,15 +1103,15 @@ int quilt_gpu_batch_fetch(QuiltGpuBatch* B, QuiltGibbsOut* out) {
     if (!B || !out) return set_err(QUILT_ERR_BAD_ARG, "null batch / out");
     if (!B->ran) return set_err(QUILT_ERR_BAD_ARG, "batch has not been run");
     if (!B->fetched_raw) {
-        CK(cudaMemcpyAsync(B->hout.p, B->dout.p, B->out_bytes, cudaMemcpyDeviceToHost, g_stream));
+        CK(cudaMemcpyAsync(B->hout().p, B->dout().p, B->out_bytes, cudaMemcpyDeviceToHost, g_stream));
         CK(cudaStreamSynchronize(g_stream));
         B->fetched_raw = true;
     }
-    for (int i = 0; i < B->n; i++) {
+    parallel_for(B->n, [&](int i) {
         const HostJob& j = B->jobs[i];
         const QuiltGibbsArgs& a = j.a;
         QuiltGibbsOut& o = out[i];
-        const char* base = (const char*)B->hout.p + j.out_off;
+        const char* base = (const char*)B->hout().p + j.out_off;
         const int under = *reinterpret_cast<const int32_t*>(base + j.lo.underflow);
         o.underflow_problem = under ? 1 : 0;
         const size_t n3 = (size_t)a.nSNPs * 3;
@@ -1050,7 +1141,7 @@ int quilt_gpu_batch_fetch(QuiltGpuBatch* B, QuiltGibbsOut* out) {
         }
         if ((a.flags & QUILT_F_RETURN_EXTRA) && o.eMatRead_t && !j.dbg_eMatRead.empty())
             std::memcpy(o.eMatRead_t, j.dbg_eMatRead.data(), j.dbg_eMatRead.size() * 8);
-    }
+    });
     return QUILT_OK;
 }
 
@@ -1077,13 +1168,13 @@ int quilt_gpu_make_eMatRead_t(const QuiltGibbsArgs* args, double* eMatRead_t, in
     if (rc != QUILT_OK) return rc;
     {
         std::lock_guard<std::mutex> lk(g_mu);
-        rc = cudaMemsetAsync(B->dout.p, 0, B->out_bytes, g_stream) == cudaSuccess ? QUILT_OK : set_err(QUILT_ERR_CUDA, "memset");
+        rc = cudaMemsetAsync(B->dout().p, 0, B->out_bytes, g_stream) == cudaSuccess ? QUILT_OK : set_err(QUILT_ERR_CUDA, "memset");
         if (rc == QUILT_OK) rc = run_bucket(B, *B->buckets[0], false, true);
         if (rc == QUILT_OK) {
             const HostJob& j = B->jobs[0];
             std::memcpy(eMatRead_t, j.dbg_eMatRead.data(), j.dbg_eMatRead.size() * 8);
             if (read_category) {
-                cudaError_t e = cudaMemcpy(read_category, (const char*)B->dout.p + j.out_off + j.lo.cat, (size_t)j.R * 4, cudaMemcpyDeviceToHost);
+                cudaError_t e = cudaMemcpy(read_category, (const char*)B->dout().p + j.out_off + j.lo.cat, (size_t)j.R * 4, cudaMemcpyDeviceToHost);
                 if (e != cudaSuccess) rc = set_err(QUILT_ERR_CUDA, cudaGetErrorString(e));
             }
         }

@@ -695,6 +695,7 @@ __global__ void __launch_bounds__(NT, (NT <= 128 ? 4 : (NT <= 256 ? 2 : 1))) k_s
 
             // ---------------------------------------------------------------- the grid's reads, chunk by chunk
             const bool prestaged = (n_g <= SW_MAXR) && (J.ts[g + 1] - J.ts[g] <= SW_MAXTAB);
+            const bool special_its = iterative && iteration <= 1;  // sweeps with pass-through / initialisation reads
             int c0 = 0;
             uint32_t tab0 = (uint32_t)J.ts[g];
             while (c0 < n_g) {
@@ -718,168 +719,73 @@ __global__ void __launch_bounds__(NT, (NT <= 128 ? 4 : (NT <= 256 ? 2 : 1))) k_s
                     cn = (int)rmask[6];
                     stage_small(s, r0 + c0, cn, (int)tab0, (int)(rmask[7] - tab0), false);
                 }
-                if (P.bmax <= 1) {
-                    for (int ir = 0; ir < cn; ir++) {
-                        const uint32_t dy = reinterpret_cast<const uint32_t*>(descs + ir)[1];
-                        if (NH == 2 && (dy & 0xff) == 1) continue;  // diploid: uninformative reads are never visited (gibbs-nipt.cpp:815)
-                        single(ir, r0 + c0 + ir, tab0);
+                for (int ir = 0; ir < cn; ir++) {
+                    const uint4 dq = *reinterpret_cast<const uint4*>(descs + ir);
+                    if (NH == 2 && (dq.y & 0xff) == 1) continue;  // diploid: uninformative reads are never visited (gibbs-nipt.cpp:815)
+                    const int r = r0 + c0 + ir;
+                    const int mode = (dq.y >> 8) & 0xff;
+                    if (NH != 2 || mode != MODE_RUN || (special_its && kind_of(r) != KIND_NORMAL)) {
+                        single(ir, r, tab0);
+                        continue;
                     }
-                } else {
-                    // -------------------------------------------------------- batched resampler
-                    // Reads are resampled strictly in order, but a read whose label does not change leaves every column
-                    // untouched, so the K-long sums of the next reads are unaffected.  A round evaluates up to bmax
-                    // consecutive reads against the current state in one pass (one reduction for all of them), takes
-                    // their decisions in parallel (one warp per read) and commits them up to and including the first
-                    // label change; the reads after it are re-evaluated in the next round.  Same arithmetic per read
-                    // as the one-at-a-time path, same order of label changes.
-                    constexpr int VC = (NH == 2) ? 8 : 16;  // values per chunk of 4 reads (padded)
-                    if (warp == 0) {
-                        uint32_t ma[2], mb[2];
-#pragma unroll
-                        for (int q = 0; q < 2; q++) {
-                            const int ir = lane + 32 * q;
-                            bool act = false, bat = false;
-                            if (ir < cn) {
-                                const uint32_t dy = reinterpret_cast<const uint32_t*>(descs + ir)[1];
-                                act = !(NH == 2 && (dy & 0xff) == 1);
-                                bat = act && ((dy >> 8) & 0xff) == MODE_RUN && kind_of(r0 + c0 + ir) == KIND_NORMAL;
-                            }
-                            ma[q] = __ballot_sync(0xffffffffu, act);
-                            mb[q] = __ballot_sync(0xffffffffu, bat);
-                        }
-                        if (lane == 0) {
-                            rmask[0] = ma[0];
-                            rmask[1] = ma[1];
-                            rmask[2] = mb[0];
-                            rmask[3] = mb[1];
-                            rmask[4] = 0;
-                            rmask[5] = 0;
-                        }
+                    // ---- hot path: diploid, table-mode read on consecutive SNPs, normal regime
+                    if (!inited) init_ab();
+                    ESrc S;
+                    {
+                        const int nb = (dq.y >> 16) & 0xff;
+                        const int g0rel = (int)(int8_t)(dq.y >> 24);
+                        S.b0 = dq.z & 0xff;
+                        S.mask = (1u << nb) - 1u;
+                        S.wlo = Wr + ((g + g0rel) & 3) * KA;
+                        S.whi = Wr + ((g + g0rel + 1) & 3) * KA;
+                        S.cross = S.b0 + nb > 32;
+                        S.tab = tabs + (dq.x - tab0);
                     }
-                    __syncthreads();
-                    uint64_t rem = (uint64_t)rmask[0] | ((uint64_t)rmask[1] << 32);
-                    const uint64_t mbat = (uint64_t)rmask[2] | ((uint64_t)rmask[3] << 32);
-                    int round = 0;
-                    while (rem) {
-                        const int ir0 = __ffsll((long long)rem) - 1;
-                        if (!((mbat >> ir0) & 1)) {
-                            single(ir0, r0 + c0 + ir0, tab0);
-                            rem &= rem - 1;
-                            continue;
-                        }
-                        if (!inited) init_ab();
-                        // the batch: leading run of batchable reads among the remaining active ones
-                        int nbatch = 0;
-                        uint64_t bsel = 0;
-                        {
-                            uint64_t t = rem;
-                            while (t && nbatch < P.bmax) {
-                                const int j = __ffsll((long long)t) - 1;
-                                if (!((mbat >> j) & 1)) break;
-                                bsel |= 1ull << j;
-                                nbatch++;
-                                t &= t - 1;
-                            }
-                        }
-                        uint32_t* chg = rmask + 4 + (round & 1);
-                        // ---- phase A: sums of every read of the batch against the current ab_m
-                        {
-                            uint64_t t = bsel;
-                            for (int b0_ = 0; b0_ < nbatch; b0_ += 4) {
-                                double cv[VC];
-#pragma unroll
-                                for (int q = 0; q < VC; q++) cv[q] = 0;
-#pragma unroll
-                                for (int jj = 0; jj < 4; jj++) {
-                                    if (b0_ + jj < nbatch) {
-                                        const int ir = __ffsll((long long)t) - 1;
-                                        t &= t - 1;
-                                        ESrc S;
-                                        const int src = make_src(ir, tab0, S);
-                                        const int hC = Hs[ir] - 1;
-                                        double s0 = 0, s1 = 0, s2 = 0;
-                                        if (src == 0) {
-                                            QB_SUM_LABELS(0, true, hC)
-                                        } else {
-                                            QB_SUM_LABELS(1, true, hC)
-                                        }
-                                        cv[jj * NH] = s0;
-                                        cv[jj * NH + 1] = s1;
-                                        if (NH == 3) cv[jj * NH + NH - 1] = s2;
-                                    }
-                                }
-                                warp_transpose_reduce<VC>(cv, lane);
-                                if ((lane & (32 / VC - 1)) == 0) part[((b0_ / 4) * VC + wtr_index<VC>(lane)) * NW + warp] = cv[0];
-                            }
-                            if (tid == 0) *chg = 0;
-                        }
-                        __syncthreads();
-                        // ---- phase B: one warp per read: totals over the warps, the decision, its record
-                        for (int j = warp; j < nbatch; j += NW) {
-                            uint64_t t = bsel;
-                            for (int q = 0; q < j; q++) t &= t - 1;
-                            const int ir = __ffsll((long long)t) - 1;
-                            double sv[NH];
-#pragma unroll
-                            for (int h = 0; h < NH; h++) {
-                                double x = part[((j / 4) * VC + (j & 3) * NH + h) * NW + (lane & (NW - 1))];
-#pragma unroll
-                                for (int d = NW / 2; d >= 1; d >>= 1) x += __shfl_xor_sync(0xffffffffu, x, d);
-                                sv[h] = x;
-                            }
-                            const int hC = Hs[ir] - 1;
-                            const Decision D = decide_read<NH>(pC, sv, hC, KIND_NORMAL, Us[ir], prior);
-                            if (lane == 0) {
-                                int* ri = reinterpret_cast<int*>(recb + j * 32);
-                                double* rd = reinterpret_cast<double*>(recb + j * 32 + 8);
-                                ri[0] = D.hN;
-                                rd[0] = D.pCnew.a;
-                                rd[1] = D.pCnew.b;
-                                rd[2] = D.pCnew.c;
-                                if (D.change) atomicOr(chg, 1u << j);
-                                if (record) {
-                                    const int r = r0 + c0 + ir;
-                                    J.xprob[3 * (size_t)r + 0] = D.x.a;
-                                    J.xprob[3 * (size_t)r + 1] = D.x.b;
-                                    J.xprob[3 * (size_t)r + 2] = D.x.c;
-                                }
-                            }
-                        }
-                        __syncthreads();
-                        // ---- phase C: commit up to and including the first label change
-                        const uint32_t cm = *chg;
-                        int consumed = nbatch;
-                        if (cm) {
-                            const int f = __ffs((int)cm) - 1;
-                            consumed = f + 1;
-                            uint64_t t = bsel;
-                            for (int q = 0; q < f; q++) t &= t - 1;
-                            const int ir = __ffsll((long long)t) - 1;
-                            const int hN = *reinterpret_cast<const int*>(recb + f * 32);
-                            const double* rd = reinterpret_cast<const double*>(recb + f * 32 + 8);
-                            pC.a = rd[0];
-                            pC.b = rd[1];
-                            pC.c = rd[2];
-                            const int hC = Hs[ir] - 1;
-                            changed = true;
-                            if (tid == 0) J.H[r0 + c0 + ir] = hN + 1;
-                            ESrc S;
-                            const int src = make_src(ir, tab0, S);
-                            if (src == 0) {
-                                QB_UPD_LABELS(0, true, hC, hN)
+                    const int hC = Hs[ir] - 1;
+                    double sv[NH];
+                    {
+                        double s0 = 0, s1 = 0, s2 = 0;
+                        if (!S.cross) {
+                            if (hC == 0) {
+                                QB_SUM_LOOP(0, ab[0], ab[1], ab[NH - 1], false)
                             } else {
-                                QB_UPD_LABELS(1, true, hC, hN)
+                                QB_SUM_LOOP(0, ab[1], ab[0], ab[NH - 1], false)
+                            }
+                        } else {
+                            if (hC == 0) {
+                                QB_SUM_LOOP(1, ab[0], ab[1], ab[NH - 1], false)
+                            } else {
+                                QB_SUM_LOOP(1, ab[1], ab[0], ab[NH - 1], false)
                             }
                         }
-                        // drop the consumed reads from the remaining set
-                        {
-                            uint64_t t = bsel;
-                            for (int q = 0; q < consumed; q++) {
-                                rem &= ~(t & (~t + 1));
-                                t &= t - 1;
+                        sv[0] = s0;
+                        sv[1] = s1;
+                        (void)s2;
+                    }
+                    bsum.run(sv);
+                    const Decision D = decide_read<NH>(pC, sv, hC, KIND_NORMAL, Us[ir], prior);
+                    pC = D.pCnew;
+                    if (D.change) {
+                        changed = true;
+                        if (tid == 0) J.H[r] = D.hN + 1;
+                        if (!S.cross) {
+                            if (hC == 0) {
+                                QB_UPD_LOOP(0, 0, 1, true)
+                            } else {
+                                QB_UPD_LOOP(0, 1, 0, true)
+                            }
+                        } else {
+                            if (hC == 0) {
+                                QB_UPD_LOOP(1, 0, 1, true)
+                            } else {
+                                QB_UPD_LOOP(1, 1, 0, true)
                             }
                         }
-                        round++;
+                    }
+                    if (record && tid == 0) {
+                        J.xprob[3 * (size_t)r + 0] = D.x.a;
+                        J.xprob[3 * (size_t)r + 1] = D.x.b;
+                        J.xprob[3 * (size_t)r + 2] = D.x.c;
                     }
                 }
                 if (!prestaged) tab0 = rmask[7];
