@@ -604,20 +604,30 @@ __global__ void __launch_bounds__(NT, (NT <= 128 ? 4 : (NT <= 256 ? 2 : 1))) k_s
     }
             // K-long sums: normal -> sum ab_C / e, sum ab_A1 * e, (sum ab_A2 * e) ; init -> every label times e
 #define QB_SUM_LOOP(SRC, XC, XA1, XA2, CMUL)                                                              \
-    _Pragma("unroll") for (int i = 0; i < EPT; i++) {                                                     \
-        const int k = tid + i * NT;                                                                       \
-        if (SRC != 3 || k < K) {                                                                          \
-            const EV ev = emission_at<SRC>(S, k);                                                         \
-            if (SRC == 3) {                                                                               \
-                s0 += CMUL ? XC[i] * ev.E : XC[i] / ev.E;                                                 \
-                s1 += XA1[i] * ev.E;                                                                      \
-                if (NH == 3) s2 += XA2[i] * ev.E;                                                         \
-            } else {                                                                                      \
-                s0 = fma(XC[i], CMUL ? ev.E : ev.invE, s0);                                               \
-                s1 = fma(XA1[i], ev.E, s1);                                                               \
-                if (NH == 3) s2 = fma(XA2[i], ev.E, s2);                                                  \
+    {                                                                                                     \
+        double t0_ = 0, t1_ = 0, t2_ = 0; /* second accumulator set: halves the dependent fma chains */  \
+        _Pragma("unroll") for (int i = 0; i < EPT; i++) {                                                 \
+            const int k = tid + i * NT;                                                                   \
+            if (SRC != 3 || k < K) {                                                                      \
+                const EV ev = emission_at<SRC>(S, k);                                                     \
+                if (SRC == 3) {                                                                           \
+                    s0 += CMUL ? XC[i] * ev.E : XC[i] / ev.E;                                             \
+                    s1 += XA1[i] * ev.E;                                                                  \
+                    if (NH == 3) s2 += XA2[i] * ev.E;                                                     \
+                } else if (i & 1) {                                                                       \
+                    t0_ = fma(XC[i], CMUL ? ev.E : ev.invE, t0_);                                         \
+                    t1_ = fma(XA1[i], ev.E, t1_);                                                         \
+                    if (NH == 3) t2_ = fma(XA2[i], ev.E, t2_);                                            \
+                } else {                                                                                  \
+                    s0 = fma(XC[i], CMUL ? ev.E : ev.invE, s0);                                           \
+                    s1 = fma(XA1[i], ev.E, s1);                                                           \
+                    if (NH == 3) s2 = fma(XA2[i], ev.E, s2);                                              \
+                }                                                                                         \
             }                                                                                             \
         }                                                                                                 \
+        s0 += t0_;                                                                                        \
+        s1 += t1_;                                                                                        \
+        if (NH == 3) s2 += t2_;                                                                           \
     }
 #define QB_SUM_LABELS(SRC, normal, hC)                                                                    \
     if (!(normal)) {                                                                                      \
