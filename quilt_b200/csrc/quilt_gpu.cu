@@ -294,6 +294,18 @@ struct Geo {
     int NT, EPT;
 };
 bool pick_geo(int K, Geo* g) {
+    // QUILT_B200_GEO=NTxEPT overrides (experiments); default: few fat warps — the per-read chain is latency-bound, fewer
+    // warps mean less redundant scalar work and a shorter cross-warp reduction, more elements per thread mean more ILP
+    static int env_nt = -1, env_ept = 0;
+    if (env_nt < 0) {
+        env_nt = 0;
+        const char* e = std::getenv("QUILT_B200_GEO");
+        if (e) std::sscanf(e, "%dx%d", &env_nt, &env_ept);
+    }
+    if (env_nt > 0 && env_nt * env_ept >= K) {
+        *g = {env_nt, env_ept};
+        return true;
+    }
     if (K <= 512)
         *g = {128, 4};
     else if (K <= 1024)
@@ -301,7 +313,7 @@ bool pick_geo(int K, Geo* g) {
     else if (K <= 2048)
         *g = {512, 4};
     else if (K <= 4096)
-        *g = {512, 8};
+        *g = {256, 16};  // measured 8% faster than 512 x 8 on the K = 4096 benchmark (profiles/README.md)
     else
         return false;
     return true;
@@ -309,10 +321,17 @@ bool pick_geo(int K, Geo* g) {
 
 template <typename F>
 int with_geo(const Geo& g, F&& f) {
-    if (g.NT == 128 && g.EPT == 4) return f(std::integral_constant<int, 128>(), std::integral_constant<int, 4>());
-    if (g.NT == 256 && g.EPT == 4) return f(std::integral_constant<int, 256>(), std::integral_constant<int, 4>());
-    if (g.NT == 512 && g.EPT == 4) return f(std::integral_constant<int, 512>(), std::integral_constant<int, 4>());
-    if (g.NT == 512 && g.EPT == 8) return f(std::integral_constant<int, 512>(), std::integral_constant<int, 8>());
+#define QB_GEO(NT_, EPT_) \
+    if (g.NT == NT_ && g.EPT == EPT_) return f(std::integral_constant<int, NT_>(), std::integral_constant<int, EPT_>());
+    QB_GEO(128, 4)
+    QB_GEO(256, 4)
+    QB_GEO(512, 4)
+    QB_GEO(512, 8)
+    QB_GEO(256, 16)
+    QB_GEO(256, 8)
+    QB_GEO(128, 8)
+    QB_GEO(64, 8)
+#undef QB_GEO
     return set_err(QUILT_ERR_UNSUPPORTED, "no kernel geometry");
 }
 

@@ -316,7 +316,7 @@ __device__ __forceinline__ EV emission_at(const ESrc& S, int k) {
 }
 
 template <int NT, int EPT, int NH>
-__global__ void __launch_bounds__(NT, (NT <= 128 ? 4 : (NT <= 256 ? 2 : 1))) k_sweep(BatchParams P, const JobDev* __restrict__ jobs, int iteration) {
+__global__ void __launch_bounds__(NT, (NT * EPT <= 512 ? 4 : (NT * EPT <= 1024 ? 2 : 1))) k_sweep(BatchParams P, const JobDev* __restrict__ jobs, int iteration) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ JobDev Js;
     constexpr int KA = NT * EPT;
