@@ -49,32 +49,102 @@ __global__ void __launch_bounds__(256) k_init_iterative(BatchParams P, const Job
     }
 }
 
-// grid = (T, jobs), 256 threads: eMatGrid[:, g] of every haplotype = product of its reads' columns, in read order
+// grid = (T, jobs), 256 threads: eMatGrid[:, g] of every haplotype = product of its reads' columns, in read order.
+// The grid's descriptors, labels and emission tables are staged in shared memory (chunked when a grid holds more
+// than MEG_MAXR reads / MEG_MAXTAB table entries); a thread keeps the three allele words a read can touch in
+// registers, so a table-mode factor costs a shift, a mask and one shared-memory load.
+constexpr int MEG_MAXR = 64;
+constexpr int MEG_MAXTAB = 1024;
 __global__ void __launch_bounds__(256) k_make_eG(BatchParams P, const JobDev* __restrict__ jobs) {
-    const JobDev& J = jobs[blockIdx.y];
+    __shared__ JobDev Js;
+    __shared__ __align__(16) ReadDesc sdesc[MEG_MAXR];
+    __shared__ double stab[MEG_MAXTAB];
+    __shared__ int sH[MEG_MAXR];
+    __shared__ int schunk[2];
+    const int tid = threadIdx.x;
+    if (tid == 0) Js = jobs[blockIdx.y];
+    __syncthreads();
+    const JobDev& J = Js;
     const int g = blockIdx.x, K = P.K, Kp = P.Kp, T = P.T, NH = P.NH;
     const int r0 = J.rs[g], r1 = J.rs[g + 1];
-    for (int k = threadIdx.x; k < Kp; k += 256) {
-        double e[3] = {1.0, 1.0, 1.0};
-        if (k < K) {
-            for (int r = r0; r < r1; r++) {
-                const ReadDesc d = J.desc[r];
-                double E;
-                if (d.mode == MODE_DENSE)
-                    E = J.dense[(size_t)d.off * Kp + k];
-                else
-                    E = J.tabs[d.off + read_pattern_global(d, J.W, Kp, g, k)].E;
-                const int h = J.H[r] - 1;
-                if (h == 0)
-                    e[0] *= E;
-                else if (h == 1)
-                    e[1] *= E;
-                else if (h == 2)
-                    e[2] *= E;
+    int c0 = r0;
+    uint32_t tab0 = (uint32_t)J.ts[g];
+    bool first = true;
+    do {
+        // chunk [c0, c0 + cn) whose tables fit the staging buffer
+        __syncthreads();
+        if (tid == 0) {
+            int n = 0;
+            uint32_t tend = tab0;
+            while (c0 + n < r1 && n < MEG_MAXR) {
+                const uint32_t tn = J.desc[c0 + n].tnext;
+                if (tn - tab0 > (uint32_t)MEG_MAXTAB) break;
+                tend = tn;
+                n++;
             }
+            schunk[0] = n;
+            schunk[1] = (int)tend;
         }
-        for (int h = 0; h < NH; h++) J.eG[((size_t)h * T + g) * Kp + k] = e[h];
-    }
+        __syncthreads();
+        const int cn = schunk[0];
+        const uint32_t tend = (uint32_t)schunk[1];
+        for (int i = tid; i < cn * 2; i += 256) reinterpret_cast<uint4*>(sdesc)[i] = reinterpret_cast<const uint4*>(J.desc + c0)[i];
+        for (int i = tid; i < cn; i += 256) sH[i] = J.H[c0 + i];
+        for (int i = tid; i < (int)(tend - tab0); i += 256) stab[i] = J.tabs[tab0 + i].E;
+        __syncthreads();
+        for (int k = tid; k < Kp; k += 256) {
+            double e[3] = {1.0, 1.0, 1.0};
+            if (!first) {
+                for (int h = 0; h < NH; h++) e[h] = J.eG[((size_t)h * T + g) * Kp + k];
+            }
+            if (k < K && cn > 0) {
+                const uint32_t wm = (g > 0) ? J.W[(size_t)(g - 1) * Kp + k] : 0u;
+                const uint32_t w0 = J.W[(size_t)g * Kp + k];
+                const uint32_t wp = (g + 1 < T) ? J.W[(size_t)(g + 1) * Kp + k] : 0u;
+                for (int ir = 0; ir < cn; ir++) {
+                    const uint4 dq = *reinterpret_cast<const uint4*>(sdesc + ir);
+                    const int mode = (dq.y >> 8) & 0xff, nb = (dq.y >> 16) & 0xff;
+                    double E;
+                    if (mode == MODE_DENSE) {
+                        E = J.dense[(size_t)dq.x * Kp + k];
+                    } else {
+                        uint32_t pat;
+                        if (mode == MODE_RUN) {
+                            const int g0rel = (int)(int8_t)(dq.y >> 24);
+                            const uint32_t b0 = dq.z & 0xff;
+                            const uint32_t lo = g0rel < 0 ? wm : (g0rel == 0 ? w0 : wp);
+                            const uint32_t hi = g0rel < 0 ? w0 : wp;
+                            pat = __funnelshift_r(lo, (b0 + nb > 32) ? hi : 0u, b0) & ((1u << nb) - 1u);
+                        } else {
+                            const uint8_t* sel = reinterpret_cast<const uint8_t*>(sdesc + ir) + 9;
+                            pat = 0;
+                            for (int q = 0; q < nb; q++) {
+                                const int wr = sel[q] >> 5, b = sel[q] & 31;
+                                const uint32_t w = wr == 0 ? wm : (wr == 1 ? w0 : wp);
+                                pat |= ((w >> b) & 1u) << q;
+                            }
+                        }
+                        E = stab[dq.x - tab0 + pat];
+                    }
+                    const int h = sH[ir] - 1;
+                    if (h == 0)
+                        e[0] *= E;
+                    else if (h == 1)
+                        e[1] *= E;
+                    else if (h == 2)
+                        e[2] *= E;
+                }
+            }
+            for (int h = 0; h < NH; h++) J.eG[((size_t)h * T + g) * Kp + k] = e[h];
+        }
+        first = false;
+        c0 += cn;
+        tab0 = tend;
+        if (cn == 0 && c0 < r1) {
+            // a single read whose table exceeds the staging buffer cannot occur (2^NBMAX <= MEG_MAXTAB)
+            break;
+        }
+    } while (c0 < r1);
 }
 
 // generic forward + backward of one haplotype.  grid = (jobs, NH).  If ext_* are given they replace the job's
@@ -143,8 +213,20 @@ __global__ void __launch_bounds__(NT) k_fb_generic(BatchParams P, const JobDev* 
     }
 }
 
+// L2 prefetch of NC columns of Kp doubles starting at p (column stride `stride` doubles), spread over the CTA
+template <int NT>
+__device__ __forceinline__ void prefetch_cols(const double* p, size_t stride, int ncols, int Kp) {
+    const int per = Kp >> 4;  // 128-byte lines per column
+    for (int l = threadIdx.x; l < ncols * per; l += NT) {
+        const int c = l / per, q = l - c * per;
+        prefetch_l2(p + (size_t)c * stride + (q << 4));
+    }
+}
+
 // shard pass (diploid).  grid = jobs.  One CTA re-runs the forward recursion of both haplotypes with the
-// generic step and, after every grid, decides between "stay" and "swap labels from here on".
+// generic step and, after every grid, decides between "stay" and "swap labels from here on"; then the generic
+// backward of both haplotypes in one walk.  Columns are pulled into L2 two grids ahead and the per-grid scalars
+// travel one grid ahead in registers, so a step costs its reductions, not a DRAM round trip.
 template <int NT, int EPT>
 __global__ void __launch_bounds__(NT) k_shard(BatchParams P, const JobDev* __restrict__ jobs, int episode) {
     __shared__ double red[2 * SW_VMAX * (NT / 32)];
@@ -152,18 +234,24 @@ __global__ void __launch_bounds__(NT) k_shard(BatchParams P, const JobDev* __res
     const int tid = threadIdx.x;
     if (tid == 0) Js = jobs[blockIdx.x];
     __syncthreads();
-    const JobDev& J = Js;
-    if (*J.underflow) return;
-    const int K = P.K, Kp = P.Kp, T = P.T, R = J.R;
+    if (*Js.underflow) return;
+    const int K = P.K, Kp = P.Kp, T = P.T, R = Js.R;
+    double* __restrict__ alphaG = Js.alpha;
+    double* __restrict__ betaG = Js.beta;
+    double* __restrict__ eGg = Js.eG;
+    double* cG = Js.c;
+    double* rateG = Js.rate;
+    const double* __restrict__ tmG = Js.tm;
     BlockSumV<NT> bsum(red);
     const double prior = P.one_over_K;
-    const double* __restrict__ runif = J.runif_shard + (size_t)episode * (T - 1);
+    const double* __restrict__ runif = Js.runif_shard + (size_t)episode * (T - 1);
+    const size_t hs = (size_t)T * Kp;  // haplotype stride
     double mloc[2];
     {
         double sl[2] = {0, 0};
         for (int g = tid; g < T; g += NT) {
-            sl[0] += log(ld_cg(J.c + g));
-            sl[1] += log(ld_cg(J.c + T + g));
+            sl[0] += log(ld_cg(cG + g));
+            sl[1] += log(ld_cg(cG + T + g));
         }
         bsum.run(sl);
         mloc[0] = -sl[0];
@@ -173,20 +261,34 @@ __global__ void __launch_bounds__(NT) k_shard(BatchParams P, const JobDev* __res
     bool in_flip = false;
     double ap[2][EPT], e[2][EPT], en[2][EPT];
 #pragma unroll
-    for (int h = 0; h < 2; h++) Col<NT, EPT>::load(e[h], J.eG + ((size_t)h * T) * Kp, K, 0.0);
+    for (int h = 0; h < 2; h++) Col<NT, EPT>::load(e[h], eGg + h * hs, K, 0.0);
+    if (T > 1) {
+        prefetch_cols<NT>(eGg + Kp, hs, 2, Kp);
+        prefetch_cols<NT>(betaG + Kp, hs, 2, Kp);
+    }
     double clast[2] = {1, 1};
+    double nx_c[2] = {ld_cg(cG), ld_cg(cG + T)};
+    double nx_x = 0, nx_t1 = 0, nx_u = (T > 1) ? runif[0] : 0.0;
     for (int g = 0; g < T; g++) {
-        double orig_c[2];
-#pragma unroll
-        for (int h = 0; h < 2; h++) orig_c[h] = ld_cg(J.c + h * T + g);
+        const double orig_c[2] = {nx_c[0], nx_c[1]};
+        const double x = nx_x, t1 = nx_t1, u = nx_u;
         if (g + 1 < T) {
+            nx_c[0] = ld_cg(cG + g + 1);
+            nx_c[1] = ld_cg(cG + T + g + 1);
+            nx_x = tmG[2 * g];
+            nx_t1 = tmG[2 * g + 1];
+            if (g + 1 < T - 1) nx_u = runif[g + 1];
 #pragma unroll
-            for (int h = 0; h < 2; h++) Col<NT, EPT>::load(en[h], J.eG + ((size_t)h * T + g + 1) * Kp, K, 0.0);
+            for (int h = 0; h < 2; h++) Col<NT, EPT>::load(en[h], eGg + h * hs + (size_t)(g + 1) * Kp, K, 0.0);
         }
         double y[2][EPT];
         if (g < T - 1) {
 #pragma unroll
-            for (int h = 0; h < 2; h++) Col<NT, EPT>::load(y[h], J.beta + ((size_t)h * T + g) * Kp, K, 0.0);
+            for (int h = 0; h < 2; h++) Col<NT, EPT>::load(y[h], betaG + h * hs + (size_t)g * Kp, K, 0.0);
+        }
+        if (g + 2 < T) {
+            prefetch_cols<NT>(eGg + (size_t)(g + 2) * Kp, hs, 2, Kp);
+            prefetch_cols<NT>(betaG + (size_t)(g + 2) * Kp, hs, 2, Kp);
         }
         double cn[2];
         if (g == 0) {
@@ -214,13 +316,12 @@ __global__ void __launch_bounds__(NT) k_shard(BatchParams P, const JobDev* __res
                     e[1][i] = t;
                 }
 #pragma unroll
-                for (int h = 0; h < 2; h++) Col<NT, EPT>::store(e[h], J.eG + ((size_t)h * T + g) * Kp, K);
+                for (int h = 0; h < 2; h++) Col<NT, EPT>::store(e[h], eGg + h * hs + (size_t)g * Kp, K);
             }
             double sp[2];
 #pragma unroll
             for (int h = 0; h < 2; h++) sp[h] = Col<NT, EPT>::sum(ap[h]);
             bsum.run(sp);
-            const double x = J.tm[2 * (g - 1)], t1 = J.tm[2 * (g - 1) + 1];
             double sv[2];
 #pragma unroll
             for (int h = 0; h < 2; h++) {
@@ -242,12 +343,12 @@ __global__ void __launch_bounds__(NT) k_shard(BatchParams P, const JobDev* __res
         }
 #pragma unroll
         for (int h = 0; h < 2; h++) {
-            Col<NT, EPT>::store(ap[h], J.alpha + ((size_t)h * T + g) * Kp, K);
-            if (tid == 0) J.c[h * T + g] = cn[h];
+            Col<NT, EPT>::store(ap[h], alphaG + h * hs + (size_t)g * Kp, K);
+            if (tid == 0) cG[h * T + g] = cn[h];
             mlc[h] -= log(cn[h]);
             clast[h] = cn[h];
         }
-        if (tid == 0) J.rate[g] = in_flip ? 1.0 : 0.0;  // reads of this grid are relabelled 3 - H when set
+        if (tid == 0) rateG[g] = in_flip ? 1.0 : 0.0;  // reads of this grid are relabelled 3 - H when set
         if (g < T - 1) {
             double dv[4] = {0, 0, 0, 0};
 #pragma unroll
@@ -267,7 +368,7 @@ __global__ void __launch_bounds__(NT) k_shard(BatchParams P, const JobDev* __res
             const double probs2 = exp(diff);
             const double psum = probs1 + probs2;
             probs1 /= psum;
-            in_flip = runif[g] > probs1;
+            in_flip = u > probs1;
         }
 #pragma unroll
         for (int h = 0; h < 2; h++) {
@@ -279,92 +380,151 @@ __global__ void __launch_bounds__(NT) k_shard(BatchParams P, const JobDev* __res
     __syncthreads();
     // relabel the reads of every grid walked in flip mode
     for (int r = tid; r < R; r += NT) {
-        if (J.rate[J.wif0[r]] != 0.0) J.H[r] = 3 - J.H[r];
+        if (rateG[Js.wif0[r]] != 0.0) Js.H[r] = 3 - Js.H[r];
     }
-    // generic backward on the (possibly swapped) eMatGrid columns
-    for (int h = 0; h < 2; h++) {
-        const double* eG = J.eG + (size_t)h * T * Kp;
-        double* beta = J.beta + (size_t)h * T * Kp;
-        double b[EPT], ee[EPT], een[EPT];
+    // generic backward on the (possibly swapped) eMatGrid columns, both haplotypes in one walk
+    // (every thread re-reads only eMatGrid elements it wrote itself above, so no fence is needed)
+    {
+        double b[2][EPT], ee[2][EPT], een[2][EPT];
 #pragma unroll
-        for (int i = 0; i < EPT; i++) b[i] = (tid + i * NT < K) ? clast[h] : 0.0;
-        Col<NT, EPT>::store(b, beta + (size_t)(T - 1) * Kp, K);
-        if (T >= 2) Col<NT, EPT>::load(ee, eG + (size_t)(T - 1) * Kp, K, 0.0);
+        for (int h = 0; h < 2; h++) {
+#pragma unroll
+            for (int i = 0; i < EPT; i++) b[h][i] = (tid + i * NT < K) ? clast[h] : 0.0;
+            Col<NT, EPT>::store(b[h], betaG + h * hs + (size_t)(T - 1) * Kp, K);
+            if (T >= 2) Col<NT, EPT>::load(ee[h], eGg + h * hs + (size_t)(T - 1) * Kp, K, 0.0);
+        }
+        if (T >= 3) prefetch_cols<NT>(eGg + (size_t)(T - 2) * Kp, hs, 2, Kp);
+        double nb_c[2] = {0, 0}, nb_t0 = 0, nb_t1 = 0;
+        if (T >= 2) {
+            nb_c[0] = ld_cg(cG + T - 2);
+            nb_c[1] = ld_cg(cG + T + T - 2);
+            nb_t0 = tmG[2 * (T - 2)];
+            nb_t1 = tmG[2 * (T - 2) + 1];
+        }
         for (int g = T - 2; g >= 0; g--) {
-            if (g >= 1) Col<NT, EPT>::load(een, eG + (size_t)g * Kp, K, 0.0);
-            const double cg = ld_cg(J.c + h * T + g);
-            const double t0 = J.tm[2 * g], t1 = J.tm[2 * g + 1];
-            double sv[1] = {0};
+            const double cg[2] = {nb_c[0], nb_c[1]};
+            const double t0 = nb_t0, t1 = nb_t1;
+            if (g >= 1) {
 #pragma unroll
-            for (int i = 0; i < EPT; i++) {
-                b[i] = ee[i] * b[i];
-                sv[0] += prior * b[i];
+                for (int h = 0; h < 2; h++) Col<NT, EPT>::load(een[h], eGg + h * hs + (size_t)g * Kp, K, 0.0);
+                nb_c[0] = ld_cg(cG + g - 1);
+                nb_c[1] = ld_cg(cG + T + g - 1);
+                nb_t0 = tmG[2 * (g - 1)];
+                nb_t1 = tmG[2 * (g - 1) + 1];
+            }
+            if (g >= 2) prefetch_cols<NT>(eGg + (size_t)(g - 1) * Kp, hs, 2, Kp);
+            double sv[2] = {0, 0};
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+#pragma unroll
+                for (int i = 0; i < EPT; i++) {
+                    b[h][i] = ee[h][i] * b[h][i];
+                    sv[h] += prior * b[h][i];
+                }
             }
             bsum.run(sv);
-            const double x = t1 * sv[0];
 #pragma unroll
-            for (int i = 0; i < EPT; i++) b[i] = (tid + i * NT < K) ? cg * (x + t0 * b[i]) : 0.0;
-            Col<NT, EPT>::store(b, beta + (size_t)g * Kp, K);
+            for (int h = 0; h < 2; h++) {
+                const double x = t1 * sv[h];
 #pragma unroll
-            for (int i = 0; i < EPT; i++) ee[i] = een[i];
+                for (int i = 0; i < EPT; i++) b[h][i] = (tid + i * NT < K) ? cg[h] * (x + t0 * b[h][i]) : 0.0;
+                Col<NT, EPT>::store(b[h], betaG + h * hs + (size_t)g * Kp, K);
+#pragma unroll
+                for (int i = 0; i < EPT; i++) ee[h][i] = een[h][i];
+            }
         }
     }
 }
 
-// gamma -> hapProbs / genProbs.  grid = (T, jobs), 256 threads = 32 SNPs of the grid x 8 slices of K.
+// gamma -> hapProbs / genProbs.  grid = (T, jobs), 128 * NH threads: each haplotype owns four warps; a thread keeps the
+// 32 per-SNP alt sums of its k's in registers (k = j + 128 i), so gamma is formed once per (k, h) straight from the
+// alpha / beta columns and never staged.  ref sums are total - alt.  The warp-level reduction is transposed (31
+// shuffle-adds leave lane b with SNP b's total).
 // first = this is the first sampling sweep (assign), otherwise accumulate; scale = 1 / n_sample applied on the last.
-__global__ void __launch_bounds__(256) k_happrobs(BatchParams P, const JobDev* __restrict__ jobs, int first, int last, double scale) {
-    extern __shared__ __align__(16) unsigned char hsm[];
-    const JobDev& J = jobs[blockIdx.y];
-    if (*J.underflow) return;
-    const int g = blockIdx.x, K = P.K, Kp = P.Kp, T = P.T, NH = P.NH, nSNPs = P.nSNPs;
-    double* gam = reinterpret_cast<double*>(hsm);                   // [NH][Kp]
-    uint32_t* w = reinterpret_cast<uint32_t*>(gam + (size_t)NH * Kp);  // [Kp]
-    double* part = reinterpret_cast<double*>(w + Kp);               // [8][3][2][32]
+template <int NH>
+__global__ void __launch_bounds__(128 * NH, NH == 2 ? 2 : 1) k_happrobs(BatchParams P, const JobDev* __restrict__ jobs, int first, int last, double scale) {
+    __shared__ JobDev Js;
+    __shared__ double part[3][4][33];
     const int tid = threadIdx.x;
-    for (int h = 0; h < NH; h++) {
-        const double x = 1 / ld_cg(J.c + h * T + g);
-        const double* a = J.alpha + ((size_t)h * T + g) * Kp;
-        const double* b = J.beta + ((size_t)h * T + g) * Kp;
-        for (int k = tid; k < K; k += 256) gam[h * Kp + k] = (ld_stream(a + k) * ld_stream(b + k)) * x;
-    }
-    for (int k = tid; k < K; k += 256) w[k] = J.W[(size_t)g * Kp + k];
+    if (tid == 0) Js = jobs[blockIdx.y];
     __syncthreads();
-    const int bit = tid & 31, sl = tid >> 5;
-    double alt[3] = {0, 0, 0}, ref[3] = {0, 0, 0};
-    const int per = (K + 7) / 8;
-    const int k0 = sl * per, k1 = min(K, k0 + per);
-    for (int k = k0; k < k1; k++) {
-        const bool set = (w[k] >> bit) & 1u;
-        for (int h = 0; h < NH; h++) {
-            const double gk = gam[h * Kp + k];
-            if (set)
-                alt[h] += gk;
-            else
-                ref[h] += gk;
+    const JobDev& J = Js;
+    if (*J.underflow) return;
+    const int g = blockIdx.x, K = P.K, Kp = P.Kp, T = P.T, nSNPs = P.nSNPs;
+    const int h = tid >> 7, j = tid & 127, lane = tid & 31, wq = (tid >> 5) & 3;
+    double acc[32];
+#pragma unroll
+    for (int b = 0; b < 32; b++) acc[b] = 0.0;
+    double tot = 0.0;
+    {
+        const double* __restrict__ a = J.alpha + ((size_t)h * T + g) * Kp;
+        const double* __restrict__ bt = J.beta + ((size_t)h * T + g) * Kp;
+        const uint32_t* __restrict__ W = J.W + (size_t)g * Kp;
+        constexpr int U = 4;
+        // register double-buffer: the next chunk's loads are in flight while this chunk's 32 x U adds run
+        double av[2][U], bv[2][U];
+        uint32_t wv[2][U];
+        auto fetch = [&](int buf, int k0) {
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const int k = k0 + 128 * u;
+                const bool in = k < K;
+                av[buf][u] = in ? ld_stream(a + k) : 0.0;
+                bv[buf][u] = in ? ld_stream(bt + k) : 0.0;
+                wv[buf][u] = in ? __ldg(W + k) : 0u;
+            }
+        };
+        fetch(0, j);
+        const double x = 1 / ld_cg(J.c + h * T + g);
+        int cur = 0;
+#pragma unroll 1
+        for (int k0 = j; k0 < K; k0 += 128 * U * 2) {
+            // two chunks per trip so that the buffer index is a compile-time constant in each half
+            if (k0 + 128 * U < K) fetch(1, k0 + 128 * U);
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const double gk = (av[0][u] * bv[0][u]) * x;
+                tot += gk;
+#pragma unroll
+                for (int b = 0; b < 32; b++)
+                    if ((wv[0][u] >> b) & 1u) acc[b] += gk;
+            }
+            if (k0 + 128 * U < K) {
+                if (k0 + 128 * U * 2 < K) fetch(0, k0 + 128 * U * 2);
+#pragma unroll
+                for (int u = 0; u < U; u++) {
+                    const double gk = (av[1][u] * bv[1][u]) * x;
+                    tot += gk;
+#pragma unroll
+                    for (int b = 0; b < 32; b++)
+                        if ((wv[1][u] >> b) & 1u) acc[b] += gk;
+                }
+            }
         }
+        (void)cur;
     }
-    for (int h = 0; h < 3; h++) {
-        part[((sl * 3 + h) * 2 + 0) * 32 + bit] = alt[h];
-        part[((sl * 3 + h) * 2 + 1) * 32 + bit] = ref[h];
-    }
+    warp_transpose_reduce<32>(acc, lane);  // lane b now holds SNP b's alt sum of this warp
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, d);
+    part[h][wq][lane] = acc[0];
+    if (lane == 0) part[h][wq][32] = tot;
     __syncthreads();
     if (tid < 32) {
+        const int bit = tid;
         const int s = 32 * g + bit;
         if (s < nSNPs) {
-            double A[3], Rf[3];
-            for (int h = 0; h < 3; h++) {
-                A[h] = 0;
-                Rf[h] = 0;
-                for (int q = 0; q < 8; q++) {
-                    A[h] += part[((q * 3 + h) * 2 + 0) * 32 + bit];
-                    Rf[h] += part[((q * 3 + h) * 2 + 1) * 32 + bit];
-                }
+            double A[3] = {0, 0, 0}, Rf[3] = {0, 0, 0};
+#pragma unroll
+            for (int hh = 0; hh < NH; hh++) {
+                const double al = (part[hh][0][bit] + part[hh][1][bit]) + (part[hh][2][bit] + part[hh][3][bit]);
+                const double tt = (part[hh][0][32] + part[hh][1][32]) + (part[hh][2][32] + part[hh][3][32]);
+                A[hh] = al;
+                Rf[hh] = tt - al;
             }
             const double eps = P.ref_error, ome = 1 - P.ref_error;
             double hp[3], gM[3], gF[3] = {0, 0, 0};
             if (!P.rare_common) {
-                for (int h = 0; h < 3; h++) hp[h] = A[h] * ome + Rf[h] * eps;
+                for (int hh = 0; hh < 3; hh++) hp[hh] = A[hh] * ome + Rf[hh] * eps;
                 gM[0] = (1 - hp[0]) * (1 - hp[1]);
                 gM[1] = (hp[0] * (1 - hp[1]) + (1 - hp[0]) * hp[1]);
                 gM[2] = hp[0] * hp[1];
@@ -374,18 +534,18 @@ __global__ void __launch_bounds__(256) k_happrobs(BatchParams P, const JobDev* _
             } else {
                 // the reference accumulates into its (never re-zeroed) local matrix: hapLocal carries that state
                 const int type = J.snp_type[s];
-                for (int h = 0; h < 3; h++) {
-                    double v = J.hapLocal[h * (size_t)nSNPs + s];
-                    if (h < NH) {
+                for (int hh = 0; hh < 3; hh++) {
+                    double v = J.hapLocal[hh * (size_t)nSNPs + s];
+                    if (hh < NH) {
                         if (type == 0)
-                            v += A[h] * ome + Rf[h] * eps;
+                            v += A[hh] * ome + Rf[hh] * eps;
                         else if (type == 1)
                             v = eps;
                         else
-                            v += (A[h] + Rf[h]) * eps + A[h] * (1 - 2 * eps);
+                            v += (A[hh] + Rf[hh]) * eps + A[hh] * (1 - 2 * eps);
                     }
-                    hp[h] = v;
-                    J.hapLocal[h * (size_t)nSNPs + s] = v;
+                    hp[hh] = v;
+                    J.hapLocal[hh * (size_t)nSNPs + s] = v;
                 }
                 gM[0] = (1 - hp[0]) * (1 - hp[1]);
                 gM[1] = hp[0] * (1 - hp[1]) + hp[1] * (1 - hp[0]);
@@ -396,10 +556,10 @@ __global__ void __launch_bounds__(256) k_happrobs(BatchParams P, const JobDev* _
                     gF[2] = hp[0] * hp[2];
                 }
             }
-            for (int h = 0; h < 3; h++) {
+            for (int hh = 0; hh < 3; hh++) {
                 // output layout [3 x nSNPs] column-major (row = haplotype / genotype)
-                const size_t o = (size_t)s * 3 + h;
-                double vh = hp[h], vm = gM[h], vf = gF[h];
+                const size_t o = (size_t)s * 3 + hh;
+                double vh = hp[hh], vm = gM[hh], vf = gF[hh];
                 if (!first) {
                     vh += J.hapProbs[o];
                     vm += J.genM[o];

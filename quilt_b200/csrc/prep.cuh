@@ -188,8 +188,15 @@ __global__ void __launch_bounds__(TAB_WARPS * 32) k_build_tables(BatchParams P, 
     }
     __syncwarp();
     // 2. how many of the K haplotypes show each pattern
-    for (int k = lane; k < P.K; k += 32) atomicAdd(&hs[read_pattern_global(d, J.W, P.Kp, g, k)], 1);
-    __syncwarp();
+    // (lanes showing the same pattern elect one leader that adds their count: no shared-memory atomics)
+    for (int k0 = 0; k0 < P.K; k0 += 32) {
+        const int k = k0 + lane;
+        const bool in = k < P.K;
+        const uint32_t pat = in ? read_pattern_global(d, J.W, P.Kp, g, k) : 0xffffffffu;
+        const uint32_t peers = __match_any_sync(0xffffffffu, pat);
+        if (in && lane == __ffs(peers) - 1) hs[pat] += __popc(peers);
+        __syncwarp();
+    }
     // 3. rescale by the maximum over the haplotypes present, then floor (gibbs-small.cpp:235-262)
     bool degenerate = false;
     double d1 = 1.0;

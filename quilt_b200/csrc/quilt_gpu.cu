@@ -293,7 +293,8 @@ int get_panel(const QuiltPanel* p, PanelDev* out) {
 struct Geo {
     int NT, EPT;
 };
-bool pick_geo(int K, Geo* g) {
+bool pick_geo(int K, Geo* g, int NH = 2) {
+    if (NH == 3 && K > 2048) return false;  // three eMatGrid columns per stage: the shared-memory ring holds K <= 2048
     // QUILT_B200_GEO=NTxEPT overrides (experiments); default: few fat warps — the per-read chain is latency-bound, fewer
     // warps mean less redundant scalar work and a shorter cross-warp reduction, more elements per thread mean more ILP
     static int env_nt = -1, env_ept = 0;
@@ -580,7 +581,17 @@ int validate(const QuiltGibbsArgs& a) {
     if (a.nGrids != (a.nSNPs + 31) / 32) return set_err(QUILT_ERR_UNSUPPORTED, "grid must be 32 SNPs per grid (grid32)");
     if (a.K > 4096) return set_err(QUILT_ERR_UNSUPPORTED, "Ksubset > 4096 not supported yet");
     const bool diploid = (a.flags & QUILT_F_SAMPLE_IS_DIPLOID) != 0;
-    if (!diploid || a.ff != 0) return set_err(QUILT_ERR_UNSUPPORTED, "NIPT (ff > 0 / three haplotypes) not supported yet");
+    if (diploid && a.ff != 0) return set_err(QUILT_ERR_BAD_ARG, "sample_is_diploid with ff != 0");
+    if (!diploid) {
+        if (a.ff < 0 || a.ff >= 1) return set_err(QUILT_ERR_BAD_ARG, "ff outside [0, 1)");
+        if (a.K > 2048) return set_err(QUILT_ERR_UNSUPPORTED, "three-haplotype (NIPT) calls support Ksubset <= 2048");
+        if ((a.flags & QUILT_F_PERFORM_BLOCK_GIBBS) && a.n_block_gibbs_iterations > 0) {
+            for (int i = 0; i < a.n_block_gibbs_iterations; i++)
+                if (a.block_gibbs_iterations[i] >= 0 && a.block_gibbs_iterations[i] < a.n_gibbs_burn_in_its + a.n_gibbs_sample_its)
+                    return set_err(QUILT_ERR_UNSUPPORTED, "NIPT block Gibbs resampler not supported yet (run with perform_block_gibbs = FALSE)");
+        }
+        if (a.flags & QUILT_F_DO_SHARD_BLOCK_GIBBS) return set_err(QUILT_ERR_UNSUPPORTED, "shard pass is diploid-only (functions.R:2552-2556)");
+    }
     const bool rc = (a.flags & QUILT_F_MAKE_EMATREAD_RARE_COMMON) != 0;
     if (rc) {
         if (a.panel->nSNPs_all != a.nSNPs) return set_err(QUILT_ERR_BAD_ARG, "rare/common call: nSNPs must equal panel nSNPs_all");
@@ -625,23 +636,34 @@ void make_params(const QuiltGibbsArgs& a, BatchParams* P) {
     P->ref_error = a.panel->ref_error;
     P->rare_common = (a.flags & QUILT_F_MAKE_EMATREAD_RARE_COMMON) ? 1 : 0;
     P->Jmax = a.Jmax;
-    const char* bm = std::getenv("QUILT_B200_BMAX");
-    P->bmax = bm ? std::atoi(bm) : 0;
-    if (P->bmax > SW_BMAX) P->bmax = SW_BMAX;
+    const char* bm = std::getenv("QUILT_B200_DBG");
+    P->dbg = bm ? (uint32_t)std::atoi(bm) : 0u;
 }
 
+// the three-haplotype (NIPT) instance exists for geometries whose shared-memory ring fits (K <= 2048)
+template <int NT, int EPT>
+constexpr bool nipt_geo() {
+    return NT * EPT <= 2048;
+}
 template <int NT, int EPT>
 int sweep_occupancy(int Kp, int NH, int* occ, int* smem) {
     const SweepSmemLayout L = sweep_smem_layout(NT * EPT, NH, NT);
     *smem = L.total;
-    CK(cudaFuncSetAttribute(k_sweep<NT, EPT, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, k_sweep<NT, EPT, 2>, NT, L.total));
+    if (NH == 2) {
+        CK(cudaFuncSetAttribute(k_sweep<NT, EPT, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, k_sweep<NT, EPT, 2>, NT, L.total));
+    } else if constexpr (nipt_geo<NT, EPT>()) {
+        CK(cudaFuncSetAttribute(k_sweep<NT, EPT, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, k_sweep<NT, EPT, 3>, NT, L.total));
+    } else {
+        return set_err(QUILT_ERR_UNSUPPORTED, "no three-haplotype sweep kernel for this K");
+    }
     return QUILT_OK;
 }
 
 int setup_bucket(QuiltGpuBatch* B, Bucket& bk, size_t* mem_budget) {
     const BatchParams& P = bk.P;
-    if (!pick_geo(P.K, &bk.geo)) return set_err(QUILT_ERR_UNSUPPORTED, "Ksubset too large");
+    if (!pick_geo(P.K, &bk.geo, P.NH)) return set_err(QUILT_ERR_UNSUPPORTED, "Ksubset too large");
     int occ = 0, smem = 0;
     int rc = with_geo(bk.geo, [&](auto nt, auto ept) { return sweep_occupancy<decltype(nt)::value, decltype(ept)::value>(P.Kp, P.NH, &occ, &smem); });
     if (rc != QUILT_OK) return rc;
@@ -764,7 +786,13 @@ int run_wave_t(QuiltGpuBatch* B, Bucket& bk, int n, const JobDev* dj, bool timed
     const BatchParams& P = bk.P;
     const SweepSmemLayout L = sweep_smem_layout(NT * EPT, P.NH, NT);
     // (buckets of different K share a template instance: re-arm the opt-in shared-memory size for this one)
-    CK(cudaFuncSetAttribute(k_sweep<NT, EPT, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+    if (P.NH == 2) {
+        CK(cudaFuncSetAttribute(k_sweep<NT, EPT, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+    } else if constexpr (nipt_geo<NT, EPT>()) {
+        CK(cudaFuncSetAttribute(k_sweep<NT, EPT, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+    } else {
+        return set_err(QUILT_ERR_UNSUPPORTED, "no three-haplotype sweep kernel for this K");
+    }
     k_copy_H<<<dim3((bk.R_max + 255) / 256, n), 256, 0, g_stream>>>(dj);
     LAUNCHED();
     int rc = run_prep(B, bk, n, dj);
@@ -779,8 +807,6 @@ int run_wave_t(QuiltGpuBatch* B, Bucket& bk, int n, const JobDev* dj, bool timed
         LAUNCHED();
     }
     int episode = 0;
-    const size_t hsm = (size_t)P.NH * P.Kp * 8 + (size_t)P.Kp * 4 + 8 * 3 * 2 * 32 * 8;
-    CK(cudaFuncSetAttribute(k_happrobs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsm));
     for (int it = 0; it < P.n_its; it++) {
         cudaEvent_t e0 = nullptr, e1 = nullptr;
         if (timed) {
@@ -788,7 +814,11 @@ int run_wave_t(QuiltGpuBatch* B, Bucket& bk, int n, const JobDev* dj, bool timed
             CK(cudaEventCreate(&e1));
             CK(cudaEventRecord(e0, g_stream));
         }
-        k_sweep<NT, EPT, 2><<<n, NT, L.total, g_stream>>>(P, dj, it);
+        if (P.NH == 2) {
+            k_sweep<NT, EPT, 2><<<n, NT, L.total, g_stream>>>(P, dj, it);
+        } else if constexpr (nipt_geo<NT, EPT>()) {
+            k_sweep<NT, EPT, 3><<<n, NT, L.total, g_stream>>>(P, dj, it);
+        }
         LAUNCHED();
         if (timed) {
             CK(cudaEventRecord(e1, g_stream));
@@ -810,7 +840,10 @@ int run_wave_t(QuiltGpuBatch* B, Bucket& bk, int n, const JobDev* dj, bool timed
         }
         if (it >= P.n_burn) {
             const int n_sample = P.n_its - P.n_burn;
-            k_happrobs<<<dim3(P.T, n), 256, hsm, g_stream>>>(P, dj, it == P.n_burn, it == P.n_its - 1, 1.0 / double(n_sample));
+            if (P.NH == 2)
+                k_happrobs<2><<<dim3(P.T, n), 256, 0, g_stream>>>(P, dj, it == P.n_burn, it == P.n_its - 1, 1.0 / double(n_sample));
+            else
+                k_happrobs<3><<<dim3(P.T, n), 384, 0, g_stream>>>(P, dj, it == P.n_burn, it == P.n_its - 1, 1.0 / double(n_sample));
             LAUNCHED();
         }
     }

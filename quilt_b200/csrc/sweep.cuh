@@ -30,7 +30,7 @@ constexpr int SW_BMAX = 16;  // reads decided per round of the batched resampler
 static_assert(SW_MAXTAB >= (1 << NBMAX), "a single emission table must fit the staging buffer");
 
 struct SweepSmemLayout {
-    int off_bar, off_red, off_cnt, off_small[2], off_pat, off_part, off_rec, off_W, off_eG, total;
+    int off_bar, off_red, off_cnt, off_sc, off_small[2], off_pat, off_part, off_rec, off_W, off_eG, total;
     int small_desc, small_tab, small_U, small_H;
 };
 __host__ __device__ inline SweepSmemLayout sweep_smem_layout(int KA, int NH, int NT) {
@@ -43,6 +43,8 @@ __host__ __device__ inline SweepSmemLayout sweep_smem_layout(int KA, int NH, int
     o = (o + 127) & ~127;
     L.off_cnt = o;
     o += 128;
+    L.off_sc = o;  // per-stage scalar packages: 2 forward + 3 backward, 64 bytes each
+    o += 5 * 64 + 64;
     L.small_desc = 0;
     L.small_tab = SW_MAXR * 32;
     L.small_U = L.small_tab + SW_MAXTAB * 16;
@@ -315,6 +317,56 @@ __device__ __forceinline__ EV emission_at(const ESrc& S, int k) {
     return r;
 }
 
+// Column update after a label change (gibbs-nipt.cpp:1092-1110): divide the old label's alphaHat_m / ab_m / eMatGrid
+// by the read's column, multiply the new label's.  Elements are handled in chunks of UPD_CH with all shared-memory
+// loads (allele word, table entry, eMatGrid values) issued before any store, so the loads of a chunk pipeline instead
+// of serialising behind the previous element's store (the compiler cannot prove table and eMatGrid do not alias).
+constexpr int UPD_CH = 4;
+template <int NT, int EPT, int NH, int SRC, int HC, int HN, bool DODIV>
+__device__ __forceinline__ void upd_loop(double (&am)[NH][EPT], double (&ab)[NH][EPT], double* eg, int KA, const ESrc& S, int K, int tid) {
+    constexpr bool EGC = DODIV && (HC < 2 || NH == 3);
+    constexpr bool EGN = (HN < 2 || NH == 3);
+#pragma unroll
+    for (int i0 = 0; i0 < EPT; i0 += UPD_CH) {
+        EV ev[UPD_CH];
+        double gc[UPD_CH], gn[UPD_CH];
+#pragma unroll
+        for (int j = 0; j < UPD_CH; j++) {
+            const int k = tid + (i0 + j) * NT;
+            if (SRC != 3 || k < K) {
+                ev[j] = emission_at<SRC>(S, k);
+                if (EGC) gc[j] = eg[HC * KA + k];
+                if (EGN) gn[j] = eg[HN * KA + k];
+            } else {
+                ev[j].E = 1.0;
+                ev[j].invE = 1.0;
+                gc[j] = 0.0;
+                gn[j] = 0.0;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < UPD_CH; j++) {
+            const int i = i0 + j;
+            if (DODIV) {
+                am[HC][i] = (SRC == 3) ? am[HC][i] / ev[j].E : div_by(am[HC][i], ev[j].E, ev[j].invE);
+                ab[HC][i] = (SRC == 3) ? ab[HC][i] / ev[j].E : div_by(ab[HC][i], ev[j].E, ev[j].invE);
+                if (EGC) gc[j] = (SRC == 3) ? gc[j] / ev[j].E : div_by(gc[j], ev[j].E, ev[j].invE);
+            }
+            am[HN][i] *= ev[j].E;
+            ab[HN][i] *= ev[j].E;
+            if (EGN) gn[j] *= ev[j].E;
+        }
+#pragma unroll
+        for (int j = 0; j < UPD_CH; j++) {
+            const int k = tid + (i0 + j) * NT;
+            if (SRC != 3 || k < K) {
+                if (EGC) eg[HC * KA + k] = gc[j];
+                if (EGN) eg[HN * KA + k] = gn[j];
+            }
+        }
+    }
+}
+
 template <int NT, int EPT, int NH>
 __global__ void __launch_bounds__(NT, (NT * EPT <= 512 ? 4 : (NT * EPT <= 1024 ? 2 : 1))) k_sweep(BatchParams P, const JobDev* __restrict__ jobs, int iteration) {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -342,16 +394,23 @@ __global__ void __launch_bounds__(NT, (NT * EPT <= 512 ? 4 : (NT * EPT <= 1024 ?
     const bool record = (P.flags & QUILT_F_RECORD_READ_SET) != 0;
     const double one_over_K = P.one_over_K;
     const int32_t* __restrict__ rs = J.rs;
+    const int32_t* __restrict__ tsG = J.ts;
+    const double* __restrict__ tmG = J.tm;
     const double* __restrict__ U = J.runif_reads + (size_t)iteration * R;
+    double* __restrict__ alphaG = J.alpha;
+    double* __restrict__ betaG = J.beta;
+    double* __restrict__ eGg = J.eG;
+    double* cG = J.c;
 
     if (tid == 0) {
         mbar_init(&bar[0], 1);
         mbar_init(&bar[1], 1);
+        mbar_init(&bar[2], 1);
         fence_barrier_init();
     }
     if (tid < 16) cnt[tid] = 0;
     __syncthreads();
-    uint32_t n_use0 = 0, n_use1 = 0;  // completed uses of each stage barrier -> wait parity
+    uint32_t n_use0 = 0, n_use1 = 0, n_use2 = 0;  // completed uses of each stage barrier -> wait parity
 
     // staging of reads [ra, ra + n) with table entries [ta, ta + nt) into stage buffer s
     auto stage_small = [&](int s, int ra, int n, int ta, int nt, bool async) {
@@ -373,10 +432,20 @@ __global__ void __launch_bounds__(NT, (NT * EPT <= 512 ? 4 : (NT * EPT <= 1024 ?
     // ---- one package = everything grid g needs: eMatGrid columns, the allele words of grid g+1 (ring of 4:
     //      grid g uses words g-1 .. g+1 while package g+1 is already filling word g+2), and the read
     //      metadata of the grid when it fits one staging buffer
-    auto issue_pkg = [&](int g) {
+    auto issue_pkg = [&](int g, int r0, int r1, int t0, int t1) {
         const int s = g & 1;
-        const int r0 = rs[g], r1 = rs[g + 1];
         const int n_g = r1 - r0;
+        {
+            // scalars the serial chain needs at grid g: first reads / table offsets of the NEXT grid (so that its
+            // package can be issued without a dependent global load), the transition pair into g, the previous c of g
+            unsigned char* sc = smem + L.off_sc + s * 64;
+            if (tid == 0) cp_async4(sc + 0, rs + g + 1);
+            if (tid == 1 && g + 2 <= T) cp_async4(sc + 4, rs + g + 2);
+            if (tid == 2) cp_async4(sc + 8, tsG + g + 1);
+            if (tid == 3 && g + 2 <= T) cp_async4(sc + 12, tsG + g + 2);
+            if (tid == 4 && g >= 1) cp_async16(sc + 16, tmG + 2 * (g - 1));
+            if (tid >= 5 && tid < 5 + NH) cp_async8(sc + 32 + 8 * (tid - 5), cG + (tid - 5) * T + g);
+        }
         if (tid == 0) {
             uint32_t bytes = 0;
             if (n_g > 0 || g == 0) bytes += NH * Kp * 8;
@@ -395,7 +464,7 @@ __global__ void __launch_bounds__(NT, (NT * EPT <= 512 ? 4 : (NT * EPT <= 1024 ?
         }
         bool small_done = false;
         if (n_g > 0) {
-            const int t0 = J.ts[g], nt = J.ts[g + 1] - t0;
+            const int nt = t1 - t0;
             if (n_g <= SW_MAXR && nt <= SW_MAXTAB) {
                 stage_small(s, r0, n_g, t0, nt, true);
                 small_done = true;
@@ -421,24 +490,44 @@ __global__ void __launch_bounds__(NT, (NT * EPT <= 512 ? 4 : (NT * EPT <= 1024 ?
 #pragma unroll
     for (int h = 0; h < NH; h++) cfin[h] = 1;
 
-    issue_pkg(0);
+    // per-grid scalars arrive with the package (cp.async into the stage's scalar block): nothing on the serial chain
+    // waits for a dependent global load
+    int cur_r0 = rs[0], cur_t0 = tsG[0];
+    issue_pkg(0, cur_r0, rs[1], cur_t0, tsG[1]);
     // =============================================================== forward + read resampling
     for (int g = 0; g < T; g++) {
         wait_pkg(g);
-        if (g + 1 < T) issue_pkg(g + 1);
         const int s = g & 1;
-        const int r0 = rs[g], r1 = rs[g + 1];
+        const int32_t* sci = reinterpret_cast<const int32_t*>(smem + L.off_sc + s * 64);
+        const double* scd = reinterpret_cast<const double*>(sci);
+        const int r0 = cur_r0, r1 = sci[0];
+        const int ts0 = cur_t0, ts1 = sci[2];
+        const int nx_r1 = sci[1], nx_t1 = sci[3];
+        const double tm_x = scd[2], tm_t1 = scd[3];
         const int n_g = r1 - r0;
         const bool has = n_g > 0;
         double* eg = eGs + (size_t)(s * NH) * KA;
         double c_old[NH];
 #pragma unroll
-        for (int h = 0; h < NH; h++) c_old[h] = ld_cg(J.c + h * T + g);
+        for (int h = 0; h < NH; h++) c_old[h] = scd[4 + h];
+        cur_r0 = r1;
+        cur_t0 = ts1;
         double ab[NH][EPT];
         // beta of this grid goes straight into the ab registers (consumed after the forward step)
         if (has) {
 #pragma unroll
-            for (int h = 0; h < NH; h++) Col<NT, EPT>::load(ab[h], J.beta + ((size_t)h * T + g) * Kp, K, 0.0);
+            for (int h = 0; h < NH; h++) Col<NT, EPT>::load(ab[h], betaG + ((size_t)h * T + g) * Kp, K, 0.0);
+        }
+        if (g + 1 < T) {
+            if (!(P.dbg & 2)) issue_pkg(g + 1, r1, nx_r1, ts1, nx_t1);
+            // pull the next grid's beta columns towards L2 (one 128-byte line per 16 doubles)
+            if (nx_r1 > r1 && !(P.dbg & 1)) {
+                const int lines = (NH * Kp) >> 4;
+                for (int l = tid; l < lines; l += NT) {
+                    const int h = l / (Kp >> 4), q = l - h * (Kp >> 4);
+                    prefetch_l2(betaG + ((size_t)h * T + g + 1) * Kp + (q << 4));
+                }
+            }
         }
         double cnew[NH];
         if (g == 0) {
@@ -466,7 +555,7 @@ __global__ void __launch_bounds__(NT, (NT * EPT <= 512 ? 4 : (NT * EPT <= 1024 ?
 #pragma unroll
             for (int h = 0; h < NH; h++) sp[h] = Col<NT, EPT>::sum(am[h]);
             bsum.run(sp);
-            const double x = J.tm[2 * (g - 1)], t1 = J.tm[2 * (g - 1) + 1];
+            const double x = tm_x, t1 = tm_t1;
             double sv[NH];
 #pragma unroll
             for (int h = 0; h < NH; h++) {
@@ -495,6 +584,7 @@ __global__ void __launch_bounds__(NT, (NT * EPT <= 512 ? 4 : (NT * EPT <= 1024 ?
             }
         }
         // am now holds alphaHat_t[:, g]; it stays in registers as the previous column of the next grid
+        if (g + 1 < T && (P.dbg & 2)) issue_pkg(g + 1, r1, nx_r1, ts1, nx_t1);  // experiment: issue after the forward step
         bool changed = false;
         if (has) {
             const unsigned char* sm = smem + L.off_small[s];
@@ -550,22 +640,7 @@ __global__ void __launch_bounds__(NT, (NT * EPT <= 512 ? 4 : (NT * EPT <= 1024 ?
             // divide the old label's alphaHat_m / ab_m / eMatGrid by the read's column, multiply the new label's
             // (gibbs-nipt.cpp:1092-1110).  Divisions: q = a * (1/e) corrected by one fma residual step = the correctly
             // rounded a / e (DESIGN.md "arithmetic"); dense columns divide.
-#define QB_UPD_LOOP(SRC, HC, HN, DODIV)                                                                   \
-    _Pragma("unroll") for (int i = 0; i < EPT; i++) {                                                     \
-        const int k = tid + i * NT;                                                                       \
-        if (SRC != 3 || k < K) {                                                                          \
-            const EV ev = emission_at<SRC>(S, k);                                                         \
-            if (DODIV) {                                                                                  \
-                am[HC][i] = (SRC == 3) ? am[HC][i] / ev.E : div_by(am[HC][i], ev.E, ev.invE);             \
-                ab[HC][i] = (SRC == 3) ? ab[HC][i] / ev.E : div_by(ab[HC][i], ev.E, ev.invE);             \
-                if (HC < 2 || NH == 3)                                                                    \
-                    eg[HC * KA + k] = (SRC == 3) ? eg[HC * KA + k] / ev.E : div_by(eg[HC * KA + k], ev.E, ev.invE); \
-            }                                                                                             \
-            am[HN][i] *= ev.E;                                                                            \
-            ab[HN][i] *= ev.E;                                                                            \
-            if (HN < 2 || NH == 3) eg[HN * KA + k] *= ev.E;                                               \
-        }                                                                                                 \
-    }
+#define QB_UPD_LOOP(SRC, HC, HN, DODIV) upd_loop<NT, EPT, NH, SRC, HC, HN, DODIV>(am, ab, eg, KA, S, K, tid);
 #define QB_UPD_LABELS(SRC, normal, hC, hN)                                                                \
     if (normal) {                                                                                         \
         if (hC == 0 && hN == 1) {                                                                         \
@@ -704,10 +779,10 @@ __global__ void __launch_bounds__(NT, (NT * EPT <= 512 ? 4 : (NT * EPT <= 1024 ?
             };
 
             // ---------------------------------------------------------------- the grid's reads, chunk by chunk
-            const bool prestaged = (n_g <= SW_MAXR) && (J.ts[g + 1] - J.ts[g] <= SW_MAXTAB);
+            const bool prestaged = (n_g <= SW_MAXR) && (ts1 - ts0 <= SW_MAXTAB);
             const bool special_its = iterative && iteration <= 1;  // sweeps with pass-through / initialisation reads
             int c0 = 0;
-            uint32_t tab0 = (uint32_t)J.ts[g];
+            uint32_t tab0 = (uint32_t)ts0;
             while (c0 < n_g) {
                 int cn = n_g;
                 if (!prestaged) {
@@ -824,15 +899,15 @@ __global__ void __launch_bounds__(NT, (NT * EPT <= 512 ? 4 : (NT * EPT <= 1024 ?
         }
 #pragma unroll
         for (int h = 0; h < NH; h++) {
-            Col<NT, EPT>::store(am[h], J.alpha + ((size_t)h * T + g) * Kp, K);
+            Col<NT, EPT>::store(am[h], alphaG + ((size_t)h * T + g) * Kp, K);
             if (changed) {
+                // (loads first: a generic store may alias shared memory, so interleaving would serialise them)
+                double tmp[EPT];
 #pragma unroll
-                for (int i = 0; i < EPT; i++) {
-                    const int k = tid + i * NT;
-                    if (k < K) st_stream(J.eG + ((size_t)h * T + g) * Kp + k, eg[h * KA + k]);
-                }
+                for (int i = 0; i < EPT; i++) tmp[i] = eg[h * KA + tid + i * NT];
+                Col<NT, EPT>::store(tmp, eGg + ((size_t)h * T + g) * Kp, K);
             }
-            if (tid == 0) J.c[h * T + g] = cnew[h];
+            if (tid == 0) cG[h * T + g] = cnew[h];
             cfin[h] = cnew[h];
         }
     }
@@ -849,41 +924,58 @@ __global__ void __launch_bounds__(NT, (NT * EPT <= 512 ? 4 : (NT * EPT <= 1024 ?
         for (int h = 0; h < NH; h++) {
 #pragma unroll
             for (int i = 0; i < EPT; i++) b[h][i] = (tid + i * NT < K) ? cfin[h] : 0.0;
-            Col<NT, EPT>::store(b[h], J.beta + ((size_t)h * T + (T - 1)) * Kp, K);
+            Col<NT, EPT>::store(b[h], betaG + ((size_t)h * T + (T - 1)) * Kp, K);
         }
-        // stage ring reused: step g needs eMatGrid[:, g + 1]
+        // Stage ring for the backward walk: step g needs eMatGrid[:, g + 1], c[g] and the transition pair g.  The
+        // allele-word ring is idle now and serves as a third column stage (diploid), so packages run NSB - 1 steps
+        // ahead of their use; the step's scalars ride along by cp.async.
+        constexpr int NSB = (NH == 2) ? 3 : 2;
+        auto bstage = [&](int q) -> double* { return q < 2 ? eGs + (size_t)(q * NH) * KA : reinterpret_cast<double*>(Wr); };
         auto issue_b = [&](int g) {
-            const int s = g & 1;
+            const int q = ((T - 2) - g) % NSB;
             if (tid == 0) {
-                const bool has1 = rs[g + 2] > rs[g + 1];
-                if (has1) {
-                    mbar_arrive_expect_tx(&bar[s], NH * Kp * 8);
+                mbar_arrive_expect_tx(&bar[q], NH * Kp * 8);
+                double* dst = bstage(q);
 #pragma unroll
-                    for (int h = 0; h < NH; h++) bulk_g2s(eGs + (size_t)(s * NH + h) * KA, J.eG + ((size_t)h * T + g + 1) * Kp, Kp * 8, &bar[s]);
-                } else {
-                    mbar_arrive(&bar[s]);
-                }
+                for (int h = 0; h < NH; h++) bulk_g2s(dst + (size_t)h * KA, eGg + ((size_t)h * T + g + 1) * Kp, Kp * 8, &bar[q]);
             }
+            unsigned char* sc = smem + L.off_sc + (2 + q) * 64;
+            if (tid == 0) cp_async4(sc + 0, rs + g + 1);
+            if (tid == 1) cp_async4(sc + 4, rs + g + 2);
+            if (tid == 4) cp_async16(sc + 16, tmG + 2 * g);
+            if (tid >= 5 && tid < 5 + NH) cp_async8(sc + 32 + 8 * (tid - 5), cG + (tid - 5) * T + g);
         };
-        if (T >= 2) issue_b(T - 2);
+#pragma unroll
+        for (int j = 0; j < NSB - 1; j++) {
+            if (T - 2 - j >= 0) issue_b(T - 2 - j);
+            cp_async_commit();
+        }
         for (int g = T - 2; g >= 0; g--) {
-            const int s = g & 1;
-            if (s == 0) {
+            const int q = ((T - 2) - g) % NSB;
+            // refill the stage step g + 1 used: every thread is past that step's block sum, i.e. done reading it
+            if (g - (NSB - 1) >= 0) issue_b(g - (NSB - 1));
+            cp_async_commit();
+            cp_async_wait_group<NSB - 1>();
+            if (q == 0) {
                 mbar_wait(&bar[0], n_use0 & 1);
                 n_use0++;
-            } else {
+            } else if (q == 1) {
                 mbar_wait(&bar[1], n_use1 & 1);
                 n_use1++;
+            } else {
+                mbar_wait(&bar[2], n_use2 & 1);
+                n_use2++;
             }
-            __syncthreads();  // everyone is done with the other stage (step g + 1) before it is refilled
-            if (g >= 1) issue_b(g - 1);
-            const bool has1 = rs[g + 2] > rs[g + 1];
-            const double* eg = eGs + (size_t)(s * NH) * KA;
-            const double t0 = J.tm[2 * g], t1 = J.tm[2 * g + 1];
+            __syncthreads();  // the other threads' cp.async scalars are visible
+            const int32_t* sci = reinterpret_cast<const int32_t*>(smem + L.off_sc + (2 + q) * 64);
+            const double* scd = reinterpret_cast<const double*>(sci);
+            const bool has1 = sci[1] > sci[0];
+            const double* eg = bstage(q);
+            const double t0 = scd[2], t1 = scd[3];
             double cg[NH], sv[NH];
 #pragma unroll
             for (int h = 0; h < NH; h++) {
-                cg[h] = ld_cg(J.c + h * T + g);
+                cg[h] = scd[4 + h];
                 if (has1) {
 #pragma unroll
                     for (int i = 0; i < EPT; i++) {
@@ -899,7 +991,7 @@ __global__ void __launch_bounds__(NT, (NT * EPT <= 512 ? 4 : (NT * EPT <= 1024 ?
                 const double x = t1 * sv[h] * one_over_K;
 #pragma unroll
                 for (int i = 0; i < EPT; i++) b[h][i] = (tid + i * NT < K) ? cg[h] * (x + t0 * b[h][i]) : 0.0;
-                Col<NT, EPT>::store(b[h], J.beta + ((size_t)h * T + g) * Kp, K);
+                Col<NT, EPT>::store(b[h], betaG + ((size_t)h * T + g) * Kp, K);
             }
         }
     }

@@ -105,7 +105,7 @@ struct BatchParams {
     double ref_error;
     int32_t rare_common;
     int32_t Jmax;
-    int32_t bmax;  // reads per round of the batched resampler (0/1: one read at a time)
+    uint32_t dbg;  // experiment switches (env QUILT_B200_DBG; 0 in production)
 };
 
 }  // namespace qb
