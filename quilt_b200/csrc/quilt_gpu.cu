@@ -26,6 +26,7 @@
 #include <vector>
 
 #include "../../include/quilt_b200.h"
+#include "block_nipt.cuh"
 #include "passes.cuh"
 #include "prep.cuh"
 #include "sweep.cuh"
@@ -338,7 +339,7 @@ int with_geo(const Geo& g, F&& f) {
 
 // ------------------------------------------------------------------------------------------------ jobs
 struct JobLayoutIn {  // byte offsets inside the job's input region
-    size_t which, rs, roff, u, pRA, wif0, ts, dense_reads, runif_reads, runif_shard, tm, desc, H0, end;
+    size_t which, rs, roff, u, pRA, wif0, ts, dense_reads, runif_reads, runif_shard, tm, desc, H0, runif_block, runif_H_class, L_grid, end;
 };
 struct JobLayoutOut {
     size_t underflow, lik, hap, genM, genF, H, Hclass, cat, end;
@@ -366,7 +367,7 @@ struct Bucket {
     int R_max = 0, n_tab_max = 0, n_dense_max = 0;
     size_t slot_bytes = 0;
     // slot layout
-    size_t o_alpha, o_beta, o_eG, o_c, o_W, o_Wc, o_tabs, o_dense, o_xprob, o_snp_type, o_rate, o_hapLocal;
+    size_t o_alpha, o_beta, o_eG, o_c, o_W, o_Wc, o_tabs, o_dense, o_xprob, o_snp_type, o_rate, o_hapLocal, o_blk;
     char* slots = nullptr;  // into the batch's slot arena (buckets run one after the other and share it)
     DBuf djobs;
     HBuf hjobs;
@@ -505,6 +506,10 @@ void layout_in(HostJob& j) {
     L.tm = o, o += al((size_t)std::max(T - 1, 1) * 16);
     L.desc = o, o += al((size_t)R * sizeof(ReadDesc));
     L.H0 = o, o += al((size_t)R * 4);
+    const bool nipt_block = !(a.flags & QUILT_F_SAMPLE_IS_DIPLOID) && (a.flags & QUILT_F_PERFORM_BLOCK_GIBBS) && j.n_ep > 0;
+    L.runif_block = o, o += al(nipt_block ? (size_t)j.n_ep * R * 8 : 0);
+    L.runif_H_class = o, o += al(nipt_block ? (size_t)j.n_ep * R * 8 : 0);
+    L.L_grid = o, o += al(nipt_block ? (size_t)T * 4 : 0);
     L.end = o;
     JobLayoutOut& O = j.lo;
     o = 0;
@@ -565,14 +570,20 @@ void fill_in(const HostJob& j, char* base) {
     if (T > 1) std::memcpy(base + L.tm, a.transMatRate_tc_H, (size_t)(T - 1) * 16);
     std::memcpy(base + L.desc, j.desc.data(), (size_t)R * sizeof(ReadDesc));
     std::memcpy(base + L.H0, a.H0, (size_t)R * 4);
+    const bool nipt_block = !(a.flags & QUILT_F_SAMPLE_IS_DIPLOID) && (a.flags & QUILT_F_PERFORM_BLOCK_GIBBS) && j.n_ep > 0;
+    if (nipt_block) {
+        std::memcpy(base + L.runif_block, a.runif_block, (size_t)j.n_ep * R * 8);
+        std::memcpy(base + L.runif_H_class, a.runif_H_class, (size_t)j.n_ep * R * 8);
+        std::memcpy(base + L.L_grid, a.L_grid, (size_t)T * 4);
+    }
 }
 
 typedef std::tuple<int, int, int, int, uint32_t, int, int, double, double, double, double, int, std::vector<int>> BucketKey;
 
 BucketKey bucket_key(const QuiltGibbsArgs& a) {
     std::vector<int> bi(a.block_gibbs_iterations, a.block_gibbs_iterations + a.n_block_gibbs_iterations);
-    return BucketKey(a.K, a.nGrids, a.nSNPs, 0, a.flags, a.n_gibbs_burn_in_its, a.n_gibbs_sample_its, a.ff, a.maxDifferenceBetweenReads,
-                     a.class_sum_cutoff, 0.0, a.Jmax, bi);
+    return BucketKey(a.K, a.nGrids, a.nSNPs, a.shuffle_bin_radius, a.flags, a.n_gibbs_burn_in_its, a.n_gibbs_sample_its, a.ff,
+                     a.maxDifferenceBetweenReads, a.class_sum_cutoff, a.block_gibbs_quantile_prob, a.Jmax, bi);
 }
 
 int validate(const QuiltGibbsArgs& a) {
@@ -586,9 +597,8 @@ int validate(const QuiltGibbsArgs& a) {
         if (a.ff < 0 || a.ff >= 1) return set_err(QUILT_ERR_BAD_ARG, "ff outside [0, 1)");
         if (a.K > 2048) return set_err(QUILT_ERR_UNSUPPORTED, "three-haplotype (NIPT) calls support Ksubset <= 2048");
         if ((a.flags & QUILT_F_PERFORM_BLOCK_GIBBS) && a.n_block_gibbs_iterations > 0) {
-            for (int i = 0; i < a.n_block_gibbs_iterations; i++)
-                if (a.block_gibbs_iterations[i] >= 0 && a.block_gibbs_iterations[i] < a.n_gibbs_burn_in_its + a.n_gibbs_sample_its)
-                    return set_err(QUILT_ERR_UNSUPPORTED, "NIPT block Gibbs resampler not supported yet (run with perform_block_gibbs = FALSE)");
+            if (!a.runif_block || !a.runif_H_class || !a.L_grid)
+                return set_err(QUILT_ERR_BAD_ARG, "NIPT block Gibbs needs runif_block, runif_H_class and L_grid");
         }
         if (a.flags & QUILT_F_DO_SHARD_BLOCK_GIBBS) return set_err(QUILT_ERR_UNSUPPORTED, "shard pass is diploid-only (functions.R:2552-2556)");
     }
@@ -636,6 +646,18 @@ void make_params(const QuiltGibbsArgs& a, BatchParams* P) {
     P->ref_error = a.panel->ref_error;
     P->rare_common = (a.flags & QUILT_F_MAKE_EMATREAD_RARE_COMMON) ? 1 : 0;
     P->Jmax = a.Jmax;
+    P->shuffle_bin_radius = a.shuffle_bin_radius;
+    P->block_q = a.block_gibbs_quantile_prob;
+    {
+        // rcpp_get_log_p_H_class2 (gibbs-nipt-block.cpp:169-208): terms of n1 .. n6, branch chosen by ff
+        const double ff = a.ff;
+        P->lhc[0] = std::log(0.5);
+        P->lhc[1] = (ff == 1) ? std::log(0.001) : std::log(0.5 - ff * 0.5);
+        P->lhc[2] = (ff == 0) ? std::log(0.001) : std::log(ff * 0.5);
+        P->lhc[3] = std::log(1 - ff * 0.5);
+        P->lhc[4] = std::log(1 * 0.5 + ff * 0.5);
+        P->lhc[5] = std::log(1 * 0.5);
+    }
     const char* bm = std::getenv("QUILT_B200_DBG");
     P->dbg = bm ? (uint32_t)std::atoi(bm) : 0u;
 }
@@ -688,6 +710,7 @@ int setup_bucket(QuiltGpuBatch* B, Bucket& bk, size_t* mem_budget) {
     bk.o_snp_type = o, o += al(P.nSNPs);
     bk.o_rate = o, o += al((size_t)P.T * 8);
     bk.o_hapLocal = o, o += al(P.rare_common ? (size_t)P.nSNPs * 24 : 0);
+    bk.o_blk = o, o += al(P.NH == 3 ? BlockScratch::bytes(P.T) : 0);
     bk.slot_bytes = o;
     int cap = g_sms * occ;
     const size_t by_mem = std::max<size_t>(1, *mem_budget / std::max<size_t>(bk.slot_bytes, 1));
@@ -733,6 +756,10 @@ void make_jobdev(const QuiltGpuBatch* B, const Bucket& bk, const HostJob& j, int
     D->runif_shard = (const double*)(in + j.li.runif_shard);
     D->tm = (const double*)(in + j.li.tm);
     D->H0 = (const int32_t*)(in + j.li.H0);
+    D->runif_block = (const double*)(in + j.li.runif_block);
+    D->runif_H_class = (const double*)(in + j.li.runif_H_class);
+    D->L_grid = (const int32_t*)(in + j.li.L_grid);
+    D->blk = (unsigned char*)(s + bk.o_blk);
     D->H = (int32_t*)(out + j.lo.H);
     D->Hclass = (int32_t*)(out + j.lo.Hclass);
     D->lik = (double*)(out + j.lo.lik);
@@ -832,6 +859,28 @@ int run_wave_t(QuiltGpuBatch* B, Bucket& bk, int n, const JobDev* dj, bool timed
             // reference's local matrices is zero, every permutation score is NaN and the identity is always kept
             // (DESIGN.md "block Gibbs, diploid"); the trailing backward passes reproduce beta unchanged.  Only the
             // shard pass alters state.
+            if (P.NH == 3) {
+                // three haplotypes: the real block resampler (block_nipt.cuh), then labels redrawn from H_class and the
+                // whole state rebuilt (gibbs-nipt-block.cpp:1900-1958; the generic backward is overwritten by the fast one)
+                if constexpr (nipt_geo<NT, EPT>()) {
+                    if (P.T > 2) {
+                        k_block_rate<<<dim3(P.T, n), 256, 0, g_stream>>>(P, dj);
+                        LAUNCHED();
+                        k_block_define<<<n, 32, 0, g_stream>>>(P, dj);
+                        LAUNCHED();
+                        k_block_nipt<NT, EPT><<<n, NT, 0, g_stream>>>(P, dj, episode);
+                        LAUNCHED();
+                    }
+                    k_sample_H<<<n, 256, 0, g_stream>>>(P, dj, episode);
+                    LAUNCHED();
+                    k_make_eG<<<dim3(P.T, n), 256, 0, g_stream>>>(P, dj);
+                    LAUNCHED();
+                    k_fb_generic<NT, EPT><<<dim3(n, P.NH), NT, 0, g_stream>>>(P, dj, 0);
+                    LAUNCHED();
+                    k_bwd_fast<NT, EPT><<<dim3(n, P.NH), NT, 0, g_stream>>>(P, dj);
+                    LAUNCHED();
+                }
+            }
             if (bk.do_shard && P.T > 1) {
                 k_shard<NT, EPT><<<n, NT, 0, g_stream>>>(P, dj, episode);
                 LAUNCHED();

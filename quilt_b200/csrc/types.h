@@ -68,6 +68,11 @@ struct JobDev {
     const double* runif_shard;  // [n_ep][T - 1]
     const double* tm;           // [T - 1][2] (sigma, 1 - sigma)
     const int32_t* H0;          // [R] starting labels
+    // three-haplotype (NIPT) block Gibbs only
+    const double* runif_block;    // [n_ep][R]
+    const double* runif_H_class;  // [n_ep][R]
+    const int32_t* L_grid;        // [T]
+    unsigned char* blk;           // per-slot scratch of the block definition / resampler (layout: BlockScratch)
     // outputs / evolving small state
     int32_t* H;       // [R] 1-based labels
     int32_t* Hclass;  // [R]
@@ -93,6 +98,50 @@ struct PanelDev {
     double ref_error;
 };
 
+// scratch of the NIPT block Gibbs episode, carved out of JobDev::blk (all arrays have T entries unless noted)
+struct BlockScratch {
+    double* rate2;      // sigma-weighted switch rate per grid boundary
+    double* smoothed;   // smoothed rate
+    double* lcs;        // [T][9] log c of the nine forward vectors (slot h, emission label i)
+    double* logc;       // [3][T] log c_h[g] workspace
+    int32_t* idx_a;     // merge-sort index buffers
+    int32_t* idx_b;
+    int32_t* to_keep;
+    int32_t* blocked_grid;
+    int32_t* grid_start;
+    int32_t* grid_end;
+    int32_t* reads_start;
+    int32_t* reads_end;
+    int32_t* grid_where;
+    int32_t* rmflag;    // blocks without reads
+    uint8_t* available;
+    int32_t* n_blocks;  // [1]
+    __host__ __device__ static size_t bytes(int T) { return (size_t)T * (8 * (2 + 9 + 3) + 4 * 10 + 1) + 64 + 16 * 16; }
+    __host__ __device__ void carve(unsigned char* p, int T) {
+        auto take = [&](size_t n) {
+            unsigned char* q = p;
+            p += (n + 15) & ~(size_t)15;
+            return q;
+        };
+        rate2 = (double*)take((size_t)T * 8);
+        smoothed = (double*)take((size_t)T * 8);
+        lcs = (double*)take((size_t)T * 72);
+        logc = (double*)take((size_t)T * 24);
+        idx_a = (int32_t*)take((size_t)T * 4);
+        idx_b = (int32_t*)take((size_t)T * 4);
+        to_keep = (int32_t*)take((size_t)T * 4);
+        blocked_grid = (int32_t*)take((size_t)T * 4);
+        grid_start = (int32_t*)take((size_t)T * 4);
+        grid_end = (int32_t*)take((size_t)T * 4);
+        reads_start = (int32_t*)take((size_t)T * 4);
+        reads_end = (int32_t*)take((size_t)T * 4);
+        grid_where = (int32_t*)take((size_t)T * 4);
+        rmflag = (int32_t*)take((size_t)T * 4);
+        available = (uint8_t*)take((size_t)T);
+        n_blocks = (int32_t*)take(64);
+    }
+};
+
 struct BatchParams {
     int32_t K, Kp, T, NH, nSNPs, n_its, n_burn;
     uint32_t flags;
@@ -106,6 +155,10 @@ struct BatchParams {
     int32_t rare_common;
     int32_t Jmax;
     uint32_t dbg;  // experiment switches (env QUILT_B200_DBG; 0 in production)
+    // NIPT block Gibbs (gibbs-nipt-block.cpp): host-evaluated libm constants so that the scores use the reference's values
+    int32_t shuffle_bin_radius;
+    double block_q;          // block_gibbs_quantile_prob
+    double lhc[6];           // log terms of rcpp_get_log_p_H_class2 for n1..n6 (gibbs-nipt-block.cpp:169-208)
 };
 
 }  // namespace qb

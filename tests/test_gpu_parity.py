@@ -182,6 +182,37 @@ def test_gibbs_production_all_snps(gpu, oracle, small_world, small_reads, K):
     _compare(f"all-SNP K={K}", g, o)
 
 
+@pytest.mark.parametrize("K", [200, 600, 1500])
+@pytest.mark.parametrize("iterative", [False, True])
+@pytest.mark.parametrize("ff", [0.1, 0.25])
+def test_gibbs_nipt_sweeps(gpu, oracle, small_world, small_reads, K, iterative, ff):
+    """three haplotypes (NIPT, ff > 0): 6 + 2 sweeps of the general read-label resampler, no block Gibbs"""
+    w = small_world if K <= 500 else synth.make_world(77 + K, K_full=K + 100, nSNPs=2240, region_bp=210_000)
+    sr = small_reads if K <= 500 else synth.make_sample_reads(w, K, coverage=0.5, region_bp=210_000)
+    call = synth.make_call(w, sr.common, 31, K=K, first_iteration=iterative, ff=ff, n_burn_in=6, n_sample=2, block_its=())
+    g, o = _run_both(gpu, oracle, call)
+    _compare(f"NIPT sweeps K={K} iterative={iterative} ff={ff}", g, o)
+
+
+@pytest.mark.parametrize("K", [200, 600])
+def test_gibbs_nipt_block_short(gpu, oracle, small_world, small_reads, K):
+    """NIPT with one block-Gibbs episode after the second sweep: bisects define-blocks / resampler / re-forward"""
+    call = synth.make_call(small_world, small_reads.common, 32, K=K, first_iteration=False, ff=0.2, n_burn_in=3, n_sample=1, block_its=(1,))
+    g, o = _run_both(gpu, oracle, call)
+    _compare(f"NIPT block short K={K}", g, o)
+
+
+@pytest.mark.parametrize("K", [200, 600, 2048])
+@pytest.mark.parametrize("iterative", [False, True])
+def test_gibbs_nipt_production(gpu, oracle, K, iterative):
+    """the production NIPT call: 20 + 1 sweeps, block Gibbs (six label permutations, H_class resampling) at 3/6/9"""
+    w = synth.make_world(55 + K, K_full=max(K + 100, 700), nSNPs=2240, region_bp=210_000)
+    sr = synth.make_sample_reads(w, K + 1, coverage=0.5, region_bp=210_000)
+    call = synth.make_call(w, sr.common, 33, K=K, first_iteration=iterative, ff=0.1)
+    g, o = _run_both(gpu, oracle, call)
+    _compare(f"NIPT production K={K} iterative={iterative}", g, o)
+
+
 def test_gibbs_unsorted_haps_and_sampling_its(gpu, oracle, small_world, small_reads):
     """which_haps_to_use unsorted (after mspbwt selection, Appendix D.10), 3 sampling sweeps averaged"""
     call = synth.make_call(small_world, small_reads.common, 25, K=300, sort_haps=False, first_iteration=False, n_burn_in=5, n_sample=3, block_its=(2,))
