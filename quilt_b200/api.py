@@ -84,13 +84,31 @@ class GpuLib(cabi._LibAPI):
     # ---- batches
     def gibbs_batch(self, calls: Sequence[GibbsCall]) -> List[GibbsResult]:
         """n independent calls through quilt_gpu_gibbs_batch (host buffers in, host buffers out)."""
-        b = Batch(self, calls)
-        try:
-            b.run()
-            b.sync()
-            return b.fetch()
-        finally:
-            b.free()
+        return self.run_prepared(self.prepare(calls))
+
+    def prepare(self, calls: Sequence[GibbsCall], touch: bool = False):
+        """argument / result structs and host result buffers for `run_prepared` (a caller that processes batch after
+        batch keeps them, like R keeps its per-worker scratch matrices, QUILT/R/quilt.R:731-762)"""
+        calls = list(calls)
+        n = len(calls)
+        args = (cabi.QuiltGibbsArgs * n)()
+        outs = (cabi.QuiltGibbsOut * n)()
+        for i, c in enumerate(calls):
+            c.fill(args[i])
+        res = [cabi.alloc_out(c, outs[i]) for i, c in enumerate(calls)]
+        if touch:
+            for r in res:
+                r.hapProbs_t.fill(0)
+                r.genProbsM_t.fill(0)
+                r.genProbsF_t.fill(0)
+        return calls, args, outs, res
+
+    def run_prepared(self, prep) -> List[GibbsResult]:
+        calls, args, outs, res = prep
+        self._check(self.lib.quilt_gpu_gibbs_batch(len(calls), args, outs), "quilt_gpu_gibbs_batch")
+        for i, r in enumerate(res):
+            r.underflow_problem = bool(outs[i].underflow_problem)
+        return res
 
 
 class Batch:

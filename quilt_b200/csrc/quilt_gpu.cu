@@ -40,6 +40,7 @@ thread_local std::string g_err;
 std::atomic<long long> g_launches{0};
 std::mutex g_mu;
 cudaStream_t g_stream = nullptr;
+cudaStream_t g_copy_in = nullptr, g_copy_out = nullptr;  // staging streams of the pipelined host-buffer path
 int g_device = -1;
 int g_sms = 0;
 
@@ -67,6 +68,8 @@ int ensure_device() {
     if (prop.major < 10) return set_err(QUILT_ERR_NO_DEVICE, "libquiltgpu is built for sm_100a only");
     g_sms = prop.multiProcessorCount;
     CK(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&g_copy_in, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&g_copy_out, cudaStreamNonBlocking));
     return QUILT_OK;
 }
 
@@ -706,7 +709,7 @@ int setup_bucket(QuiltGpuBatch* B, Bucket& bk, size_t* mem_budget) {
     bk.o_Wc = o, o += al(P.rare_common ? (size_t)B->panel.Tc * P.Kp * 4 : 0);
     bk.o_tabs = o, o += al((size_t)std::max(bk.n_tab_max, 1) * sizeof(TabEnt));
     bk.o_dense = o, o += al((size_t)std::max(bk.n_dense_max, 1) * P.Kp * 8);
-    bk.o_xprob = o, o += al((size_t)bk.R_max * 24);
+    bk.o_xprob = o, o += al((size_t)bk.R_max * 32);
     bk.o_snp_type = o, o += al(P.nSNPs);
     bk.o_rate = o, o += al((size_t)P.T * 8);
     bk.o_hapLocal = o, o += al(P.rare_common ? (size_t)P.nSNPs * 24 : 0);
@@ -715,8 +718,8 @@ int setup_bucket(QuiltGpuBatch* B, Bucket& bk, size_t* mem_budget) {
     int cap = g_sms * occ;
     const size_t by_mem = std::max<size_t>(1, *mem_budget / std::max<size_t>(bk.slot_bytes, 1));
     bk.n_slots = (int)std::min<size_t>(std::min<size_t>(cap, bk.jobs.size()), by_mem);
-    CK(bk.djobs.alloc((size_t)bk.n_slots * sizeof(JobDev)));
-    CK(bk.hjobs.alloc((size_t)bk.n_slots * sizeof(JobDev)));
+    CK(bk.djobs.alloc(bk.jobs.size() * sizeof(JobDev)));
+    CK(bk.hjobs.alloc(bk.jobs.size() * sizeof(JobDev)));
     bk.perform_block = (P.flags & QUILT_F_PERFORM_BLOCK_GIBBS) != 0;
     bk.do_shard = (P.flags & QUILT_F_DO_SHARD_BLOCK_GIBBS) != 0;
     bk.debug = (P.flags & (QUILT_F_RETURN_ALPHA | QUILT_F_RETURN_EXTRA)) != 0;
@@ -929,7 +932,7 @@ int fetch_debug(QuiltGpuBatch* B, Bucket& bk, int w0, int n) {
         if (P.flags & QUILT_F_RETURN_EXTRA) {
             DBuf d;
             CK(d.alloc((size_t)P.K * j.R * 8));
-            const JobDev* dj = (const JobDev*)bk.djobs.p + i;
+            const JobDev* dj = (const JobDev*)bk.djobs.p + w0 + i;
             k_expand_eMatRead<<<j.R, 256, 0, g_stream>>>(P, dj, (double*)d.p);
             LAUNCHED();
             CK(cudaStreamSynchronize(g_stream));
@@ -940,38 +943,48 @@ int fetch_debug(QuiltGpuBatch* B, Bucket& bk, int w0, int n) {
     return QUILT_OK;
 }
 
+// JobDev records of every wave of a bucket (slot = position inside the wave), uploaded once
+int upload_jobdevs(QuiltGpuBatch* B, Bucket& bk) {
+    const int nj = (int)bk.jobs.size();
+    JobDev* hj = (JobDev*)bk.hjobs.p;
+    for (int q = 0; q < nj; q++) make_jobdev(B, bk, B->jobs[bk.jobs[q]], q % bk.n_slots, &hj[q]);
+    CK(cudaMemcpyAsync(bk.djobs.p, hj, (size_t)nj * sizeof(JobDev), cudaMemcpyHostToDevice, g_stream));
+    return QUILT_OK;
+}
+
+int run_wave(QuiltGpuBatch* B, Bucket& bk, int w0, int n, bool timed, bool prep_only) {
+    if (bk.P.rare_common) {
+        for (int i = 0; i < n; i++)
+            CK(cudaMemsetAsync((char*)bk.slots + (size_t)i * bk.slot_bytes + bk.o_hapLocal, 0, (size_t)bk.P.nSNPs * 24, g_stream));
+    }
+    const JobDev* dj = (const JobDev*)bk.djobs.p + w0;
+    int rc;
+    if (prep_only) {
+        k_copy_H<<<dim3((bk.R_max + 255) / 256, n), 256, 0, g_stream>>>(dj);
+        LAUNCHED();
+        rc = run_prep(B, bk, n, dj);
+        if (rc == QUILT_OK) {
+            k_export_cat<<<dim3((bk.R_max + 255) / 256, n), 256, 0, g_stream>>>(dj);
+            LAUNCHED();
+        }
+    } else {
+        rc = with_geo(bk.geo, [&](auto nt, auto ept) { return run_wave_t<decltype(nt)::value, decltype(ept)::value>(B, bk, n, dj, timed); });
+    }
+    if (rc != QUILT_OK) return rc;
+    if (bk.debug) {
+        rc = fetch_debug(B, bk, w0, n);
+        if (rc != QUILT_OK) return rc;
+    }
+    return QUILT_OK;
+}
+
 int run_bucket(QuiltGpuBatch* B, Bucket& bk, bool timed, bool prep_only = false) {
     const int nj = (int)bk.jobs.size();
+    int rc = upload_jobdevs(B, bk);
+    if (rc != QUILT_OK) return rc;
     for (int w0 = 0; w0 < nj; w0 += bk.n_slots) {
-        const int n = std::min(bk.n_slots, nj - w0);
-        JobDev* hj = (JobDev*)bk.hjobs.p;
-        // the previous wave's kernels may still be reading the device copy; the stream orders the upload after them,
-        // but the pinned source must not be rewritten before that upload has been consumed
-        if (w0 > 0) CK(cudaStreamSynchronize(g_stream));
-        for (int i = 0; i < n; i++) make_jobdev(B, bk, B->jobs[bk.jobs[w0 + i]], i, &hj[i]);
-        CK(cudaMemcpyAsync(bk.djobs.p, hj, (size_t)n * sizeof(JobDev), cudaMemcpyHostToDevice, g_stream));
-        if (bk.P.rare_common) {
-            for (int i = 0; i < n; i++)
-                CK(cudaMemsetAsync((char*)bk.slots + (size_t)i * bk.slot_bytes + bk.o_hapLocal, 0, (size_t)bk.P.nSNPs * 24, g_stream));
-        }
-        const JobDev* dj = (const JobDev*)bk.djobs.p;
-        int rc;
-        if (prep_only) {
-            k_copy_H<<<dim3((bk.R_max + 255) / 256, n), 256, 0, g_stream>>>(dj);
-            LAUNCHED();
-            rc = run_prep(B, bk, n, dj);
-            if (rc == QUILT_OK) {
-                k_export_cat<<<dim3((bk.R_max + 255) / 256, n), 256, 0, g_stream>>>(dj);
-                LAUNCHED();
-            }
-        } else {
-            rc = with_geo(bk.geo, [&](auto nt, auto ept) { return run_wave_t<decltype(nt)::value, decltype(ept)::value>(B, bk, n, dj, timed); });
-        }
+        rc = run_wave(B, bk, w0, std::min(bk.n_slots, nj - w0), timed, prep_only);
         if (rc != QUILT_OK) return rc;
-        if (bk.debug) {
-            rc = fetch_debug(B, bk, w0, n);
-            if (rc != QUILT_OK) return rc;
-        }
     }
     return QUILT_OK;
 }
@@ -1057,8 +1070,7 @@ int quilt_gpu_batch_free(QuiltGpuBatch* b) {
     return QUILT_OK;
 }
 
-int quilt_gpu_batch_stage(int32_t n, const QuiltGibbsArgs* args, QuiltGpuBatch** batch) {
-    std::lock_guard<std::mutex> lk(g_mu);
+static int stage_impl(int32_t n, const QuiltGibbsArgs* args, QuiltGpuBatch** batch, bool upload) {
     if (n <= 0 || !args || !batch) return set_err(QUILT_ERR_BAD_ARG, "bad batch arguments");
     int rc = ensure_device();
     if (rc != QUILT_OK) return rc;
@@ -1074,14 +1086,21 @@ int quilt_gpu_batch_stage(int32_t n, const QuiltGibbsArgs* args, QuiltGpuBatch**
     if ((rc = get_panel(args[0].panel, &B->panel)) != QUILT_OK) return rc;
     std::map<BucketKey, int> index;
     size_t in_total = 0, out_total = 0;
+    {
+        // descriptor building is O(sum J) per job and independent across jobs
+        std::vector<int> rcs(n, QUILT_OK);
+        std::vector<std::string> errs(n);
+        QuiltGpuBatch* Bp = B.get();
+        parallel_for(n, [&](int i) {
+            rcs[i] = prepare_job(Bp->jobs[i]);
+            if (rcs[i] != QUILT_OK) errs[i] = g_err;
+        });
+        for (int i = 0; i < n; i++)
+            if (rcs[i] != QUILT_OK) return set_err(rcs[i], errs[i]);
+    }
     for (int i = 0; i < n; i++) {
         HostJob& j = B->jobs[i];
-        if ((rc = prepare_job(j)) != QUILT_OK) return rc;
         layout_in(j);
-        j.in_off = in_total;
-        j.out_off = out_total;
-        in_total += j.li.end;
-        out_total += j.lo.end;
         const BucketKey key = bucket_key(j.a);
         auto it = index.find(key);
         if (it == index.end()) {
@@ -1096,6 +1115,16 @@ int quilt_gpu_batch_stage(int32_t n, const QuiltGibbsArgs* args, QuiltGpuBatch**
         }
         B->buckets[j.bucket]->jobs.push_back(i);
     }
+    // arena offsets in (bucket, position) order: the jobs of a wave are contiguous, so a wave's inputs / outputs move
+    // with one copy each (pipelined path)
+    for (auto& bk : B->buckets)
+        for (int ji : bk->jobs) {
+            HostJob& j = B->jobs[ji];
+            j.in_off = in_total;
+            j.out_off = out_total;
+            in_total += j.li.end;
+            out_total += j.lo.end;
+        }
     B->in_bytes = in_total;
     B->out_bytes = out_total;
     {
@@ -1109,12 +1138,12 @@ int quilt_gpu_batch_stage(int32_t n, const QuiltGibbsArgs* args, QuiltGpuBatch**
         B->hout_ = g_hcache_out.acquire(out_total, &e);
         CK(e);
     }
-    {
+    if (upload) {
         QuiltGpuBatch* Bp = B.get();
         char* hin = (char*)Bp->hin().p;
         parallel_for(n, [&](int i) { fill_in(Bp->jobs[i], hin + Bp->jobs[i].in_off); });
+        CK(cudaMemcpyAsync(B->din().p, B->hin().p, in_total, cudaMemcpyHostToDevice, g_stream));
     }
-    CK(cudaMemcpyAsync(B->din().p, B->hin().p, in_total, cudaMemcpyHostToDevice, g_stream));
     size_t free_b = 0, total_b = 0;
     CK(cudaMemGetInfo(&free_b, &total_b));
     for (auto& c : g_dcache_slots.free_) free_b += c->bytes;  // a cached arena will be reused or dropped
@@ -1136,6 +1165,11 @@ int quilt_gpu_batch_stage(int32_t n, const QuiltGibbsArgs* args, QuiltGpuBatch**
     CK(cudaStreamSynchronize(g_stream));
     *batch = B.release();
     return QUILT_OK;
+}
+
+int quilt_gpu_batch_stage(int32_t n, const QuiltGibbsArgs* args, QuiltGpuBatch** batch) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    return stage_impl(n, args, batch, true);
 }
 
 int quilt_gpu_batch_run(QuiltGpuBatch* B) {
@@ -1199,6 +1233,42 @@ int quilt_gpu_batch_bytes(QuiltGpuBatch* B, int64_t* h2d, int64_t* d2h, double* 
     return QUILT_OK;
 }
 
+static void unpack_job(const QuiltGpuBatch* B, int i, QuiltGibbsOut* out) {
+    const HostJob& j = B->jobs[i];
+    const QuiltGibbsArgs& a = j.a;
+    QuiltGibbsOut& o = out[i];
+    const char* base = (const char*)B->hout().p + j.out_off;
+    const int under = *reinterpret_cast<const int32_t*>(base + j.lo.underflow);
+    o.underflow_problem = under ? 1 : 0;
+    const size_t n3 = (size_t)a.nSNPs * 3;
+    if (o.hapProbs_t) std::memcpy(o.hapProbs_t, base + j.lo.hap, n3 * 8);
+    if (o.genProbsM_t) std::memcpy(o.genProbsM_t, base + j.lo.genM, n3 * 8);
+    if (o.genProbsF_t) std::memcpy(o.genProbsF_t, base + j.lo.genF, n3 * 8);
+    if (o.H) std::memcpy(o.H, base + j.lo.H, (size_t)j.R * 4);
+    if (o.H_class && (a.flags & QUILT_F_RECORD_READ_SET)) std::memcpy(o.H_class, base + j.lo.Hclass, (size_t)j.R * 4);
+    if (o.read_category) std::memcpy(o.read_category, base + j.lo.cat, (size_t)j.R * 4);
+    if (o.per_it_likelihoods) {
+        const int n_rows = (a.n_gibbs_sample_its == 0) ? 1 : j.n_its;
+        std::memset(o.per_it_likelihoods, 0, (size_t)n_rows * 13 * 8);
+        const double* lik = reinterpret_cast<const double*>(base + j.lo.lik);
+        for (int it = 0; it < std::min(n_rows, j.n_its); it++) {
+            fill_lik_row(a, lik + (size_t)it * LIK_N, it, n_rows, o.per_it_likelihoods);
+        }
+    }
+    const int NH = (a.flags & QUILT_F_SAMPLE_IS_DIPLOID) ? 2 : 3;
+    if (a.flags & QUILT_F_RETURN_ALPHA) {
+        const size_t per = (size_t)a.nGrids * a.K;
+        for (int h = 0; h < NH; h++) {
+            if (o.alphaHat_t[h] && !j.dbg_alpha.empty()) std::memcpy(o.alphaHat_t[h], &j.dbg_alpha[h * per], per * 8);
+            if (o.betaHat_t[h] && !j.dbg_beta.empty()) std::memcpy(o.betaHat_t[h], &j.dbg_beta[h * per], per * 8);
+            if (o.eMatGrid_t[h] && !j.dbg_eG.empty()) std::memcpy(o.eMatGrid_t[h], &j.dbg_eG[h * per], per * 8);
+            if (o.c[h] && !j.dbg_c.empty()) std::memcpy(o.c[h], &j.dbg_c[(size_t)h * a.nGrids], (size_t)a.nGrids * 8);
+        }
+    }
+    if ((a.flags & QUILT_F_RETURN_EXTRA) && o.eMatRead_t && !j.dbg_eMatRead.empty())
+        std::memcpy(o.eMatRead_t, j.dbg_eMatRead.data(), j.dbg_eMatRead.size() * 8);
+}
+
 int quilt_gpu_batch_fetch(QuiltGpuBatch* B, QuiltGibbsOut* out) {
     std::lock_guard<std::mutex> lk(g_mu);
     if (!B || !out) return set_err(QUILT_ERR_BAD_ARG, "null batch / out");
@@ -1208,53 +1278,93 @@ int quilt_gpu_batch_fetch(QuiltGpuBatch* B, QuiltGibbsOut* out) {
         CK(cudaStreamSynchronize(g_stream));
         B->fetched_raw = true;
     }
-    parallel_for(B->n, [&](int i) {
-        const HostJob& j = B->jobs[i];
-        const QuiltGibbsArgs& a = j.a;
-        QuiltGibbsOut& o = out[i];
-        const char* base = (const char*)B->hout().p + j.out_off;
-        const int under = *reinterpret_cast<const int32_t*>(base + j.lo.underflow);
-        o.underflow_problem = under ? 1 : 0;
-        const size_t n3 = (size_t)a.nSNPs * 3;
-        if (o.hapProbs_t) std::memcpy(o.hapProbs_t, base + j.lo.hap, n3 * 8);
-        if (o.genProbsM_t) std::memcpy(o.genProbsM_t, base + j.lo.genM, n3 * 8);
-        if (o.genProbsF_t) std::memcpy(o.genProbsF_t, base + j.lo.genF, n3 * 8);
-        if (o.H) std::memcpy(o.H, base + j.lo.H, (size_t)j.R * 4);
-        if (o.H_class && (a.flags & QUILT_F_RECORD_READ_SET)) std::memcpy(o.H_class, base + j.lo.Hclass, (size_t)j.R * 4);
-        if (o.read_category) std::memcpy(o.read_category, base + j.lo.cat, (size_t)j.R * 4);
-        if (o.per_it_likelihoods) {
-            const int n_rows = (a.n_gibbs_sample_its == 0) ? 1 : j.n_its;
-            std::memset(o.per_it_likelihoods, 0, (size_t)n_rows * 13 * 8);
-            const double* lik = reinterpret_cast<const double*>(base + j.lo.lik);
-            for (int it = 0; it < std::min(n_rows, j.n_its); it++) {
-                fill_lik_row(a, lik + (size_t)it * LIK_N, it, n_rows, o.per_it_likelihoods);
-            }
-        }
-        const int NH = (a.flags & QUILT_F_SAMPLE_IS_DIPLOID) ? 2 : 3;
-        if (a.flags & QUILT_F_RETURN_ALPHA) {
-            const size_t per = (size_t)a.nGrids * a.K;
-            for (int h = 0; h < NH; h++) {
-                if (o.alphaHat_t[h] && !j.dbg_alpha.empty()) std::memcpy(o.alphaHat_t[h], &j.dbg_alpha[h * per], per * 8);
-                if (o.betaHat_t[h] && !j.dbg_beta.empty()) std::memcpy(o.betaHat_t[h], &j.dbg_beta[h * per], per * 8);
-                if (o.eMatGrid_t[h] && !j.dbg_eG.empty()) std::memcpy(o.eMatGrid_t[h], &j.dbg_eG[h * per], per * 8);
-                if (o.c[h] && !j.dbg_c.empty()) std::memcpy(o.c[h], &j.dbg_c[(size_t)h * a.nGrids], (size_t)a.nGrids * 8);
-            }
-        }
-        if ((a.flags & QUILT_F_RETURN_EXTRA) && o.eMatRead_t && !j.dbg_eMatRead.empty())
-            std::memcpy(o.eMatRead_t, j.dbg_eMatRead.data(), j.dbg_eMatRead.size() * 8);
-    });
+    parallel_for(B->n, [&](int i) { unpack_job(B, i, out); });
     return QUILT_OK;
 }
 
+// Host buffers in, host buffers out.  Waves are pipelined: while the kernels of wave w run, the host fills the pinned
+// input block of wave w + 1 (one H2D copy per wave on a copy stream) and unpacks the results of wave w - 1 (one D2H copy
+// per wave on a second copy stream), so staging overlaps compute instead of preceding / following it.
 int quilt_gpu_gibbs_batch(int32_t n, const QuiltGibbsArgs* args, QuiltGibbsOut* out) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!out) return set_err(QUILT_ERR_BAD_ARG, "null out");
     QuiltGpuBatch* B = nullptr;
-    int rc = quilt_gpu_batch_stage(n, args, &B);
+    int rc = stage_impl(n, args, &B, false);
     if (rc != QUILT_OK) return rc;
-    rc = quilt_gpu_batch_run(B);
-    if (rc == QUILT_OK) rc = quilt_gpu_batch_sync(B);
-    if (rc == QUILT_OK) rc = quilt_gpu_batch_fetch(B, out);
-    quilt_gpu_batch_free(B);
-    return rc;
+    struct Wave {
+        Bucket* bk;
+        int w0, n;
+        cudaEvent_t ev_in = nullptr, ev_done = nullptr, ev_out = nullptr;
+    };
+    std::vector<Wave> waves;
+    for (auto& bk : B->buckets)
+        for (int w0 = 0; w0 < (int)bk->jobs.size(); w0 += bk->n_slots) waves.push_back({bk.get(), w0, std::min(bk->n_slots, (int)bk->jobs.size() - w0)});
+    auto cleanup = [&](int code) {
+        cudaStreamSynchronize(g_stream);
+        cudaStreamSynchronize(g_copy_in);
+        cudaStreamSynchronize(g_copy_out);
+        for (auto& w : waves) {
+            if (w.ev_in) cudaEventDestroy(w.ev_in);
+            if (w.ev_done) cudaEventDestroy(w.ev_done);
+            if (w.ev_out) cudaEventDestroy(w.ev_out);
+        }
+        delete B;
+        return code;
+    };
+#define CKP(call)                                                                                        \
+    do {                                                                                                 \
+        cudaError_t e__ = (call);                                                                        \
+        if (e__ != cudaSuccess)                                                                          \
+            return cleanup(set_err(QUILT_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__) + " @" + std::to_string(__LINE__))); \
+    } while (0)
+    CKP(cudaMemsetAsync(B->dout().p, 0, B->out_bytes, g_stream));
+    Bucket* uploaded = nullptr;
+    auto unpack_wave = [&](const Wave& w) {
+        parallel_for(w.n, [&](int i) { unpack_job(B, w.bk->jobs[w.w0 + i], out); });
+    };
+    for (size_t wi = 0; wi < waves.size(); wi++) {
+        Wave& w = waves[wi];
+        const HostJob& first = B->jobs[w.bk->jobs[w.w0]];
+        const HostJob& last = B->jobs[w.bk->jobs[w.w0 + w.n - 1]];
+        const size_t in_lo = first.in_off, in_hi = last.in_off + last.li.end;
+        const size_t out_lo = first.out_off, out_hi = last.out_off + last.lo.end;
+        // host: this wave's inputs into the pinned block (runs while the previous wave computes)
+        char* hin = (char*)B->hin().p;
+        parallel_for(w.n, [&](int i) {
+            const HostJob& j = B->jobs[w.bk->jobs[w.w0 + i]];
+            fill_in(j, hin + j.in_off);
+        });
+        CKP(cudaEventCreateWithFlags(&w.ev_in, cudaEventDisableTiming));
+        CKP(cudaEventCreateWithFlags(&w.ev_done, cudaEventDisableTiming));
+        CKP(cudaEventCreateWithFlags(&w.ev_out, cudaEventDisableTiming));
+        CKP(cudaMemcpyAsync((char*)B->din().p + in_lo, hin + in_lo, in_hi - in_lo, cudaMemcpyHostToDevice, g_copy_in));
+        CKP(cudaEventRecord(w.ev_in, g_copy_in));
+        CKP(cudaStreamWaitEvent(g_stream, w.ev_in, 0));
+        if (uploaded != w.bk) {
+            rc = upload_jobdevs(B, *w.bk);
+            if (rc != QUILT_OK) return cleanup(rc);
+            uploaded = w.bk;
+        }
+        rc = run_wave(B, *w.bk, w.w0, w.n, false, false);
+        if (rc != QUILT_OK) return cleanup(rc);
+        CKP(cudaEventRecord(w.ev_done, g_stream));
+        CKP(cudaStreamWaitEvent(g_copy_out, w.ev_done, 0));
+        CKP(cudaMemcpyAsync((char*)B->hout().p + out_lo, (const char*)B->dout().p + out_lo, out_hi - out_lo, cudaMemcpyDeviceToHost, g_copy_out));
+        CKP(cudaEventRecord(w.ev_out, g_copy_out));
+        // host: results of the previous wave (its D2H finishes while this wave computes)
+        if (wi > 0) {
+            CKP(cudaEventSynchronize(waves[wi - 1].ev_out));
+            unpack_wave(waves[wi - 1]);
+        }
+    }
+    if (!waves.empty()) {
+        CKP(cudaEventSynchronize(waves.back().ev_out));
+        unpack_wave(waves.back());
+    }
+    CKP(cudaGetLastError());
+#undef CKP
+    B->ran = true;
+    return cleanup(QUILT_OK);
 }
 
 int quilt_gpu_gibbs(const QuiltGibbsArgs* args, QuiltGibbsOut* out) { return quilt_gpu_gibbs_batch(1, args, out); }

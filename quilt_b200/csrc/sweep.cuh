@@ -92,12 +92,28 @@ struct BlockSumV {
             phase ^= 1;
             if ((lane & 15) == 0) buf[(lane >> 4) * NW + warp] = x;
             __syncthreads();
-            double s = buf[(lane >> 4) * NW + (lane & (NW - 1))];
+            // every thread reads all warp partials (broadcast 16-byte loads) and adds them in one fixed tree: ~3 dependent
+            // adds instead of log2(NW) + 1 shuffle round trips
+            double p0[NW], p1[NW];
 #pragma unroll
-            for (int d = NW / 2; d >= 1; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
-            const double o = __shfl_xor_sync(0xffffffffu, s, 16);
-            v[0] = upper ? o : s;
-            v[1] = upper ? s : o;
+            for (int w = 0; w < NW; w += 2) {
+                const double2 a = *reinterpret_cast<const double2*>(buf + w);
+                const double2 b = *reinterpret_cast<const double2*>(buf + NW + w);
+                p0[w] = a.x;
+                p0[w + 1] = a.y;
+                p1[w] = b.x;
+                p1[w + 1] = b.y;
+            }
+#pragma unroll
+            for (int st = 1; st < NW; st <<= 1) {
+#pragma unroll
+                for (int w = 0; w + st < NW; w += 2 * st) {
+                    p0[w] += p0[w + st];
+                    p1[w] += p1[w + st];
+                }
+            }
+            v[0] = p0[0];
+            v[1] = p1[0];
             return;
         }
 #pragma unroll
@@ -177,6 +193,38 @@ struct Decision {
 __device__ __forceinline__ double quot(double a, double b, double rb) {
     const double q = a * rb;
     return fma(fma(-q, b, a), rb, q);
+}
+
+// Diploid, normal regime, decisive case: the label follows from comparing chance * denom with the unnormalised
+// probability of label 0; a guard band (1e-11 relative, five orders above the rounding of the exact path) and the
+// chance ~ 1 corner send everything else to the exact code, so the labels are those of decide_read bit for bit.
+// The normalised probabilities (only needed for H_class) are formed in the sweep epilogue from the recorded products.
+struct FastDecision {
+    bool decided;
+    int hN;
+    double prod_pC, prod_pA1, prod_pA2;
+};
+__device__ __forceinline__ FastDecision decide_diploid_fast(const P3& pC_in, double sv0, double sv1, int hC_in, double chance, const P3& prior) {
+    FastDecision F;
+    const bool c0 = hC_in == 0;
+    const double pa = c0 ? pC_in.b : pC_in.a;
+    F.prod_pC = ((pC_in.a * pC_in.b) * pC_in.c) * (c0 ? prior.a : prior.b);
+    F.prod_pA1 = ((c0 ? sv0 * sv1 : sv1 * sv0) * pC_in.c) * (c0 ? prior.b : prior.a);
+    F.prod_pA2 = ((c0 ? sv0 * pa : pa * sv0) * pC_in.c) * prior.c;
+    const double denom = F.prod_pC + F.prod_pA1 + F.prod_pA2;
+    const double P0 = c0 ? F.prod_pC : F.prod_pA1;
+    const double t = chance * denom;
+    const double margin = 1e-11 * denom;
+    F.decided = false;
+    F.hN = 0;
+    if (t < P0 - margin) {
+        F.decided = true;
+        F.hN = 0;
+    } else if (t > P0 + margin && chance < 1 - 1e-9 && F.prod_pA2 == 0) {
+        F.decided = true;
+        F.hN = 1;
+    }
+    return F;
 }
 
 template <int NH>
@@ -772,9 +820,10 @@ __global__ void __launch_bounds__(NT, (NT * EPT <= 512 ? 4 : (NT * EPT <= 1024 ?
                     QB_UPD(src, normal, hC, hN)
                 }
                 if (record && tid == 0) {
-                    J.xprob[3 * (size_t)r + 0] = D.x.a;
-                    J.xprob[3 * (size_t)r + 1] = D.x.b;
-                    J.xprob[3 * (size_t)r + 2] = D.x.c;
+                    J.xprob[4 * (size_t)r + 0] = D.x.a;
+                    J.xprob[4 * (size_t)r + 1] = D.x.b;
+                    J.xprob[4 * (size_t)r + 2] = D.x.c;
+                    J.xprob[4 * (size_t)r + 3] = -1.0;  // already normalised
                 }
             };
 
@@ -848,8 +897,32 @@ __global__ void __launch_bounds__(NT, (NT * EPT <= 512 ? 4 : (NT * EPT <= 1024 ?
                         (void)s2;
                     }
                     bsum.run(sv);
-                    const Decision D = decide_read<NH>(pC, sv, hC, KIND_NORMAL, Us[ir], prior);
-                    pC = D.pCnew;
+                    const FastDecision F = decide_diploid_fast(pC, sv[0], sv[1], hC, Us[ir], prior);
+                    Decision D;
+                    if (F.decided) {
+                        D.hN = F.hN;
+                        D.change = F.hN != hC;
+                        if (D.change) {
+                            // hN is the other label: the column sums become the two K-long sums just formed
+                            pC.a = (hC == 0) ? sv[0] : sv[1];
+                            pC.b = (hC == 0) ? sv[1] : sv[0];
+                        }
+                        if (record && tid == 0) {
+                            J.xprob[4 * (size_t)r + 0] = F.prod_pC;
+                            J.xprob[4 * (size_t)r + 1] = F.prod_pA1;
+                            J.xprob[4 * (size_t)r + 2] = F.prod_pA2;
+                            J.xprob[4 * (size_t)r + 3] = (double)hC;  // raw products of a read whose label was hC
+                        }
+                    } else {
+                        D = decide_read<NH>(pC, sv, hC, KIND_NORMAL, Us[ir], prior);
+                        pC = D.pCnew;
+                        if (record && tid == 0) {
+                            J.xprob[4 * (size_t)r + 0] = D.x.a;
+                            J.xprob[4 * (size_t)r + 1] = D.x.b;
+                            J.xprob[4 * (size_t)r + 2] = D.x.c;
+                            J.xprob[4 * (size_t)r + 3] = -1.0;
+                        }
+                    }
                     if (D.change) {
                         changed = true;
                         if (tid == 0) J.H[r] = D.hN + 1;
@@ -866,11 +939,6 @@ __global__ void __launch_bounds__(NT, (NT * EPT <= 512 ? 4 : (NT * EPT <= 1024 ?
                                 QB_UPD_LOOP(1, 1, 0, true)
                             }
                         }
-                    }
-                    if (record && tid == 0) {
-                        J.xprob[3 * (size_t)r + 0] = D.x.a;
-                        J.xprob[3 * (size_t)r + 1] = D.x.b;
-                        J.xprob[3 * (size_t)r + 2] = D.x.c;
                     }
                 }
                 if (!prestaged) tab0 = rmask[7];
@@ -1006,7 +1074,18 @@ __global__ void __launch_bounds__(NT, (NT * EPT <= 512 ? 4 : (NT * EPT <= 1024 ?
             if (NH == 2 && J.desc[r].cat == 1) {
                 hc = J.Hclass[r];
             } else {
-                hc = classify_H(P, J.xprob[3 * (size_t)r], J.xprob[3 * (size_t)r + 1], J.xprob[3 * (size_t)r + 2]);
+                const double* xp = J.xprob + 4 * (size_t)r;
+                double x0 = xp[0], x1 = xp[1], x2 = xp[2];
+                if (xp[3] >= 0) {
+                    // raw products of the fast decision path: normalise exactly as decide_read does
+                    const double denom = x0 + x1 + x2;
+                    const double nC = x0 / denom, nA1 = x1 / denom, nA2 = x2 / denom;
+                    const bool c0 = xp[3] == 0.0;
+                    x0 = c0 ? nC : nA1;
+                    x1 = c0 ? nA1 : nC;
+                    x2 = nA2;
+                }
+                hc = classify_H(P, x0, x1, x2);
                 J.Hclass[r] = hc;
             }
             atomicAdd(&cnt[3 + hc], 1);

@@ -52,7 +52,8 @@ struct JobDev {
     ReadDesc* desc;  // [R]
     TabEnt* tabs;    // table pool
     double* dense;   // [n_dense][Kp]
-    double* xprob;   // [R][3] label probabilities of the last visit (H_class is derived from them)
+    double* xprob;   // [R][4] label probabilities of the last visit (H_class is derived from them): normalised (slot 3 = -1)
+                     // or the raw products of the fast decision path (slot 3 = label the read had)
     uint8_t* snp_type;  // [nSNPs] all-SNP calls: 0 common, 1 rare without carrier, 2 rare with carrier(s)
     double* rate;       // [T] scratch (block definition)
     // inputs

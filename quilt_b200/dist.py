@@ -152,3 +152,10 @@ def barrier():
 
     if td.is_initialized() and td.get_world_size() > 1:
         td.barrier()
+
+
+def shutdown():
+    import torch.distributed as td
+
+    if td.is_initialized():
+        td.destroy_process_group()
