@@ -844,10 +844,15 @@ int run_wave_t(QuiltGpuBatch* B, Bucket& bk, int n, const JobDev* dj, bool timed
             CK(cudaEventCreate(&e1));
             CK(cudaEventRecord(e0, g_stream));
         }
+        bool blk_next = false;
+        if (bk.perform_block)
+            for (int b : bk.block_its) blk_next = blk_next || (b == it);
+        // alpha columns are written only when a consumer follows this sweep (see k_sweep)
+        const int store_alpha = (it >= P.n_burn || (P.NH == 3 && blk_next) || bk.debug || it == P.n_its - 1) ? 1 : 0;
         if (P.NH == 2) {
-            k_sweep<NT, EPT, 2><<<n, NT, L.total, g_stream>>>(P, dj, it);
+            k_sweep<NT, EPT, 2><<<n, NT, L.total, g_stream>>>(P, dj, it, store_alpha);
         } else if constexpr (nipt_geo<NT, EPT>()) {
-            k_sweep<NT, EPT, 3><<<n, NT, L.total, g_stream>>>(P, dj, it);
+            k_sweep<NT, EPT, 3><<<n, NT, L.total, g_stream>>>(P, dj, it, store_alpha);
         }
         LAUNCHED();
         if (timed) {

@@ -416,7 +416,7 @@ __device__ __forceinline__ void upd_loop(double (&am)[NH][EPT], double (&ab)[NH]
 }
 
 template <int NT, int EPT, int NH>
-__global__ void __launch_bounds__(NT, (NT * EPT <= 512 ? 4 : (NT * EPT <= 1024 ? 2 : 1))) k_sweep(BatchParams P, const JobDev* __restrict__ jobs, int iteration) {
+__global__ void __launch_bounds__(NT, (NT * EPT <= 512 ? 4 : (NT * EPT <= 1024 ? 2 : 1))) k_sweep(BatchParams P, const JobDev* __restrict__ jobs, int iteration, int store_alpha) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ JobDev Js;
     constexpr int KA = NT * EPT;
@@ -967,7 +967,9 @@ __global__ void __launch_bounds__(NT, (NT * EPT <= 512 ? 4 : (NT * EPT <= 1024 ?
         }
 #pragma unroll
         for (int h = 0; h < NH; h++) {
-            Col<NT, EPT>::store(am[h], alphaG + ((size_t)h * T + g) * Kp, K);
+            // alphaHat_t in HBM is only read by the passes that may follow a sweep (gamma -> hapProbs after a sampling
+            // sweep, the NIPT block episode, debug export); the next sweep rebuilds alpha from its registers
+            if (store_alpha) Col<NT, EPT>::store(am[h], alphaG + ((size_t)h * T + g) * Kp, K);
             if (changed) {
                 // (loads first: a generic store may alias shared memory, so interleaving would serialise them)
                 double tmp[EPT];
