@@ -352,7 +352,7 @@ __global__ void __launch_bounds__(32) k_block_define(BatchParams P, const JobDev
 
 // emission value of read r (descriptor d, staged nowhere: global tables) for haplotype k at grid g
 __device__ __forceinline__ double read_emission_global(const JobDev& J, const ReadDesc& d, int Kp, int g, int k) {
-    if (d.mode == MODE_DENSE) return J.dense[(size_t)d.off * Kp + k];
+    if (d.mode == MODE_DENSE) return J.dense[(size_t)d.off * Kp + k].E;
     return J.tabs[d.off + read_pattern_global(d, J.W, Kp, g, k)].E;
 }
 

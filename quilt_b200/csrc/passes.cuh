@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(256) k_make_eG(BatchParams P, const JobDev* __
                     const int mode = (dq.y >> 8) & 0xff, nb = (dq.y >> 16) & 0xff;
                     double E;
                     if (mode == MODE_DENSE) {
-                        E = J.dense[(size_t)dq.x * Kp + k];
+                        E = J.dense[(size_t)dq.x * Kp + k].E;
                     } else {
                         uint32_t pat;
                         if (mode == MODE_RUN) {

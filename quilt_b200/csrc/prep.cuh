@@ -266,7 +266,7 @@ __global__ void __launch_bounds__(256) k_build_dense(BatchParams P, const JobDev
     if ((int)blockIdx.x >= J.n_dense) return;
     const int r = J.dense_reads[blockIdx.x];
     const ReadDesc d = J.desc[r];
-    double* col = J.dense + (size_t)d.off * P.Kp;
+    TabEnt* col = J.dense + (size_t)d.off * P.Kp;
     const int uo = J.roff[r];
     int cnt = J.roff[r + 1] - uo;
     if (cnt - 1 >= P.Jmax) cnt = P.Jmax + 1;
@@ -287,7 +287,8 @@ __global__ void __launch_bounds__(256) k_build_dense(BatchParams P, const JobDev
             }
             if (E > x) x = E;
         }
-        col[k] = E;
+        col[k].E = E;
+        col[k].invE = 1.0;
     }
     bool degenerate = false;
     double d1 = 1;
@@ -310,7 +311,7 @@ __global__ void __launch_bounds__(256) k_build_dense(BatchParams P, const JobDev
     // rescale + find the first non-1 haplotype (smallest k) and the count
     int nn = 0, kfirst = 0x7fffffff;
     for (int k = threadIdx.x; k < P.K; k += 256) {
-        double E = col[k];
+        double E = col[k].E;
         if (rescale) {
             if (degenerate) {
                 E = 1;
@@ -318,8 +319,9 @@ __global__ void __launch_bounds__(256) k_build_dense(BatchParams P, const JobDev
                 E *= d1;
                 if (E < P.d2) E = P.d2;
             }
-            col[k] = E;
+            col[k].E = E;
         }
+        col[k].invE = 1 / E;
         if (E < ONE_THRESH) {
             nn++;
             if (k < kfirst) kfirst = k;
@@ -344,9 +346,9 @@ __global__ void __launch_bounds__(256) k_build_dense(BatchParams P, const JobDev
     __syncthreads();
     int more = 0;
     if (nn > 0) {
-        const double val = col[kfirst];
+        const double val = col[kfirst].E;
         for (int k = threadIdx.x; k < P.K; k += 256) {
-            const double E = col[k];
+            const double E = col[k].E;
             if (E < ONE_THRESH && E != val) more = 1;
         }
     }
@@ -377,7 +379,7 @@ __global__ void __launch_bounds__(256) k_expand_eMatRead(BatchParams P, const Jo
     for (int k = threadIdx.x; k < P.K; k += 256) {
         double E;
         if (d.mode == MODE_DENSE)
-            E = J.dense[(size_t)d.off * P.Kp + k];
+            E = J.dense[(size_t)d.off * P.Kp + k].E;
         else
             E = J.tabs[d.off + read_pattern_global(d, J.W, P.Kp, g, k)].E;
         out[(size_t)r * P.K + k] = E;

@@ -456,6 +456,9 @@ int prepare_job(HostJob& j) {
             if (wg < w - 1 || wg > w + 1) table = false;
             if (q > 0 && s != a.reads.u[o + q - 1] + 1) run = false;
         }
+        // non-consecutive SNPs (possible only for hand-made inputs: a read's SNPs are a contiguous index range) would
+        // need a per-haplotype gathered pattern; such reads are kept as dense columns instead
+        if (table && !run) table = false;
         if (table) {
             d.nb = (uint8_t)cnt;
             d.off = (uint32_t)n_tab;
@@ -708,7 +711,7 @@ int setup_bucket(QuiltGpuBatch* B, Bucket& bk, size_t* mem_budget) {
     bk.o_W = o, o += al((size_t)P.T * P.Kp * 4);
     bk.o_Wc = o, o += al(P.rare_common ? (size_t)B->panel.Tc * P.Kp * 4 : 0);
     bk.o_tabs = o, o += al((size_t)std::max(bk.n_tab_max, 1) * sizeof(TabEnt));
-    bk.o_dense = o, o += al((size_t)std::max(bk.n_dense_max, 1) * P.Kp * 8);
+    bk.o_dense = o, o += al((size_t)std::max(bk.n_dense_max, 1) * P.Kp * sizeof(TabEnt));
     bk.o_xprob = o, o += al((size_t)bk.R_max * 32);
     bk.o_snp_type = o, o += al(P.nSNPs);
     bk.o_rate = o, o += al((size_t)P.T * 8);
@@ -742,7 +745,7 @@ void make_jobdev(const QuiltGpuBatch* B, const Bucket& bk, const HostJob& j, int
     D->Wc = (uint32_t*)(s + bk.o_Wc);
     D->desc = (ReadDesc*)(in + j.li.desc);
     D->tabs = (TabEnt*)(s + bk.o_tabs);
-    D->dense = (double*)(s + bk.o_dense);
+    D->dense = (TabEnt*)(s + bk.o_dense);
     D->xprob = (double*)(s + bk.o_xprob);
     D->snp_type = (uint8_t*)(s + bk.o_snp_type);
     D->rate = (double*)(s + bk.o_rate);

@@ -24,7 +24,8 @@
 namespace qb {
 
 constexpr int SW_MAXR = 48;     // reads staged in shared memory at a time (longer grids are processed in chunks)
-constexpr int SW_MAXTAB = 384;  // table entries staged at a time (>= 2^NBMAX, so any table-mode read fits)
+constexpr int SW_MAXTAB = 704;  // table entries staged at a time (>= 2^NBMAX, so any table-mode read fits); sized so that
+                                // ~97 % of the all-SNP grids of the benchmark (311 +- 205 entries) are staged with their package
 constexpr int SW_VMAX = 4;
 constexpr int SW_BMAX = 16;  // reads decided per round of the batched resampler
 static_assert(SW_MAXTAB >= (1 << NBMAX), "a single emission table must fit the staging buffer");
@@ -54,12 +55,10 @@ __host__ __device__ inline SweepSmemLayout sweep_smem_layout(int KA, int NH, int
     o += small_total;
     L.off_small[1] = o;
     o += small_total;
-    L.off_pat = o;
-    o += KA * 2;
+    L.off_pat = o;  // (gather-mode pattern scratch: the host turns such reads into dense columns, nothing to reserve)
     L.off_part = o;
-    o += SW_BMAX * (NH == 2 ? 2 : 4) * (NT / 32) * 8;
-    L.off_rec = o;
-    o += SW_BMAX * 32 + 64;
+    L.off_rec = o;  // chunking scratch of grids whose reads exceed one staging buffer
+    o += 64;
     o = (o + 127) & ~127;
     L.off_W = o;
     o += 4 * KA * 4;
@@ -337,7 +336,7 @@ struct ESrc {
     const uint32_t* whi;   // RUN: next word (only read when the run crosses)
     const uint16_t* spat;  // GATHER: materialised patterns
     const TabEnt* tab;     // table (shared memory)
-    const double* dcol;    // DENSE: K-long column (global memory)
+    const TabEnt* dcol;    // DENSE: K-long {E, 1/E} column (global memory)
     uint32_t b0, mask;
     bool cross;
 };
@@ -348,8 +347,10 @@ template <int SRC>  // 0: run inside one word, 1: run crossing into the next wor
 __device__ __forceinline__ EV emission_at(const ESrc& S, int k) {
     EV r;
     if (SRC == 3) {
-        r.E = S.dcol[k];
-        r.invE = 1 / r.E;
+        double2 te;
+        asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(te.x), "=d"(te.y) : "l"(S.dcol + k));
+        r.E = te.x;
+        r.invE = te.y;
         return r;
     }
     uint32_t pat;
@@ -396,9 +397,9 @@ __device__ __forceinline__ void upd_loop(double (&am)[NH][EPT], double (&ab)[NH]
         for (int j = 0; j < UPD_CH; j++) {
             const int i = i0 + j;
             if (DODIV) {
-                am[HC][i] = (SRC == 3) ? am[HC][i] / ev[j].E : div_by(am[HC][i], ev[j].E, ev[j].invE);
-                ab[HC][i] = (SRC == 3) ? ab[HC][i] / ev[j].E : div_by(ab[HC][i], ev[j].E, ev[j].invE);
-                if (EGC) gc[j] = (SRC == 3) ? gc[j] / ev[j].E : div_by(gc[j], ev[j].E, ev[j].invE);
+                am[HC][i] = div_by(am[HC][i], ev[j].E, ev[j].invE);
+                ab[HC][i] = div_by(ab[HC][i], ev[j].E, ev[j].invE);
+                if (EGC) gc[j] = div_by(gc[j], ev[j].E, ev[j].invE);
             }
             am[HN][i] *= ev[j].E;
             ab[HN][i] *= ev[j].E;
@@ -435,9 +436,7 @@ __global__ void __launch_bounds__(NT, (NT * EPT <= 512 ? 4 : (NT * EPT <= 1024 ?
     uint32_t* Wr = reinterpret_cast<uint32_t*>(smem + L.off_W);          // [4][KA] ring of allele words
     uint16_t* spat = reinterpret_cast<uint16_t*>(smem + L.off_pat);      // [KA] allele patterns of gather-mode reads
     double* eGs = reinterpret_cast<double*>(smem + L.off_eG);            // [2][NH][KA]
-    double* part = reinterpret_cast<double*>(smem + L.off_part);         // batched resampler: [chunk * VC + value][NW]
-    unsigned char* recb = smem + L.off_rec;                              // batched resampler: [SW_BMAX] x {int hN; double pCnew[3]}
-    uint32_t* rmask = reinterpret_cast<uint32_t*>(recb + SW_BMAX * 32);  // [0..1] active, [2..3] batchable, [4..5] change masks, [6..7] chunk
+    uint32_t* rmask = reinterpret_cast<uint32_t*>(smem + L.off_rec);     // [6..7] chunk size / table end of an over-full grid
     const bool iterative = (P.flags & QUILT_F_GIBBS_INITIALIZE_ITERATIVELY) != 0;
     const bool record = (P.flags & QUILT_F_RECORD_READ_SET) != 0;
     const double one_over_K = P.one_over_K;
@@ -733,11 +732,7 @@ __global__ void __launch_bounds__(NT, (NT * EPT <= 512 ? 4 : (NT * EPT <= 1024 ?
             const int k = tid + i * NT;                                                                   \
             if (SRC != 3 || k < K) {                                                                      \
                 const EV ev = emission_at<SRC>(S, k);                                                     \
-                if (SRC == 3) {                                                                           \
-                    s0 += CMUL ? XC[i] * ev.E : XC[i] / ev.E;                                             \
-                    s1 += XA1[i] * ev.E;                                                                  \
-                    if (NH == 3) s2 += XA2[i] * ev.E;                                                     \
-                } else if (i & 1) {                                                                       \
+                if (i & 1) {                                                                       \
                     t0_ = fma(XC[i], CMUL ? ev.E : ev.invE, t0_);                                         \
                     t1_ = fma(XA1[i], ev.E, t1_);                                                         \
                     if (NH == 3) t2_ = fma(XA2[i], ev.E, t2_);                                            \

@@ -51,7 +51,7 @@ struct JobDev {
     uint32_t* Wc;   // [Tc][Kp]      scratch: words on the panel's common-SNP axis (all-SNP calls only)
     ReadDesc* desc;  // [R]
     TabEnt* tabs;    // table pool
-    double* dense;   // [n_dense][Kp]
+    TabEnt* dense;   // [n_dense][Kp] {E, 1/E} columns of the reads kept dense
     double* xprob;   // [R][4] label probabilities of the last visit (H_class is derived from them): normalised (slot 3 = -1)
                      // or the raw products of the fast decision path (slot 3 = label the read had)
     uint8_t* snp_type;  // [nSNPs] all-SNP calls: 0 common, 1 rare without carrier, 2 rare with carrier(s)

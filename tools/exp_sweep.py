@@ -11,11 +11,14 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 cfgs = sys.argv[1:] or [""]
 for c in cfgs:
     env = dict(os.environ)
+    extra = []
     for kv in c.split(","):
-        if "=" in kv:
+        if kv == "ALL":
+            extra.append("--all-snps")
+        elif "=" in kv:
             k, v = kv.split("=", 1)
             env["QUILT_B200_" + k] = v
-    r = subprocess.run([sys.executable, os.path.join(HERE, "prof_sweep.py"), "--K", "4096", "--jobs", "148", "--its", "8"], env=env,
+    r = subprocess.run([sys.executable, os.path.join(HERE, "prof_sweep.py"), "--K", "4096", "--jobs", "148", "--its", "8"] + extra, env=env,
                        capture_output=True, text=True)
     lines = [ln for ln in r.stderr.splitlines() if ln.startswith("{")]
     print(json.dumps({"cfg": c, "rc": r.returncode, "timing": lines[-1] if lines else r.stderr[-300:]}), flush=True)
