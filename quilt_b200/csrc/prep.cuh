@@ -157,23 +157,49 @@ __device__ __forceinline__ double emission_factor_apply(double E, int type, bool
     return E;
 }
 
-constexpr int TAB_WARPS = 4;
+constexpr int TAB_WARPS = 8;
 
-// one warp per table-mode read.  grid = (ceil(R_max / TAB_WARPS), jobs)
+// allele pattern from the three staged word columns (grids g-1, g, g+1) in shared memory
+__device__ __forceinline__ uint32_t read_pattern_staged(const ReadDesc& d, const uint32_t* Ws, int Kp, int k) {
+    if (d.mode == MODE_RUN) {
+        const uint32_t lo = Ws[(d.g0rel + 1) * Kp + k];
+        const uint32_t hi = (d.b0 + d.nb > 32) ? Ws[(d.g0rel + 2) * Kp + k] : 0u;
+        return __funnelshift_r(lo, hi, d.b0) & ((1u << d.nb) - 1u);
+    }
+    uint32_t pat = 0;
+    for (int j = 0; j < d.nb; j++) {
+        const int wr = d.sel[j] >> 5, b = d.sel[j] & 31;
+        pat |= ((Ws[wr * Kp + k] >> b) & 1u) << j;
+    }
+    return pat;
+}
+
+// One CTA per (grid, job): the allele words a read of this grid can touch (grids g-1 .. g+1) are staged in shared
+// memory once, then each warp takes table-mode reads of the grid in turn.  grid = (T, jobs), 256 threads,
+// dynamic shared memory = 3 * Kp * 4 bytes.
 __global__ void __launch_bounds__(TAB_WARPS * 32) k_build_tables(BatchParams P, const JobDev* __restrict__ jobs) {
+    extern __shared__ __align__(16) uint32_t Ws[];  // [3][Kp]
     __shared__ int hist[TAB_WARPS][1 << NBMAX];
     const JobDev& J = jobs[blockIdx.y];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int r = blockIdx.x * TAB_WARPS + warp;
-    if (r >= J.R) return;
-    ReadDesc d = J.desc[r];
-    if (d.mode == MODE_DENSE) return;
-    const int nb = d.nb, n = 1 << nb;
-    const int g = J.wif0[r];
-    const int uo = J.roff[r];
+    const int g = blockIdx.x, Kp = P.Kp, T = P.T;
+    const int r0 = J.rs[g], r1 = J.rs[g + 1];
+    if (r0 >= r1) return;
+    for (int i = threadIdx.x; i < 3 * Kp; i += TAB_WARPS * 32) {
+        const int w = i / Kp, k = i - w * Kp;
+        const int gg = g - 1 + w;
+        Ws[i] = (gg >= 0 && gg < T) ? J.W[(size_t)gg * Kp + k] : 0u;
+    }
+    __syncthreads();
     const bool rescale = (P.flags & QUILT_F_RESCALE_EMATREAD) != 0;
-    TabEnt* tab = J.tabs + d.off;
     int* hs = hist[warp];
+    for (int r = r0 + warp; r < r1; r += TAB_WARPS) {
+    ReadDesc d = J.desc[r];
+    if (d.mode == MODE_DENSE) continue;
+    const int nb = d.nb, n = 1 << nb;
+    const int uo = J.roff[r];
+    TabEnt* tab = J.tabs + d.off;
+    __syncwarp();
     // 1. raw products per allele pattern, factors applied in read order
     for (int pat = lane; pat < n; pat += 32) {
         double E = 1.0;
@@ -192,7 +218,7 @@ __global__ void __launch_bounds__(TAB_WARPS * 32) k_build_tables(BatchParams P, 
     for (int k0 = 0; k0 < P.K; k0 += 32) {
         const int k = k0 + lane;
         const bool in = k < P.K;
-        const uint32_t pat = in ? read_pattern_global(d, J.W, P.Kp, g, k) : 0xffffffffu;
+        const uint32_t pat = in ? read_pattern_staged(d, Ws, Kp, k) : 0xffffffffu;
         const uint32_t peers = __match_any_sync(0xffffffffu, pat);
         if (in && lane == __ffs(peers) - 1) hs[pat] += __popc(peers);
         __syncwarp();
@@ -257,6 +283,7 @@ __global__ void __launch_bounds__(TAB_WARPS * 32) k_build_tables(BatchParams P, 
         if (P.flags & QUILT_F_DISABLE_READ_CATEGORY_USAGE) cat = 0;
         J.desc[r].cat = (uint8_t)cat;
     }
+    }  // reads of the grid
 }
 
 // one CTA per dense-mode read (many SNPs, or SNPs outside grids wif0-1..wif0+1): the K-long column itself.

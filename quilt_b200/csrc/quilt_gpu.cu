@@ -804,8 +804,12 @@ int run_prep(QuiltGpuBatch* B, Bucket& bk, int n, const JobDev* dj) {
         k_unpack_common<<<dim3(kb, P.T, n), 256, 0, g_stream>>>(B->panel, dj, P.K, P.Kp, 0);
         LAUNCHED();
     }
-    k_build_tables<<<dim3((bk.R_max + TAB_WARPS - 1) / TAB_WARPS, n), TAB_WARPS * 32, 0, g_stream>>>(P, dj);
-    LAUNCHED();
+    {
+        const int tsm = 3 * P.Kp * 4;
+        CK(cudaFuncSetAttribute(k_build_tables, cudaFuncAttributeMaxDynamicSharedMemorySize, tsm));
+        k_build_tables<<<dim3(P.T, n), TAB_WARPS * 32, tsm, g_stream>>>(P, dj);
+        LAUNCHED();
+    }
     if (bk.n_dense_max > 0) {
         k_build_dense<<<dim3(bk.n_dense_max, n), 256, 0, g_stream>>>(P, dj);
         LAUNCHED();
