@@ -457,6 +457,7 @@ __global__ void __launch_bounds__(NT, (NT * EPT <= 512 ? 4 : (NT * EPT <= 1024 ?
     }
     if (tid < 16) cnt[tid] = 0;
     __syncthreads();
+    const int n_tab_total = tsG[T];
     uint32_t n_use0 = 0, n_use1 = 0, n_use2 = 0;  // completed uses of each stage barrier -> wait parity
 
     // staging of reads [ra, ra + n) with table entries [ta, ta + nt) into stage buffer s
@@ -485,13 +486,28 @@ __global__ void __launch_bounds__(NT, (NT * EPT <= 512 ? 4 : (NT * EPT <= 1024 ?
         {
             // scalars the serial chain needs at grid g: first reads / table offsets of the NEXT grid (so that its
             // package can be issued without a dependent global load), the transition pair into g, the previous c of g
+            // one predicated 4-byte cp.async per lane of warp 1 (no divergent single-thread blocks: warp 0 already
+            // carries the bulk-copy issue, and everything a single warp does alone delays the next block barrier)
             unsigned char* sc = smem + L.off_sc + s * 64;
-            if (tid == 0) cp_async4(sc + 0, rs + g + 1);
-            if (tid == 1 && g + 2 <= T) cp_async4(sc + 4, rs + g + 2);
-            if (tid == 2) cp_async4(sc + 8, tsG + g + 1);
-            if (tid == 3 && g + 2 <= T) cp_async4(sc + 12, tsG + g + 2);
-            if (tid == 4 && g >= 1) cp_async16(sc + 16, tmG + 2 * (g - 1));
-            if (tid >= 5 && tid < 5 + NH) cp_async8(sc + 32 + 8 * (tid - 5), cG + (tid - 5) * T + g);
+            const int q = tid - 32;
+            if (q >= 0 && q < 8 + 2 * NH) {
+                const int32_t* src;
+                bool ok = true;
+                if (q < 2) {
+                    src = rs + g + 1 + q;
+                    ok = g + 1 + q <= T;
+                } else if (q < 4) {
+                    src = tsG + g + 1 + (q - 2);
+                    ok = g + 1 + (q - 2) <= T;
+                } else if (q < 8) {
+                    src = reinterpret_cast<const int32_t*>(tmG + 2 * (g - 1)) + (q - 4);
+                    ok = g >= 1;
+                } else {
+                    const int hh = (q - 8) >> 1;
+                    src = reinterpret_cast<const int32_t*>(cG + hh * T + g) + ((q - 8) & 1);
+                }
+                if (ok) cp_async4(sc + 4 * q, src);
+            }
         }
         if (tid == 0) {
             uint32_t bytes = 0;
@@ -518,6 +534,24 @@ __global__ void __launch_bounds__(NT, (NT * EPT <= 512 ? 4 : (NT * EPT <= 1024 ?
             }
         }
         if (!small_done) cp_async_commit();
+        // Pull the FOLLOWING grid's read metadata towards L2 (a window from its first read / table entry on): the
+        // cp.async package above is waited for by the next block barrier (measured), so its latency is on the serial
+        // chain; when the lines already sit in L2 that wait is an L2 hit, not a DRAM round trip.
+        if (!(P.dbg & 8)) {
+            constexpr int PF_READS = 32, PF_TAB = 512;
+            const int nd = min(PF_READS, R - r1), ntb = min(PF_TAB, n_tab_total - t1);
+            const int l_desc = (nd * 32 + 127) >> 7, l_tab = (ntb * 16 + 127) >> 7, l_u = (nd * 8 + 127) >> 7, l_h = (nd * 4 + 127) >> 7;
+            int l = tid;
+            if (l < l_desc) {
+                prefetch_l2(reinterpret_cast<const char*>(J.desc + r1) + (l << 7));
+            } else if ((l -= l_desc) < l_tab) {
+                prefetch_l2(reinterpret_cast<const char*>(J.tabs + t1) + (l << 7));
+            } else if ((l -= l_tab) < l_u) {
+                prefetch_l2(reinterpret_cast<const char*>(U + r1) + (l << 7));
+            } else if ((l -= l_u) < l_h) {
+                prefetch_l2(reinterpret_cast<const char*>(J.H + r1) + (l << 7));
+            }
+        }
     };
     auto wait_pkg = [&](int g) {
         const int s = g & 1;
@@ -567,6 +601,7 @@ __global__ void __launch_bounds__(NT, (NT * EPT <= 512 ? 4 : (NT * EPT <= 1024 ?
         }
         if (g + 1 < T) {
             if (!(P.dbg & 2)) issue_pkg(g + 1, r1, nx_r1, ts1, nx_t1);
+            if (P.dbg & 4) cp_async_wait_all();  // experiment: does the next barrier already wait for the cp.async package?
             // pull the next grid's beta columns towards L2 (one 128-byte line per 16 doubles)
             if (nx_r1 > r1 && !(P.dbg & 1)) {
                 const int lines = (NH * Kp) >> 4;
@@ -1005,10 +1040,17 @@ __global__ void __launch_bounds__(NT, (NT * EPT <= 512 ? 4 : (NT * EPT <= 1024 ?
                 for (int h = 0; h < NH; h++) bulk_g2s(dst + (size_t)h * KA, eGg + ((size_t)h * T + g + 1) * Kp, Kp * 8, &bar[q]);
             }
             unsigned char* sc = smem + L.off_sc + (2 + q) * 64;
-            if (tid == 0) cp_async4(sc + 0, rs + g + 1);
-            if (tid == 1) cp_async4(sc + 4, rs + g + 2);
-            if (tid == 4) cp_async16(sc + 16, tmG + 2 * g);
-            if (tid >= 5 && tid < 5 + NH) cp_async8(sc + 32 + 8 * (tid - 5), cG + (tid - 5) * T + g);
+            const int ql = tid - 32;
+            if (ql >= 0 && ql < 8 + 2 * NH && (ql < 2 || ql >= 4)) {
+                const int32_t* src;
+                if (ql < 2)
+                    src = rs + g + 1 + ql;
+                else if (ql < 8)
+                    src = reinterpret_cast<const int32_t*>(tmG + 2 * g) + (ql - 4);
+                else
+                    src = reinterpret_cast<const int32_t*>(cG + ((ql - 8) >> 1) * T + g) + ((ql - 8) & 1);
+                cp_async4(sc + 4 * ql, src);
+            }
         };
 #pragma unroll
         for (int j = 0; j < NSB - 1; j++) {
