@@ -462,14 +462,20 @@ __global__ void __launch_bounds__(NT, (NT * EPT <= 512 ? 4 : (NT * EPT <= 1024 ?
 
     // staging of reads [ra, ra + n) with table entries [ta, ta + nt) into stage buffer s
     auto stage_small = [&](int s, int ra, int n, int ta, int nt, bool async) {
+        // warp 0 issues the bulk copies of the package; the other warps share the cp.async staging so that no warp
+        // reaches the next block barrier much later than the rest
         unsigned char* sm = smem + L.off_small[s];
-        const unsigned char* gd = reinterpret_cast<const unsigned char*>(J.desc + ra);
-        for (int i = tid; i < n * 2; i += NT) cp_async16(sm + L.small_desc + i * 16, gd + i * 16);
-        const unsigned char* gt = reinterpret_cast<const unsigned char*>(J.tabs + ta);
-        for (int i = tid; i < nt; i += NT) cp_async16(sm + L.small_tab + i * 16, gt + i * 16);
-        for (int i = tid; i < n; i += NT) {
-            cp_async8(sm + L.small_U + i * 8, U + ra + i);
-            cp_async4(sm + L.small_H + i * 4, J.H + ra + i);
+        constexpr int NS = (NT > 32) ? NT - 32 : NT;
+        const int t2 = (NT > 32) ? tid - 32 : tid;
+        if (t2 >= 0) {
+            const unsigned char* gd = reinterpret_cast<const unsigned char*>(J.desc + ra);
+            for (int i = t2; i < n * 2; i += NS) cp_async16(sm + L.small_desc + i * 16, gd + i * 16);
+            const unsigned char* gt = reinterpret_cast<const unsigned char*>(J.tabs + ta);
+            for (int i = t2; i < nt; i += NS) cp_async16(sm + L.small_tab + i * 16, gt + i * 16);
+            for (int i = t2; i < n; i += NS) {
+                cp_async8(sm + L.small_U + i * 8, U + ra + i);
+                cp_async4(sm + L.small_H + i * 4, J.H + ra + i);
+            }
         }
         cp_async_commit();
         if (!async) {
@@ -541,8 +547,9 @@ __global__ void __launch_bounds__(NT, (NT * EPT <= 512 ? 4 : (NT * EPT <= 1024 ?
             constexpr int PF_READS = 32, PF_TAB = 512;
             const int nd = min(PF_READS, R - r1), ntb = min(PF_TAB, n_tab_total - t1);
             const int l_desc = (nd * 32 + 127) >> 7, l_tab = (ntb * 16 + 127) >> 7, l_u = (nd * 8 + 127) >> 7, l_h = (nd * 4 + 127) >> 7;
-            int l = tid;
-            if (l < l_desc) {
+            int l = tid - 64;  // (warps 0 and 1 carry the bulk-copy issue and the scalar package)
+            if (l < 0) {
+            } else if (l < l_desc) {
                 prefetch_l2(reinterpret_cast<const char*>(J.desc + r1) + (l << 7));
             } else if ((l -= l_desc) < l_tab) {
                 prefetch_l2(reinterpret_cast<const char*>(J.tabs + t1) + (l << 7));
@@ -605,7 +612,7 @@ __global__ void __launch_bounds__(NT, (NT * EPT <= 512 ? 4 : (NT * EPT <= 1024 ?
             // pull the next grid's beta columns towards L2 (one 128-byte line per 16 doubles)
             if (nx_r1 > r1 && !(P.dbg & 1)) {
                 const int lines = (NH * Kp) >> 4;
-                for (int l = tid; l < lines; l += NT) {
+                for (int l = (NT > 32 ? tid - 32 : tid); l >= 0 && l < lines; l += (NT > 32 ? NT - 32 : NT)) {
                     const int h = l / (Kp >> 4), q = l - h * (Kp >> 4);
                     prefetch_l2(betaG + ((size_t)h * T + g + 1) * Kp + (q << 4));
                 }
@@ -937,11 +944,11 @@ __global__ void __launch_bounds__(NT, (NT * EPT <= 512 ? 4 : (NT * EPT <= 1024 ?
                             pC.a = (hC == 0) ? sv[0] : sv[1];
                             pC.b = (hC == 0) ? sv[1] : sv[0];
                         }
-                        if (record && tid == 0) {
-                            J.xprob[4 * (size_t)r + 0] = F.prod_pC;
-                            J.xprob[4 * (size_t)r + 1] = F.prod_pA1;
-                            J.xprob[4 * (size_t)r + 2] = F.prod_pA2;
-                            J.xprob[4 * (size_t)r + 3] = (double)hC;  // raw products of a read whose label was hC
+                        if (record && tid >= NT - 4) {
+                            // (last warp, one lane per slot: warp 0 already carries the label store and the bulk-copy issue)
+                            const int q = tid - (NT - 4);
+                            const double v = q == 0 ? F.prod_pC : (q == 1 ? F.prod_pA1 : (q == 2 ? F.prod_pA2 : (double)hC));
+                            J.xprob[4 * (size_t)r + q] = v;  // raw products of a read whose label was hC
                         }
                     } else {
                         D = decide_read<NH>(pC, sv, hC, KIND_NORMAL, Us[ir], prior);
