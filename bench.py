@@ -40,6 +40,8 @@ WORKLOADS = {
     # name: K, K_full, nSNPs (common), all-SNP factor, region bp, coverage, samples per GPU per step
     "chr20_2Mb_1x_K4096": dict(K=4096, K_full=5008, nSNPs=32000, factor=3, region_bp=3_000_000, coverage=1.0, samples=37),
     "chr20_2Mb_1x_K512": dict(K=512, K_full=5008, nSNPs=32000, factor=3, region_bp=3_000_000, coverage=1.0, samples=64),
+    # BASELINE.json config #4 (per-GPU share): NIPT, three haplotypes, fetal fraction 10 %, 0.5x, K = 2048; common-SNP calls only
+    "nipt_2Mb_0.5x_K2048": dict(K=2048, K_full=5008, nSNPs=32000, factor=0, region_bp=3_000_000, coverage=0.5, samples=48, ff=0.1),
     "tiny": dict(K=256, K_full=600, nSNPs=3200, factor=3, region_bp=300_000, coverage=1.0, samples=4),
 }
 METRIC = "diploid samples/sec, chr20 2Mb @1x cov, K=4096, 5008-hap panel; 1/2/4/8 GPU"
@@ -119,8 +121,10 @@ def build_inputs(wl, rank, world_obj, log):
     n_samples = wl["samples"]
     for s in range(n_samples):
         seed = 1000 * (rank + 1) + s
-        sr = synth.make_sample_reads(world_obj, seed, coverage=wl["coverage"], region_bp=wl["region_bp"])
-        calls += schedule.sample_calls(world_obj, sr, seed + 7, K=wl["K"])
+        ff = wl.get("ff", 0.0)
+        sr = synth.make_sample_reads(world_obj, seed, coverage=wl["coverage"], region_bp=wl["region_bp"], n_true_haps=3 if ff > 0 else 2,
+                                     hap_probs=(0.5, 0.5 - ff / 2, ff / 2) if ff > 0 else None)
+        calls += schedule.sample_calls(world_obj, sr, seed + 7, K=wl["K"], ff=ff, impute_rare_common=wl["factor"] > 0)
     log(f"inputs: {n_samples} samples -> {len(calls)} Gibbs calls in {time.time() - t0:.1f}s")
     return calls
 
@@ -146,11 +150,15 @@ def cpu_arm(wl, world_obj, log, budget_calls_per_thread=1):
     mem_cap = max(1, int(psutil.virtual_memory().available / 1e9 / per_thread_gb))
     threads = max(1, min(cores, mem_cap))
     jobs = []
+    ff = wl.get("ff", 0.0)
+    has_all = wl["factor"] > 0
     for t in range(threads):
-        sr = synth.make_sample_reads(world_obj, 777000 + t, coverage=wl["coverage"], region_bp=wl["region_bp"])
+        sr = synth.make_sample_reads(world_obj, 777000 + t, coverage=wl["coverage"], region_bp=wl["region_bp"], n_true_haps=3 if ff > 0 else 2,
+                                     hap_probs=(0.5, 0.5 - ff / 2, ff / 2) if ff > 0 else None)
         kind = "iterative" if t % 3 == 0 else "normal"
-        jobs.append((kind, synth.make_call(world_obj, sr.common, 5000 + t, K=K, first_iteration=(kind == "iterative"))))
-        jobs.append(("all", synth.make_call(world_obj, sr.all, 6000 + t, K=K, all_snps=True, sort_haps=False)))
+        jobs.append((kind, synth.make_call(world_obj, sr.common, 5000 + t, K=K, first_iteration=(kind == "iterative"), ff=ff)))
+        if has_all:
+            jobs.append(("all", synth.make_call(world_obj, sr.all, 6000 + t, K=K, all_snps=True, sort_haps=False, ff=ff)))
 
     def run(job):
         t0 = time.perf_counter()
@@ -168,7 +176,7 @@ def cpu_arm(wl, world_obj, log, budget_calls_per_thread=1):
         tt[k].append(v)
     t_it = statistics.mean(tt["iterative"]) if tt["iterative"] else statistics.mean(tt["normal"])
     t_no = statistics.mean(tt["normal"]) if tt["normal"] else t_it
-    t_all = statistics.mean(tt["all"])
+    t_all = statistics.mean(tt["all"]) if tt["all"] else 0.0
     per_sample = 8 * t_it + 16 * t_no + 8 * t_all
     value = threads / per_sample
     log(f"cpu arm: {threads} threads ({cores} cores), t_iterative {t_it:.2f}s t_normal {t_no:.2f}s t_all {t_all:.2f}s -> {value:.4f} samples/s (wall {wall:.1f}s)")
@@ -197,6 +205,9 @@ def main():
     if args.warmup < 3:
         args.warmup = 3
     wl = dict(WORKLOADS[args.workload])
+    global METRIC
+    if args.workload != "chr20_2Mb_1x_K4096":
+        METRIC = f"samples/sec, workload {args.workload} (not the BASELINE.json headline configuration)"
     if args.samples > 0:
         wl["samples"] = args.samples
 
@@ -212,7 +223,7 @@ def main():
         "workload": args.workload,
         "K": wl["K"], "K_full": wl["K_full"], "nSNPs_common": wl["nSNPs"], "nSNPs_all": wl["nSNPs"] * wl["factor"],
         "nGrids": (wl["nSNPs"] + 31) // 32, "nGrids_all": (wl["nSNPs"] * wl["factor"] + 31) // 32,
-        "coverage": wl["coverage"], "samples_per_gpu_per_step": wl["samples"], "calls_per_sample": 32,
+        "coverage": wl["coverage"], "samples_per_gpu_per_step": wl["samples"], "calls_per_sample": 32 if wl["factor"] > 0 else 24, "ff": wl.get("ff", 0.0),
         "schedule": "8 chains x (3 common-SNP calls + 1 all-SNP call), 20+1 sweeps, shard passes at sweeps 3/6/9",
         "parallelism": f"samples sharded over {args.gpus} GPU(s), no data-path collective",
         "l2": "per-wave working set (>= 29 GB of alpha/beta/eMatGrid columns) is far larger than the 126 MB L2",

@@ -23,6 +23,7 @@ def sample_calls(
     nGibbsSamples: int = 7,
     n_seek_its: int = 3,
     impute_rare_common: bool = True,
+    ff: float = 0.0,
 ) -> List[cabi.GibbsCall]:
     """all Gibbs calls of one sample at QUILT2 defaults: (nGibbsSamples + 1) x (n_seek_its common + 1 all-SNP)"""
     calls: List[cabi.GibbsCall] = []
@@ -30,10 +31,10 @@ def sample_calls(
     for chain in range(nGibbsSamples + 1):
         for i_it in range(n_seek_its):
             calls.append(
-                synth.make_call(world, reads.common, int(rng.integers(1 << 31)), K=K, first_iteration=(i_it == 0), sort_haps=(i_it == 0))
+                synth.make_call(world, reads.common, int(rng.integers(1 << 31)), K=K, first_iteration=(i_it == 0), sort_haps=(i_it == 0), ff=ff)
             )
         if impute_rare_common and reads.all is not None:
-            calls.append(synth.make_call(world, reads.all, int(rng.integers(1 << 31)), K=K, all_snps=True, sort_haps=False))
+            calls.append(synth.make_call(world, reads.all, int(rng.integers(1 << 31)), K=K, all_snps=True, sort_haps=False, ff=ff))
     return calls
 
 
