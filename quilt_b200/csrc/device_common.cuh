@@ -104,6 +104,22 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
                  : "memory");
 }
 
+// ---------------------------------------------------------------- thread-block cluster (K > 4096: two CTAs per job)
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// store a double into the same shared-memory location of CTA `rank` of the cluster (distributed shared memory)
+__device__ __forceinline__ void st_dsmem(double* local_ptr, uint32_t rank, double v) {
+    uint32_t ra;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(local_ptr)), "r"(rank));
+    asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(ra), "d"(v) : "memory");
+}
+
 // streaming global access (state columns are touched once per pass: keep them out of L1)
 __device__ __forceinline__ double ld_stream(const double* p) {
     double v;

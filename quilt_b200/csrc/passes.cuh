@@ -227,29 +227,34 @@ __device__ __forceinline__ void prefetch_cols(const double* p, size_t stride, in
 // generic step and, after every grid, decides between "stay" and "swap labels from here on"; then the generic
 // backward of both haplotypes in one walk.  Columns are pulled into L2 two grids ahead and the per-grid scalars
 // travel one grid ahead in registers, so a step costs its reductions, not a DRAM round trip.
-template <int NT, int EPT>
+// CL = 2: two-CTA cluster, each CTA owns half of the K states (see k_sweep).
+template <int NT, int EPT, int CL = 1>
 __global__ void __launch_bounds__(NT) k_shard(BatchParams P, const JobDev* __restrict__ jobs, int episode) {
-    __shared__ double red[2 * SW_VMAX * (NT / 32)];
+    __shared__ double red[2 * CL * SW_VMAX * (NT / 32)];
     __shared__ JobDev Js;
     const int tid = threadIdx.x;
-    if (tid == 0) Js = jobs[blockIdx.x];
+    if (tid == 0) Js = jobs[blockIdx.x / CL];
     __syncthreads();
     if (*Js.underflow) return;
-    const int K = P.K, Kp = P.Kp, T = P.T, R = Js.R;
-    double* __restrict__ alphaG = Js.alpha;
-    double* __restrict__ betaG = Js.beta;
-    double* __restrict__ eGg = Js.eG;
+    const uint32_t crank = (CL > 1) ? cluster_ctarank() : 0u;
+    const int kbase = (int)crank * (NT * EPT);
+    const int K = max(0, min(P.K - kbase, NT * EPT));  // states of this CTA
+    const int Kp = P.Kp, T = P.T, R = Js.R;
+    const int Kpl = max(0, min(P.Kp - kbase, NT * EPT));  // padded states of this CTA
+    double* __restrict__ alphaG = Js.alpha + kbase;
+    double* __restrict__ betaG = Js.beta + kbase;
+    double* __restrict__ eGg = Js.eG + kbase;
     double* cG = Js.c;
     double* rateG = Js.rate;
     const double* __restrict__ tmG = Js.tm;
-    BlockSumV<NT> bsum(red);
+    BlockSumV<NT, CL> bsum(red, crank);
     const double prior = P.one_over_K;
     const double* __restrict__ runif = Js.runif_shard + (size_t)episode * (T - 1);
     const size_t hs = (size_t)T * Kp;  // haplotype stride
     double mloc[2];
     {
         double sl[2] = {0, 0};
-        for (int g = tid; g < T; g += NT) {
+        for (int g = tid + (int)crank * NT; g < T; g += NT * CL) {  // (cluster: grids split over the two CTAs)
             sl[0] += log(ld_cg(cG + g));
             sl[1] += log(ld_cg(cG + T + g));
         }
@@ -263,8 +268,8 @@ __global__ void __launch_bounds__(NT) k_shard(BatchParams P, const JobDev* __res
 #pragma unroll
     for (int h = 0; h < 2; h++) Col<NT, EPT>::load(e[h], eGg + h * hs, K, 0.0);
     if (T > 1) {
-        prefetch_cols<NT>(eGg + Kp, hs, 2, Kp);
-        prefetch_cols<NT>(betaG + Kp, hs, 2, Kp);
+        prefetch_cols<NT>(eGg + Kp, hs, 2, Kpl);
+        prefetch_cols<NT>(betaG + Kp, hs, 2, Kpl);
     }
     double clast[2] = {1, 1};
     double nx_c[2] = {ld_cg(cG), ld_cg(cG + T)};
@@ -287,8 +292,8 @@ __global__ void __launch_bounds__(NT) k_shard(BatchParams P, const JobDev* __res
             for (int h = 0; h < 2; h++) Col<NT, EPT>::load(y[h], betaG + h * hs + (size_t)g * Kp, K, 0.0);
         }
         if (g + 2 < T) {
-            prefetch_cols<NT>(eGg + (size_t)(g + 2) * Kp, hs, 2, Kp);
-            prefetch_cols<NT>(betaG + (size_t)(g + 2) * Kp, hs, 2, Kp);
+            prefetch_cols<NT>(eGg + (size_t)(g + 2) * Kp, hs, 2, Kpl);
+            prefetch_cols<NT>(betaG + (size_t)(g + 2) * Kp, hs, 2, Kpl);
         }
         double cn[2];
         if (g == 0) {
@@ -378,9 +383,11 @@ __global__ void __launch_bounds__(NT) k_shard(BatchParams P, const JobDev* __res
         }
     }
     __syncthreads();
-    // relabel the reads of every grid walked in flip mode
-    for (int r = tid; r < R; r += NT) {
-        if (rateG[Js.wif0[r]] != 0.0) Js.H[r] = 3 - Js.H[r];
+    // relabel the reads of every grid walked in flip mode (once per job: the first CTA of a cluster)
+    if (crank == 0) {
+        for (int r = tid; r < R; r += NT) {
+            if (rateG[Js.wif0[r]] != 0.0) Js.H[r] = 3 - Js.H[r];
+        }
     }
     // generic backward on the (possibly swapped) eMatGrid columns, both haplotypes in one walk
     // (every thread re-reads only eMatGrid elements it wrote itself above, so no fence is needed)
@@ -393,7 +400,7 @@ __global__ void __launch_bounds__(NT) k_shard(BatchParams P, const JobDev* __res
             Col<NT, EPT>::store(b[h], betaG + h * hs + (size_t)(T - 1) * Kp, K);
             if (T >= 2) Col<NT, EPT>::load(ee[h], eGg + h * hs + (size_t)(T - 1) * Kp, K, 0.0);
         }
-        if (T >= 3) prefetch_cols<NT>(eGg + (size_t)(T - 2) * Kp, hs, 2, Kp);
+        if (T >= 3) prefetch_cols<NT>(eGg + (size_t)(T - 2) * Kp, hs, 2, Kpl);
         double nb_c[2] = {0, 0}, nb_t0 = 0, nb_t1 = 0;
         if (T >= 2) {
             nb_c[0] = ld_cg(cG + T - 2);
@@ -412,7 +419,7 @@ __global__ void __launch_bounds__(NT) k_shard(BatchParams P, const JobDev* __res
                 nb_t0 = tmG[2 * (g - 1)];
                 nb_t1 = tmG[2 * (g - 1) + 1];
             }
-            if (g >= 2) prefetch_cols<NT>(eGg + (size_t)(g - 1) * Kp, hs, 2, Kp);
+            if (g >= 2) prefetch_cols<NT>(eGg + (size_t)(g - 1) * Kp, hs, 2, Kpl);
             double sv[2] = {0, 0};
 #pragma unroll
             for (int h = 0; h < 2; h++) {

@@ -296,6 +296,7 @@ int get_panel(const QuiltPanel* p, PanelDev* out) {
 // ------------------------------------------------------------------------------------------------ geometry
 struct Geo {
     int NT, EPT;
+    int CL = 1;  // CTAs per job in the sweep / shard kernels (thread-block cluster splitting the K states)
 };
 bool pick_geo(int K, Geo* g, int NH = 2) {
     if (NH == 3 && K > 2048) return false;  // three eMatGrid columns per stage: the shared-memory ring holds K <= 2048
@@ -308,7 +309,7 @@ bool pick_geo(int K, Geo* g, int NH = 2) {
         if (e) std::sscanf(e, "%dx%d", &env_nt, &env_ept);
     }
     if (env_nt > 0 && env_nt * env_ept >= K) {
-        *g = {env_nt, env_ept};
+        *g = {env_nt, env_ept, 1};
         return true;
     }
     if (K <= 512)
@@ -318,7 +319,9 @@ bool pick_geo(int K, Geo* g, int NH = 2) {
     else if (K <= 2048)
         *g = {512, 4};
     else if (K <= 4096)
-        *g = {256, 16};  // measured 8% faster than 512 x 8 on the K = 4096 benchmark (profiles/README.md)
+        *g = {256, 16};  // measured 19% faster than 512 x 8 on the K = 4096 benchmark
+    else if (K <= 8192 && NH == 2)
+        *g = {256, 16, 2};  // two-CTA cluster, 4096 states per CTA
     else
         return false;
     return true;
@@ -596,7 +599,7 @@ int validate(const QuiltGibbsArgs& a) {
     if (!a.panel) return set_err(QUILT_ERR_BAD_ARG, "panel is NULL");
     if (a.K <= 0 || a.nGrids <= 0 || a.nSNPs <= 0) return set_err(QUILT_ERR_BAD_ARG, "bad K / nGrids / nSNPs");
     if (a.nGrids != (a.nSNPs + 31) / 32) return set_err(QUILT_ERR_UNSUPPORTED, "grid must be 32 SNPs per grid (grid32)");
-    if (a.K > 4096) return set_err(QUILT_ERR_UNSUPPORTED, "Ksubset > 4096 not supported yet");
+    if (a.K > 8192) return set_err(QUILT_ERR_UNSUPPORTED, "Ksubset > 8192 not supported");
     const bool diploid = (a.flags & QUILT_F_SAMPLE_IS_DIPLOID) != 0;
     if (diploid && a.ff != 0) return set_err(QUILT_ERR_BAD_ARG, "sample_is_diploid with ff != 0");
     if (!diploid) {
@@ -673,10 +676,38 @@ template <int NT, int EPT>
 constexpr bool nipt_geo() {
     return NT * EPT <= 2048;
 }
+// launch of a kernel whose CTAs come in clusters of CL (CL = 1: plain launch)
+template <typename... KArgs, typename... Args>
+cudaError_t launch_cl(void (*kern)(KArgs...), int n_ctas, int nt, size_t smem, int CL, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(n_ctas);
+    cfg.blockDim = dim3(nt);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = g_stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, args...);
+}
+
 template <int NT, int EPT>
-int sweep_occupancy(int Kp, int NH, int* occ, int* smem) {
-    const SweepSmemLayout L = sweep_smem_layout(NT * EPT, NH, NT);
+int sweep_occupancy(int Kp, int NH, int CL, int* occ, int* smem) {
+    const SweepSmemLayout L = sweep_smem_layout(NT * EPT, NH, NT, CL);
     *smem = L.total;
+    if (CL == 2) {
+        if constexpr (NT == 256 && EPT == 16) {
+            if (NH != 2) return set_err(QUILT_ERR_UNSUPPORTED, "cluster sweep is diploid-only");
+            CK(cudaFuncSetAttribute(k_sweep<NT, EPT, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+            *occ = 1;  // one CTA per SM; a job takes two SMs
+            return QUILT_OK;
+        } else {
+            return set_err(QUILT_ERR_UNSUPPORTED, "no cluster sweep kernel for this geometry");
+        }
+    }
     if (NH == 2) {
         CK(cudaFuncSetAttribute(k_sweep<NT, EPT, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, k_sweep<NT, EPT, 2>, NT, L.total));
@@ -693,7 +724,7 @@ int setup_bucket(QuiltGpuBatch* B, Bucket& bk, size_t* mem_budget) {
     const BatchParams& P = bk.P;
     if (!pick_geo(P.K, &bk.geo, P.NH)) return set_err(QUILT_ERR_UNSUPPORTED, "Ksubset too large");
     int occ = 0, smem = 0;
-    int rc = with_geo(bk.geo, [&](auto nt, auto ept) { return sweep_occupancy<decltype(nt)::value, decltype(ept)::value>(P.Kp, P.NH, &occ, &smem); });
+    int rc = with_geo(bk.geo, [&](auto nt, auto ept) { return sweep_occupancy<decltype(nt)::value, decltype(ept)::value>(P.Kp, P.NH, bk.geo.CL, &occ, &smem); });
     if (rc != QUILT_OK) return rc;
     if (occ < 1) return set_err(QUILT_ERR_UNSUPPORTED, "sweep kernel does not fit on an SM for this K");
     for (int ji : bk.jobs) {
@@ -718,7 +749,7 @@ int setup_bucket(QuiltGpuBatch* B, Bucket& bk, size_t* mem_budget) {
     bk.o_hapLocal = o, o += al(P.rare_common ? (size_t)P.nSNPs * 24 : 0);
     bk.o_blk = o, o += al(P.NH == 3 ? BlockScratch::bytes(P.T) : 0);
     bk.slot_bytes = o;
-    int cap = g_sms * occ;
+    int cap = (g_sms / bk.geo.CL) * occ;
     const size_t by_mem = std::max<size_t>(1, *mem_budget / std::max<size_t>(bk.slot_bytes, 1));
     bk.n_slots = (int)std::min<size_t>(std::min<size_t>(cap, bk.jobs.size()), by_mem);
     CK(bk.djobs.alloc(bk.jobs.size() * sizeof(JobDev)));
@@ -821,9 +852,16 @@ int run_prep(QuiltGpuBatch* B, Bucket& bk, int n, const JobDev* dj) {
 template <int NT, int EPT>
 int run_wave_t(QuiltGpuBatch* B, Bucket& bk, int n, const JobDev* dj, bool timed) {
     const BatchParams& P = bk.P;
-    const SweepSmemLayout L = sweep_smem_layout(NT * EPT, P.NH, NT);
+    const int CL = bk.geo.CL;
+    const SweepSmemLayout L = sweep_smem_layout(NT * EPT, P.NH, NT, CL);
     // (buckets of different K share a template instance: re-arm the opt-in shared-memory size for this one)
-    if (P.NH == 2) {
+    if (CL == 2) {
+        if constexpr (NT == 256 && EPT == 16) {
+            CK(cudaFuncSetAttribute(k_sweep<NT, EPT, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+        } else {
+            return set_err(QUILT_ERR_UNSUPPORTED, "no cluster sweep kernel for this geometry");
+        }
+    } else if (P.NH == 2) {
         CK(cudaFuncSetAttribute(k_sweep<NT, EPT, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
     } else if constexpr (nipt_geo<NT, EPT>()) {
         CK(cudaFuncSetAttribute(k_sweep<NT, EPT, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
@@ -840,7 +878,10 @@ int run_wave_t(QuiltGpuBatch* B, Bucket& bk, int n, const JobDev* dj, bool timed
     } else {
         k_make_eG<<<dim3(P.T, n), 256, 0, g_stream>>>(P, dj);
         LAUNCHED();
-        k_fb_generic<NT, EPT><<<dim3(n, P.NH), NT, 0, g_stream>>>(P, dj, 1);
+        if (CL == 2)
+            k_fb_generic<512, 16><<<dim3(n, P.NH), 512, 0, g_stream>>>(P, dj, 1);  // one CTA holds all K <= 8192 states here
+        else
+            k_fb_generic<NT, EPT><<<dim3(n, P.NH), NT, 0, g_stream>>>(P, dj, 1);
         LAUNCHED();
     }
     int episode = 0;
@@ -856,7 +897,9 @@ int run_wave_t(QuiltGpuBatch* B, Bucket& bk, int n, const JobDev* dj, bool timed
             for (int b : bk.block_its) blk_next = blk_next || (b == it);
         // alpha columns are written only when a consumer follows this sweep (see k_sweep)
         const int store_alpha = (it >= P.n_burn || (P.NH == 3 && blk_next) || bk.debug || it == P.n_its - 1) ? 1 : 0;
-        if (P.NH == 2) {
+        if (CL == 2) {
+            if constexpr (NT == 256 && EPT == 16) CK(launch_cl(k_sweep<NT, EPT, 2, 2>, 2 * n, NT, (size_t)L.total, 2, P, dj, it, store_alpha));
+        } else if (P.NH == 2) {
             k_sweep<NT, EPT, 2><<<n, NT, L.total, g_stream>>>(P, dj, it, store_alpha);
         } else if constexpr (nipt_geo<NT, EPT>()) {
             k_sweep<NT, EPT, 3><<<n, NT, L.total, g_stream>>>(P, dj, it, store_alpha);
@@ -897,7 +940,11 @@ int run_wave_t(QuiltGpuBatch* B, Bucket& bk, int n, const JobDev* dj, bool timed
                 }
             }
             if (bk.do_shard && P.T > 1) {
-                k_shard<NT, EPT><<<n, NT, 0, g_stream>>>(P, dj, episode);
+                if (CL == 2) {
+                    if constexpr (NT == 256 && EPT == 16) CK(launch_cl(k_shard<NT, EPT, 2>, 2 * n, NT, (size_t)0, 2, P, dj, episode));
+                } else {
+                    k_shard<NT, EPT><<<n, NT, 0, g_stream>>>(P, dj, episode);
+                }
                 LAUNCHED();
             }
             episode++;
@@ -1459,7 +1506,7 @@ int quilt_gpu_forward_backward(int32_t K, int32_t T, const double* eMatGrid_t, c
     int rc = ensure_device();
     if (rc != QUILT_OK) return rc;
     Geo geo;
-    if (!pick_geo(K, &geo)) return set_err(QUILT_ERR_UNSUPPORTED, "K > 4096 not supported yet");
+    if (!pick_geo(K, &geo)) return set_err(QUILT_ERR_UNSUPPORTED, "K > 8192 not supported");
     const int Kp = (K + 31) & ~31;
     const size_t cols = (size_t)T * Kp;
     DBuf da, db, de, dc, dtm, dj, du;
@@ -1490,11 +1537,17 @@ int quilt_gpu_forward_backward(int32_t K, int32_t T, const double* eMatGrid_t, c
     P.T = T;
     P.NH = 1;
     P.one_over_K = 1 / double(K);
-    rc = with_geo(geo, [&](auto nt, auto ept) {
-        k_fb_generic<decltype(nt)::value, decltype(ept)::value><<<dim3(1, 1), decltype(nt)::value, 0, g_stream>>>(P, (const JobDev*)dj.p, 1);
+    if (geo.CL == 2) {
+        k_fb_generic<512, 16><<<dim3(1, 1), 512, 0, g_stream>>>(P, (const JobDev*)dj.p, 1);
         LAUNCHED();
-        return QUILT_OK;
-    });
+        rc = QUILT_OK;
+    } else {
+        rc = with_geo(geo, [&](auto nt, auto ept) {
+            k_fb_generic<decltype(nt)::value, decltype(ept)::value><<<dim3(1, 1), decltype(nt)::value, 0, g_stream>>>(P, (const JobDev*)dj.p, 1);
+            LAUNCHED();
+            return QUILT_OK;
+        });
+    }
     if (rc != QUILT_OK) return rc;
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(g_stream));

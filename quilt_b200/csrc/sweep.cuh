@@ -34,13 +34,13 @@ struct SweepSmemLayout {
     int off_bar, off_red, off_cnt, off_sc, off_small[2], off_pat, off_part, off_rec, off_W, off_eG, total;
     int small_desc, small_tab, small_U, small_H;
 };
-__host__ __device__ inline SweepSmemLayout sweep_smem_layout(int KA, int NH, int NT) {
+__host__ __device__ inline SweepSmemLayout sweep_smem_layout(int KA, int NH, int NT, int CL = 1) {
     SweepSmemLayout L;
     int o = 0;
     L.off_bar = o;
     o += 64;
     L.off_red = o;
-    o += 2 * SW_VMAX * (NT / 32) * 8;
+    o += 2 * CL * SW_VMAX * (NT / 32) * 8;
     o = (o + 127) & ~127;
     L.off_cnt = o;
     o += 128;
@@ -68,17 +68,60 @@ __host__ __device__ inline SweepSmemLayout sweep_smem_layout(int KA, int NH, int
     return L;
 }
 
-template <int NT>
+template <int NT, int CL = 1>
 struct BlockSumV {
     static constexpr int NW = NT / 32;  // power of two (4, 8, 16)
-    double* scratch;                    // [2][SW_VMAX][NW]
+    double* scratch;                    // [2][CL][SW_VMAX][NW]
     int phase;
-    __device__ __forceinline__ BlockSumV(double* s) : scratch(s), phase(0) {}
+    uint32_t crank;
+    __device__ __forceinline__ BlockSumV(double* s, uint32_t rank = 0) : scratch(s), phase(0), crank(rank) {}
+    // CL == 2: the K states of a job are split over the two CTAs of a cluster.  Every warp pushes its partial into the
+    // scratch of BOTH CTAs (own shared memory + distributed shared memory of the peer), one cluster barrier replaces
+    // __syncthreads, and every thread of both CTAs adds the 2 * NW partials in the same fixed order (rank 0 first),
+    // so the two CTAs hold bit-identical totals and take identical decisions.
+    template <int V>
+    __device__ __forceinline__ void run_cluster(double (&v)[V]) {
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+        for (int i = 0; i < V; i++) {
+#pragma unroll
+            for (int d = 16; d >= 1; d >>= 1) v[i] += __shfl_xor_sync(0xffffffffu, v[i], d);
+        }
+        double* buf = scratch + phase * (CL * SW_VMAX * NW);
+        phase ^= 1;
+        if (lane == 0) {
+#pragma unroll
+            for (int i = 0; i < V; i++) {
+                double* slot = buf + (crank * SW_VMAX + i) * NW + warp;
+                *slot = v[i];
+                st_dsmem(slot, crank ^ 1u, v[i]);
+            }
+        }
+        cluster_sync_all();
+#pragma unroll
+        for (int i = 0; i < V; i++) {
+            double p[CL * NW];
+#pragma unroll
+            for (int r = 0; r < CL; r++)
+#pragma unroll
+                for (int w = 0; w < NW; w++) p[r * NW + w] = buf[(r * SW_VMAX + i) * NW + w];
+#pragma unroll
+            for (int st = 1; st < CL * NW; st <<= 1) {
+#pragma unroll
+                for (int w = 0; w + st < CL * NW; w += 2 * st) p[w] += p[w + st];
+            }
+            v[i] = p[0];
+        }
+    }
     // Every thread returns the same, bit-identical totals: xor butterfly inside each warp, one shared-memory slot per
     // warp, then every warp butterflies the NW partials again (same operation order in all warps).  Two alternating
     // scratch buffers make one __syncthreads per call enough.
     template <int V>
     __device__ __forceinline__ void run(double (&v)[V]) {
+        if (CL > 1) {
+            run_cluster(v);
+            return;
+        }
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
         if (V == 2 && NW > 1) {
             // two values: the lower half-warp reduces v[0], the upper half v[1] (half the shuffles of two butterflies)
@@ -416,7 +459,10 @@ __device__ __forceinline__ void upd_loop(double (&am)[NH][EPT], double (&ab)[NH]
     }
 }
 
-template <int NT, int EPT, int NH>
+// CL = 2: the job's K states are split over the two CTAs of a thread-block cluster (K > NT * EPT): CTA `crank` owns
+// k in [crank * KA, crank * KA + KA); block sums meet through distributed shared memory (BlockSumV<NT, 2>), both CTAs
+// take every decision redundantly.
+template <int NT, int EPT, int NH, int CL = 1>
 __global__ void __launch_bounds__(NT, (NT * EPT <= 512 ? 4 : (NT * EPT <= 1024 ? 2 : 1))) k_sweep(BatchParams P, const JobDev* __restrict__ jobs, int iteration, int store_alpha) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ JobDev Js;
@@ -424,14 +470,21 @@ __global__ void __launch_bounds__(NT, (NT * EPT <= 512 ? 4 : (NT * EPT <= 1024 ?
     constexpr int NW = NT / 32;
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) Js = jobs[blockIdx.x];
+    if (tid == 0) Js = jobs[blockIdx.x / CL];
     __syncthreads();
     const JobDev& J = Js;
-    if (*J.underflow) return;
-    const int K = P.K, Kp = P.Kp, T = P.T, R = J.R;
-    const SweepSmemLayout L = sweep_smem_layout(KA, NH, NT);
+    if (*J.underflow) return;  // (both CTAs of a cluster read the same flag)
+    const uint32_t crank = (CL > 1) ? cluster_ctarank() : 0u;
+    const int kbase = (CL > 1) ? (int)crank * KA : 0;                     // first haplotype state of this CTA
+    const int K = (CL > 1) ? max(0, min(P.K - kbase, KA)) : P.K;          // states of this CTA (all bounds checks below are local)
+    const int Kp = P.Kp;                                                  // column stride in HBM
+    const int Kpl = (CL > 1) ? max(0, min(P.Kp - kbase, KA)) : P.Kp;      // padded states of this CTA (bulk-copy length)
+    // (per-job scalars — labels, c, label-probability records, the sweep record — are written by both CTAs: the values
+    //  are bit-identical, and each CTA only ever reads back what it wrote itself)
+    const int T = P.T, R = J.R;
+    const SweepSmemLayout L = sweep_smem_layout(KA, NH, NT, CL);
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L.off_bar);
-    BlockSumV<NT> bsum(reinterpret_cast<double*>(smem + L.off_red));
+    BlockSumV<NT, CL> bsum(reinterpret_cast<double*>(smem + L.off_red), crank);
     int* cnt = reinterpret_cast<int*>(smem + L.off_cnt);
     uint32_t* Wr = reinterpret_cast<uint32_t*>(smem + L.off_W);          // [4][KA] ring of allele words
     uint16_t* spat = reinterpret_cast<uint16_t*>(smem + L.off_pat);      // [KA] allele patterns of gather-mode reads
@@ -444,9 +497,9 @@ __global__ void __launch_bounds__(NT, (NT * EPT <= 512 ? 4 : (NT * EPT <= 1024 ?
     const int32_t* __restrict__ tsG = J.ts;
     const double* __restrict__ tmG = J.tm;
     const double* __restrict__ U = J.runif_reads + (size_t)iteration * R;
-    double* __restrict__ alphaG = J.alpha;
-    double* __restrict__ betaG = J.beta;
-    double* __restrict__ eGg = J.eG;
+    double* __restrict__ alphaG = J.alpha + kbase;
+    double* __restrict__ betaG = J.beta + kbase;
+    double* __restrict__ eGg = J.eG + kbase;
     double* cG = J.c;
 
     if (tid == 0) {
@@ -517,19 +570,19 @@ __global__ void __launch_bounds__(NT, (NT * EPT <= 512 ? 4 : (NT * EPT <= 1024 ?
         }
         if (tid == 0) {
             uint32_t bytes = 0;
-            if (n_g > 0 || g == 0) bytes += NH * Kp * 8;
-            if (g == 0) bytes += Kp * 4;
-            if (g + 1 < T) bytes += Kp * 4;
+            if (n_g > 0 || g == 0) bytes += NH * Kpl * 8;
+            if (g == 0) bytes += Kpl * 4;
+            if (g + 1 < T) bytes += Kpl * 4;
             if (bytes > 0)
                 mbar_arrive_expect_tx(&bar[s], bytes);
             else
                 mbar_arrive(&bar[s]);
             if (n_g > 0 || g == 0) {
 #pragma unroll
-                for (int h = 0; h < NH; h++) bulk_g2s(eGs + (size_t)(s * NH + h) * KA, J.eG + ((size_t)h * T + g) * Kp, Kp * 8, &bar[s]);
+                for (int h = 0; h < NH; h++) bulk_g2s(eGs + (size_t)(s * NH + h) * KA, eGg + ((size_t)h * T + g) * Kp, Kpl * 8, &bar[s]);
             }
-            if (g == 0) bulk_g2s(Wr, J.W, Kp * 4, &bar[s]);
-            if (g + 1 < T) bulk_g2s(Wr + ((g + 1) & 3) * KA, J.W + (size_t)(g + 1) * Kp, Kp * 4, &bar[s]);
+            if (g == 0) bulk_g2s(Wr, J.W + kbase, Kpl * 4, &bar[s]);
+            if (g + 1 < T) bulk_g2s(Wr + ((g + 1) & 3) * KA, J.W + kbase + (size_t)(g + 1) * Kp, Kpl * 4, &bar[s]);
         }
         bool small_done = false;
         if (n_g > 0) {
@@ -611,9 +664,9 @@ __global__ void __launch_bounds__(NT, (NT * EPT <= 512 ? 4 : (NT * EPT <= 1024 ?
             if (P.dbg & 4) cp_async_wait_all();  // experiment: does the next barrier already wait for the cp.async package?
             // pull the next grid's beta columns towards L2 (one 128-byte line per 16 doubles)
             if (nx_r1 > r1 && !(P.dbg & 1)) {
-                const int lines = (NH * Kp) >> 4;
+                const int lines = (NH * Kpl) >> 4;
                 for (int l = (NT > 32 ? tid - 32 : tid); l >= 0 && l < lines; l += (NT > 32 ? NT - 32 : NT)) {
-                    const int h = l / (Kp >> 4), q = l - h * (Kp >> 4);
+                    const int h = l / (Kpl >> 4), q = l - h * (Kpl >> 4);
                     prefetch_l2(betaG + ((size_t)h * T + g + 1) * Kp + (q << 4));
                 }
             }
@@ -721,7 +774,7 @@ __global__ void __launch_bounds__(NT, (NT * EPT <= 512 ? 4 : (NT * EPT <= 1024 ?
                 S.cross = S.b0 + nb > 32;
                 S.tab = tabs + (dq.x - tab0);
                 S.spat = spat;
-                S.dcol = J.dense + (size_t)dq.x * Kp;
+                S.dcol = J.dense + (size_t)dq.x * Kp + kbase;
                 if (mode == MODE_DENSE) return 3;
                 if (mode == MODE_GATHER) return 2;
                 return S.cross ? 1 : 0;
@@ -1041,10 +1094,10 @@ __global__ void __launch_bounds__(NT, (NT * EPT <= 512 ? 4 : (NT * EPT <= 1024 ?
         auto issue_b = [&](int g) {
             const int q = ((T - 2) - g) % NSB;
             if (tid == 0) {
-                mbar_arrive_expect_tx(&bar[q], NH * Kp * 8);
+                mbar_arrive_expect_tx(&bar[q], NH * Kpl * 8);
                 double* dst = bstage(q);
 #pragma unroll
-                for (int h = 0; h < NH; h++) bulk_g2s(dst + (size_t)h * KA, eGg + ((size_t)h * T + g + 1) * Kp, Kp * 8, &bar[q]);
+                for (int h = 0; h < NH; h++) bulk_g2s(dst + (size_t)h * KA, eGg + ((size_t)h * T + g + 1) * Kp, Kpl * 8, &bar[q]);
             }
             unsigned char* sc = smem + L.off_sc + (2 + q) * 64;
             const int ql = tid - 32;
@@ -1142,7 +1195,7 @@ __global__ void __launch_bounds__(NT, (NT * EPT <= 512 ? 4 : (NT * EPT <= 1024 ?
     for (int h = 0; h < NH; h++) {
         sl[h] = 0;
         sc[h] = 0;
-        for (int g = tid; g < T; g += NT) {
+        for (int g = tid + (int)crank * NT; g < T; g += NT * CL) {  // (cluster: the grids are split over the two CTAs, the block sum adds both)
             const double cv = ld_cg(J.c + h * T + g);
             sl[h] += log(cv);
             sc[h] += cv;

@@ -213,6 +213,29 @@ def test_gibbs_nipt_production(gpu, oracle, K, iterative):
     _compare(f"NIPT production K={K} iterative={iterative}", g, o)
 
 
+@pytest.mark.parametrize("K", [4100, 5000, 8192])
+@pytest.mark.parametrize("iterative", [False, True])
+def test_gibbs_production_large_K(gpu, oracle, K, iterative):
+    """Ksubset in (4096, 8192]: the sweep / shard kernels run as two-CTA clusters (4096 states per CTA, block sums
+    exchanged through distributed shared memory)"""
+    w = synth.make_world(300 + K, K_full=K + 60, nSNPs=1600, region_bp=150_000)
+    sr = synth.make_sample_reads(w, K, coverage=1.0, region_bp=150_000)
+    call = synth.make_call(w, sr.common, 51, K=K, first_iteration=iterative)
+    g, o = _run_both(gpu, oracle, call)
+    _compare(f"large K={K} iterative={iterative}", g, o)
+
+
+def test_forward_backward_large_K(gpu, oracle):
+    rng = np.random.default_rng(8)
+    K, T = 6000, 9
+    e = np.asfortranarray(rng.random((K, T)) * 0.9 + 0.05)
+    sigma = rng.random(T - 1) * 0.5 + 0.5
+    tm = np.asfortranarray(np.stack([sigma, 1 - sigma]))
+    ag, bg, cg = gpu.forward_backward(e, tm)
+    ao, bo, co = oracle.forward_backward(e, tm)
+    assert _rel(cg, co) < 1e-12 and _rel(ag, ao) < 1e-11 and _rel(bg, bo) < 1e-11
+
+
 def test_gibbs_unsorted_haps_and_sampling_its(gpu, oracle, small_world, small_reads):
     """which_haps_to_use unsorted (after mspbwt selection, Appendix D.10), 3 sampling sweeps averaged"""
     call = synth.make_call(small_world, small_reads.common, 25, K=300, sort_haps=False, first_iteration=False, n_burn_in=5, n_sample=3, block_its=(2,))

@@ -15,6 +15,10 @@ for c in cfgs:
     for kv in c.split(","):
         if kv == "ALL":
             extra.append("--all-snps")
+        elif kv.startswith("K="):
+            extra += ["--K", kv[2:]]
+        elif kv.startswith("JOBS="):
+            extra += ["--jobs", kv[5:]]
         elif "=" in kv:
             k, v = kv.split("=", 1)
             env["QUILT_B200_" + k] = v
