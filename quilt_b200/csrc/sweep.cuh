@@ -506,12 +506,16 @@ __global__ void __launch_bounds__(NT, (NT * EPT <= 512 ? 4 : (NT * EPT <= 1024 ?
         mbar_init(&bar[0], 1);
         mbar_init(&bar[1], 1);
         mbar_init(&bar[2], 1);
+        mbar_init(&bar[3], 1);  // eMatGrid columns into ring buffer 0 / 1 (forward)
+        mbar_init(&bar[4], 1);
+        mbar_init(&bar[5], 1);  // beta columns (forward)
         fence_barrier_init();
     }
     if (tid < 16) cnt[tid] = 0;
     __syncthreads();
     const int n_tab_total = tsG[T];
     uint32_t n_use0 = 0, n_use1 = 0, n_use2 = 0;  // completed uses of each stage barrier -> wait parity
+    uint32_t n_useE0 = 0, n_useE1 = 0, n_useB = 0;
 
     // staging of reads [ra, ra + n) with table entries [ta, ta + nt) into stage buffer s
     auto stage_small = [&](int s, int ra, int n, int ta, int nt, bool async) {
@@ -570,17 +574,12 @@ __global__ void __launch_bounds__(NT, (NT * EPT <= 512 ? 4 : (NT * EPT <= 1024 ?
         }
         if (tid == 0) {
             uint32_t bytes = 0;
-            if (n_g > 0 || g == 0) bytes += NH * Kpl * 8;
             if (g == 0) bytes += Kpl * 4;
             if (g + 1 < T) bytes += Kpl * 4;
             if (bytes > 0)
                 mbar_arrive_expect_tx(&bar[s], bytes);
             else
                 mbar_arrive(&bar[s]);
-            if (n_g > 0 || g == 0) {
-#pragma unroll
-                for (int h = 0; h < NH; h++) bulk_g2s(eGs + (size_t)(s * NH + h) * KA, eGg + ((size_t)h * T + g) * Kp, Kpl * 8, &bar[s]);
-            }
             if (g == 0) bulk_g2s(Wr, J.W + kbase, Kpl * 4, &bar[s]);
             if (g + 1 < T) bulk_g2s(Wr + ((g + 1) & 3) * KA, J.W + kbase + (size_t)(g + 1) * Kp, Kpl * 4, &bar[s]);
         }
@@ -625,6 +624,37 @@ __global__ void __launch_bounds__(NT, (NT * EPT <= 512 ? 4 : (NT * EPT <= 1024 ?
         }
         __syncthreads();
     };
+    // The two big ring buffers alternate between three tenants (all by bulk copy, i.e. off the LSU and not ordered by
+    // the block barriers): buffer g & 1 holds eMatGrid[:, g] for the whole of grid g; the other buffer holds
+    // beta[:, g] from the top of grid g until alpha * beta has been formed, and then receives eMatGrid[:, g + 1].
+    auto issue_eG = [&](int g) {  // caller: every thread is done with buffer g & 1
+        if (tid == 0) {
+            const int s = g & 1;
+            fence_proxy_async();
+            mbar_arrive_expect_tx(&bar[3 + s], NH * Kpl * 8);
+#pragma unroll
+            for (int h = 0; h < NH; h++) bulk_g2s(eGs + (size_t)(s * NH + h) * KA, eGg + ((size_t)h * T + g) * Kp, Kpl * 8, &bar[3 + s]);
+        }
+    };
+    auto wait_eG = [&](int g) {
+        if (g & 1) {
+            mbar_wait(&bar[4], n_useE1 & 1);
+            n_useE1++;
+        } else {
+            mbar_wait(&bar[3], n_useE0 & 1);
+            n_useE0++;
+        }
+    };
+    auto issue_beta = [&](int g) {  // into the buffer eMatGrid[:, g - 1] has left
+        if (tid == 0) {
+            const int s = (g & 1) ^ 1;
+            fence_proxy_async();
+            mbar_arrive_expect_tx(&bar[5], NH * Kpl * 8);
+#pragma unroll
+            for (int h = 0; h < NH; h++) bulk_g2s(eGs + (size_t)(s * NH + h) * KA, betaG + ((size_t)h * T + g) * Kp, Kpl * 8, &bar[5]);
+        }
+    };
+
 
     double am[NH][EPT];  // alpha of the previous grid (normalised) on entry to a grid, alphaHat_m / alpha of this grid afterwards
     double cfin[NH];     // c of the last grid processed
@@ -635,6 +665,7 @@ __global__ void __launch_bounds__(NT, (NT * EPT <= 512 ? 4 : (NT * EPT <= 1024 ?
     // waits for a dependent global load
     int cur_r0 = rs[0], cur_t0 = tsG[0];
     issue_pkg(0, cur_r0, rs[1], cur_t0, tsG[1]);
+    issue_eG(0);
     // =============================================================== forward + read resampling
     for (int g = 0; g < T; g++) {
         wait_pkg(g);
@@ -654,10 +685,16 @@ __global__ void __launch_bounds__(NT, (NT * EPT <= 512 ? 4 : (NT * EPT <= 1024 ?
         cur_r0 = r1;
         cur_t0 = ts1;
         double ab[NH][EPT];
-        // beta of this grid goes straight into the ab registers (consumed after the forward step)
+        const bool next_has = (g + 1 < T) && (nx_r1 > r1);
+        if (has || g == 0) wait_eG(g);
+        // beta of this grid arrives by bulk copy in the other ring buffer (consumed after the forward step)
+        bool beta_pending = false, eG_next_issued = !next_has;
         if (has) {
-#pragma unroll
-            for (int h = 0; h < NH; h++) Col<NT, EPT>::load(ab[h], betaG + ((size_t)h * T + g) * Kp, K, 0.0);
+            issue_beta(g);
+            beta_pending = true;
+        } else if (next_has) {
+            issue_eG(g + 1);
+            eG_next_issued = true;
         }
         if (g + 1 < T) {
             if (!(P.dbg & 2)) issue_pkg(g + 1, r1, nx_r1, ts1, nx_t1);
@@ -750,16 +787,28 @@ __global__ void __launch_bounds__(NT, (NT * EPT <= 512 ? 4 : (NT * EPT <= 1024 ?
                 // alphaHat_m = alpha, betaHat_m = beta, ab_m = alpha * beta ; pC = colsums (gibbs-nipt.cpp:836-858)
                 double sv[NH];
 #pragma unroll
+                mbar_wait(&bar[5], n_useB & 1);
+                n_useB++;
+                beta_pending = false;
+                const double* bs = eGs + (size_t)((s ^ 1) * NH) * KA;
+#pragma unroll
                 for (int h = 0; h < NH; h++) {
 #pragma unroll
-                    for (int i = 0; i < EPT; i++) ab[h][i] = am[h][i] * ab[h][i];
+                    for (int i = 0; i < EPT; i++) {
+                        const int k = tid + i * NT;
+                        ab[h][i] = (k < K) ? am[h][i] * bs[h * KA + k] : 0.0;
+                    }
                     sv[h] = Col<NT, EPT>::sum(ab[h]);
                 }
-                bsum.run(sv);
+                bsum.run(sv);  // (every thread is past its reads of the beta buffer)
                 pC.a = sv[0];
                 pC.b = sv[1];
                 if (NH == 3) pC.c = sv[NH - 1];
                 inited = true;
+                if (!eG_next_issued) {
+                    issue_eG(g + 1);
+                    eG_next_issued = true;
+                }
             };
             // ESrc of chunk-local read ir; returns the source kind (0..3)
             auto make_src = [&](int ir, uint32_t tab0, ESrc& S) -> int {
@@ -1040,6 +1089,16 @@ __global__ void __launch_bounds__(NT, (NT * EPT <= 512 ? 4 : (NT * EPT <= 1024 ?
 #undef QB_UPD
 #undef QB_UPD_LABELS
 #undef QB_UPD_LOOP
+            if (beta_pending) {
+                // no read of this grid was visited: consume the beta copy so that its buffer can move on
+                mbar_wait(&bar[5], n_useB & 1);
+                n_useB++;
+                beta_pending = false;
+            }
+            if (!eG_next_issued) {
+                issue_eG(g + 1);
+                eG_next_issued = true;
+            }
             if (changed) {
                 // gibbs-nipt.cpp:1262-1292: renormalise every haplotype's column and fold into c
                 double sv[NH];
