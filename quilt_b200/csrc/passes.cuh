@@ -223,24 +223,31 @@ __device__ __forceinline__ void prefetch_cols(const double* p, size_t stride, in
     }
 }
 
-// shard pass (diploid).  grid = jobs.  One CTA re-runs the forward recursion of both haplotypes with the
-// generic step and, after every grid, decides between "stay" and "swap labels from here on"; then the generic
-// backward of both haplotypes in one walk.  Columns are pulled into L2 two grids ahead and the per-grid scalars
-// travel one grid ahead in registers, so a step costs its reductions, not a DRAM round trip.
-// CL = 2: two-CTA cluster, each CTA owns half of the K states (see k_sweep).
+// shard pass (diploid).  grid = jobs (x CL).  One CTA (or two-CTA cluster, CL = 2: each CTA owns half of the K states,
+// see k_sweep) re-runs the forward recursion of both haplotypes with the generic step and, after every grid, decides
+// between "stay" and "swap labels from here on"; then the generic backward of both haplotypes in one walk.
+//
+// Columns arrive by bulk copy (TMA engine, mbarrier completion) in a ring of three column PAIRS in shared memory with
+// rotating tenants: eMatGrid[:, g] sits in pair 2g mod 3, beta[:, g] in pair (2g + 1) mod 3.  When the forward step has
+// consumed eMatGrid[:, g] its pair receives beta[:, g + 1]; when the scores have consumed beta[:, g] its pair receives
+// eMatGrid[:, g + 2] — every column is in flight for at least a full step, nothing waits in registers.
+// dynamic shared memory = 3 * 2 * KA * 8 bytes.
 template <int NT, int EPT, int CL = 1>
 __global__ void __launch_bounds__(NT) k_shard(BatchParams P, const JobDev* __restrict__ jobs, int episode) {
+    extern __shared__ __align__(128) unsigned char shsm[];
     __shared__ double red[2 * CL * SW_VMAX * (NT / 32)];
     __shared__ JobDev Js;
+    __shared__ __align__(8) uint64_t bar[3];
+    constexpr int KA = NT * EPT;
     const int tid = threadIdx.x;
     if (tid == 0) Js = jobs[blockIdx.x / CL];
     __syncthreads();
     if (*Js.underflow) return;
     const uint32_t crank = (CL > 1) ? cluster_ctarank() : 0u;
-    const int kbase = (int)crank * (NT * EPT);
-    const int K = max(0, min(P.K - kbase, NT * EPT));  // states of this CTA
+    const int kbase = (CL > 1) ? (int)crank * KA : 0;
+    const int K = (CL > 1) ? max(0, min(P.K - kbase, KA)) : P.K;       // states of this CTA
     const int Kp = P.Kp, T = P.T, R = Js.R;
-    const int Kpl = max(0, min(P.Kp - kbase, NT * EPT));  // padded states of this CTA
+    const int Kpl = (CL > 1) ? max(0, min(P.Kp - kbase, KA)) : P.Kp;   // padded states of this CTA (bulk-copy length)
     double* __restrict__ alphaG = Js.alpha + kbase;
     double* __restrict__ betaG = Js.beta + kbase;
     double* __restrict__ eGg = Js.eG + kbase;
@@ -251,6 +258,41 @@ __global__ void __launch_bounds__(NT) k_shard(BatchParams P, const JobDev* __res
     const double prior = P.one_over_K;
     const double* __restrict__ runif = Js.runif_shard + (size_t)episode * (T - 1);
     const size_t hs = (size_t)T * Kp;  // haplotype stride
+    double* ring = reinterpret_cast<double*>(shsm);  // [3 pairs][2 haplotypes][KA]
+    if (tid == 0) {
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
+        mbar_init(&bar[2], 1);
+        fence_barrier_init();
+    }
+    __syncthreads();
+    uint32_t use0 = 0, use1 = 0, use2 = 0;
+    // both haplotypes' column g of `src` into ring pair q (caller: every thread is done with that pair)
+    auto issue = [&](int q, const double* src, int g) {
+        if (tid == 0) {
+            fence_proxy_async();
+            mbar_arrive_expect_tx(&bar[q], 2 * Kpl * 8);
+            bulk_g2s(ring + (size_t)(q * 2) * KA, src + (size_t)g * Kp, Kpl * 8, &bar[q]);
+            bulk_g2s(ring + (size_t)(q * 2 + 1) * KA, src + hs + (size_t)g * Kp, Kpl * 8, &bar[q]);
+        }
+    };
+    auto wait = [&](int q) {
+        if (q == 0) {
+            mbar_wait(&bar[0], use0 & 1);
+            use0++;
+        } else if (q == 1) {
+            mbar_wait(&bar[1], use1 & 1);
+            use1++;
+        } else {
+            mbar_wait(&bar[2], use2 & 1);
+            use2++;
+        }
+    };
+    issue(0, eGg, 0);                 // eMatGrid[:, 0] -> pair 0
+    if (T > 1) {
+        issue(1, betaG, 0);           // beta[:, 0]     -> pair 1
+        issue(2, eGg, 1);             // eMatGrid[:, 1] -> pair 2
+    }
     double mloc[2];
     {
         double sl[2] = {0, 0};
@@ -264,16 +306,11 @@ __global__ void __launch_bounds__(NT) k_shard(BatchParams P, const JobDev* __res
     }
     double mlc[2] = {0, 0};
     bool in_flip = false;
-    double ap[2][EPT], e[2][EPT], en[2][EPT];
-#pragma unroll
-    for (int h = 0; h < 2; h++) Col<NT, EPT>::load(e[h], eGg + h * hs, K, 0.0);
-    if (T > 1) {
-        prefetch_cols<NT>(eGg + Kp, hs, 2, Kpl);
-        prefetch_cols<NT>(betaG + Kp, hs, 2, Kpl);
-    }
+    double ap[2][EPT];
     double clast[2] = {1, 1};
     double nx_c[2] = {ld_cg(cG), ld_cg(cG + T)};
     double nx_x = 0, nx_t1 = 0, nx_u = (T > 1) ? runif[0] : 0.0;
+    int qe = 0, qb = 1;  // ring pairs of eMatGrid[:, g] and beta[:, g]
     for (int g = 0; g < T; g++) {
         const double orig_c[2] = {nx_c[0], nx_c[1]};
         const double x = nx_x, t1 = nx_t1, u = nx_u;
@@ -283,27 +320,21 @@ __global__ void __launch_bounds__(NT) k_shard(BatchParams P, const JobDev* __res
             nx_x = tmG[2 * g];
             nx_t1 = tmG[2 * g + 1];
             if (g + 1 < T - 1) nx_u = runif[g + 1];
-#pragma unroll
-            for (int h = 0; h < 2; h++) Col<NT, EPT>::load(en[h], eGg + h * hs + (size_t)(g + 1) * Kp, K, 0.0);
         }
-        double y[2][EPT];
-        if (g < T - 1) {
-#pragma unroll
-            for (int h = 0; h < 2; h++) Col<NT, EPT>::load(y[h], betaG + h * hs + (size_t)g * Kp, K, 0.0);
-        }
-        if (g + 2 < T) {
-            prefetch_cols<NT>(eGg + (size_t)(g + 2) * Kp, hs, 2, Kpl);
-            prefetch_cols<NT>(betaG + (size_t)(g + 2) * Kp, hs, 2, Kpl);
-        }
+        wait(qe);
+        const double* e0 = ring + (size_t)(qe * 2 + (in_flip && g > 0 ? 1 : 0)) * KA;  // flip mode: the columns trade places
+        const double* e1 = ring + (size_t)(qe * 2 + (in_flip && g > 0 ? 0 : 1)) * KA;
         double cn[2];
         if (g == 0) {
             double sv[2];
 #pragma unroll
-            for (int h = 0; h < 2; h++) {
-#pragma unroll
-                for (int i = 0; i < EPT; i++) ap[h][i] = prior * e[h][i];
-                sv[h] = Col<NT, EPT>::sum(ap[h]);
+            for (int i = 0; i < EPT; i++) {
+                const int k = tid + i * NT;
+                ap[0][i] = (k < K) ? prior * e0[k] : 0.0;
+                ap[1][i] = (k < K) ? prior * e1[k] : 0.0;
             }
+            sv[0] = Col<NT, EPT>::sum(ap[0]);
+            sv[1] = Col<NT, EPT>::sum(ap[1]);
             bsum.run(sv);
 #pragma unroll
             for (int h = 0; h < 2; h++) {
@@ -314,14 +345,15 @@ __global__ void __launch_bounds__(NT) k_shard(BatchParams P, const JobDev* __res
         } else {
             if (in_flip) {
                 // eMatGrid_t1.col(g) <-> eMatGrid_t2.col(g), in place
+                double t0v[EPT], t1v[EPT];
 #pragma unroll
                 for (int i = 0; i < EPT; i++) {
-                    const double t = e[0][i];
-                    e[0][i] = e[1][i];
-                    e[1][i] = t;
+                    const int k = tid + i * NT;
+                    t0v[i] = (k < K) ? e0[k] : 0.0;
+                    t1v[i] = (k < K) ? e1[k] : 0.0;
                 }
-#pragma unroll
-                for (int h = 0; h < 2; h++) Col<NT, EPT>::store(e[h], eGg + h * hs + (size_t)g * Kp, K);
+                Col<NT, EPT>::store(t0v, eGg + (size_t)g * Kp, K);
+                Col<NT, EPT>::store(t1v, eGg + hs + (size_t)g * Kp, K);
             }
             double sp[2];
 #pragma unroll
@@ -333,11 +365,15 @@ __global__ void __launch_bounds__(NT) k_shard(BatchParams P, const JobDev* __res
                 const double alphaConst = t1 * sp[h];
                 const double jump = alphaConst * prior;
                 const double c2 = orig_c[h];
+                const double* eh = h == 0 ? e0 : e1;
 #pragma unroll
-                for (int i = 0; i < EPT; i++) ap[h][i] = (tid + i * NT < K) ? (c2 * e[h][i]) * (x * ap[h][i] + jump) : 0.0;
+                for (int i = 0; i < EPT; i++) {
+                    const int k = tid + i * NT;
+                    ap[h][i] = (k < K) ? (c2 * eh[k]) * (x * ap[h][i] + jump) : 0.0;
+                }
                 sv[h] = Col<NT, EPT>::sum(ap[h]);
             }
-            bsum.run(sv);
+            bsum.run(sv);  // (every thread is past its reads of eMatGrid[:, g])
 #pragma unroll
             for (int h = 0; h < 2; h++) {
                 const double sc = 1 / sv[h];
@@ -346,6 +382,8 @@ __global__ void __launch_bounds__(NT) k_shard(BatchParams P, const JobDev* __res
                 for (int i = 0; i < EPT; i++) ap[h][i] *= sc;
             }
         }
+        // eMatGrid[:, g] is consumed (the block sums above are behind every thread's reads): its pair takes beta[:, g + 1]
+        if (g + 1 < T - 1) issue(qe, betaG, g + 1);
 #pragma unroll
         for (int h = 0; h < 2; h++) {
             Col<NT, EPT>::store(ap[h], alphaG + h * hs + (size_t)g * Kp, K);
@@ -355,15 +393,21 @@ __global__ void __launch_bounds__(NT) k_shard(BatchParams P, const JobDev* __res
         }
         if (tid == 0) rateG[g] = in_flip ? 1.0 : 0.0;  // reads of this grid are relabelled 3 - H when set
         if (g < T - 1) {
+            wait(qb);
+            const double* y0 = ring + (size_t)(qb * 2) * KA;
+            const double* y1 = y0 + KA;
             double dv[4] = {0, 0, 0, 0};
 #pragma unroll
             for (int i = 0; i < EPT; i++) {
-                dv[0] += ap[0][i] * y[0][i];
-                dv[1] += ap[1][i] * y[1][i];
-                dv[2] += ap[1][i] * y[0][i];
-                dv[3] += ap[0][i] * y[1][i];
+                const int k = tid + i * NT;
+                const double b0 = (k < K) ? y0[k] : 0.0, b1 = (k < K) ? y1[k] : 0.0;
+                dv[0] += ap[0][i] * b0;
+                dv[1] += ap[1][i] * b1;
+                dv[2] += ap[1][i] * b0;
+                dv[3] += ap[0][i] * b1;
             }
-            bsum.run(dv);
+            bsum.run(dv);  // (every thread is past its reads of beta[:, g])
+            if (g + 2 < T) issue(qb, eGg, g + 2);
             const double pA1 = mlc[0] + mloc[0] + log(dv[0]);
             const double pA2 = mlc[1] + mloc[1] + log(dv[1]);
             const double pB1 = mlc[1] + mloc[0] + log(dv[2]);
@@ -376,11 +420,11 @@ __global__ void __launch_bounds__(NT) k_shard(BatchParams P, const JobDev* __res
             in_flip = u > probs1;
         }
 #pragma unroll
-        for (int h = 0; h < 2; h++) {
-            mloc[h] += log(orig_c[h]);
-#pragma unroll
-            for (int i = 0; i < EPT; i++) e[h][i] = en[h][i];
-        }
+        for (int h = 0; h < 2; h++) mloc[h] += log(orig_c[h]);
+        // tenants of the next grid: eMatGrid[:, g + 1] sits in the pair that was neither e nor beta of this grid
+        const int qn = 3 - qe - qb;
+        qb = qe;
+        qe = qn;
     }
     __syncthreads();
     // relabel the reads of every grid walked in flip mode (once per job: the first CTA of a cluster)
@@ -389,18 +433,22 @@ __global__ void __launch_bounds__(NT) k_shard(BatchParams P, const JobDev* __res
             if (rateG[Js.wif0[r]] != 0.0) Js.H[r] = 3 - Js.H[r];
         }
     }
-    // generic backward on the (possibly swapped) eMatGrid columns, both haplotypes in one walk
-    // (every thread re-reads only eMatGrid elements it wrote itself above, so no fence is needed)
+    // generic backward on the (possibly swapped) eMatGrid columns, both haplotypes in one walk.  The swapped columns
+    // were written through the generic proxy by this CTA: order them before the bulk (async proxy) reads below.
+    __threadfence();
+    fence_proxy_async_all();
+    __syncthreads();
     {
-        double b[2][EPT], ee[2][EPT], een[2][EPT];
+        double b[2][EPT];
 #pragma unroll
         for (int h = 0; h < 2; h++) {
 #pragma unroll
             for (int i = 0; i < EPT; i++) b[h][i] = (tid + i * NT < K) ? clast[h] : 0.0;
             Col<NT, EPT>::store(b[h], betaG + h * hs + (size_t)(T - 1) * Kp, K);
-            if (T >= 2) Col<NT, EPT>::load(ee[h], eGg + h * hs + (size_t)(T - 1) * Kp, K, 0.0);
         }
-        if (T >= 3) prefetch_cols<NT>(eGg + (size_t)(T - 2) * Kp, hs, 2, Kpl);
+        // step g needs eMatGrid[:, g + 1]; step index j = T - 2 - g uses pair j mod 3, packages run two steps ahead
+        if (T >= 2) issue(0, eGg, T - 1);
+        if (T >= 3) issue(1, eGg, T - 2);
         double nb_c[2] = {0, 0}, nb_t0 = 0, nb_t1 = 0;
         if (T >= 2) {
             nb_c[0] = ld_cg(cG + T - 2);
@@ -408,26 +456,31 @@ __global__ void __launch_bounds__(NT) k_shard(BatchParams P, const JobDev* __res
             nb_t0 = tmG[2 * (T - 2)];
             nb_t1 = tmG[2 * (T - 2) + 1];
         }
+        int q = 0;
         for (int g = T - 2; g >= 0; g--) {
             const double cg[2] = {nb_c[0], nb_c[1]};
             const double t0 = nb_t0, t1 = nb_t1;
             if (g >= 1) {
-#pragma unroll
-                for (int h = 0; h < 2; h++) Col<NT, EPT>::load(een[h], eGg + h * hs + (size_t)g * Kp, K, 0.0);
                 nb_c[0] = ld_cg(cG + g - 1);
                 nb_c[1] = ld_cg(cG + T + g - 1);
                 nb_t0 = tmG[2 * (g - 1)];
                 nb_t1 = tmG[2 * (g - 1) + 1];
             }
-            if (g >= 2) prefetch_cols<NT>(eGg + (size_t)(g - 1) * Kp, hs, 2, Kpl);
+            // the pair step g + 1 used is free (every thread passed that step's block sum): fill it for step g - 2
+            if (g - 2 >= 0) issue((q + 2) % 3, eGg, g - 1);
+            wait(q);
+            const double* ee0 = ring + (size_t)(q * 2) * KA;
+            const double* ee1 = ee0 + KA;
             double sv[2] = {0, 0};
 #pragma unroll
-            for (int h = 0; h < 2; h++) {
-#pragma unroll
-                for (int i = 0; i < EPT; i++) {
-                    b[h][i] = ee[h][i] * b[h][i];
-                    sv[h] += prior * b[h][i];
+            for (int i = 0; i < EPT; i++) {
+                const int k = tid + i * NT;
+                if (k < K) {
+                    b[0][i] = ee0[k] * b[0][i];
+                    b[1][i] = ee1[k] * b[1][i];
                 }
+                sv[0] += prior * b[0][i];
+                sv[1] += prior * b[1][i];
             }
             bsum.run(sv);
 #pragma unroll
@@ -436,9 +489,8 @@ __global__ void __launch_bounds__(NT) k_shard(BatchParams P, const JobDev* __res
 #pragma unroll
                 for (int i = 0; i < EPT; i++) b[h][i] = (tid + i * NT < K) ? cg[h] * (x + t0 * b[h][i]) : 0.0;
                 Col<NT, EPT>::store(b[h], betaG + h * hs + (size_t)g * Kp, K);
-#pragma unroll
-                for (int i = 0; i < EPT; i++) ee[h][i] = een[h][i];
             }
+            q = (q + 1) % 3;
         }
     }
 }

@@ -940,10 +940,15 @@ int run_wave_t(QuiltGpuBatch* B, Bucket& bk, int n, const JobDev* dj, bool timed
                 }
             }
             if (bk.do_shard && P.T > 1) {
+                const size_t ssm = (size_t)3 * 2 * NT * EPT * 8;  // ring of three column pairs
                 if (CL == 2) {
-                    if constexpr (NT == 256 && EPT == 16) CK(launch_cl(k_shard<NT, EPT, 2>, 2 * n, NT, (size_t)0, 2, P, dj, episode));
+                    if constexpr (NT == 256 && EPT == 16) {
+                        CK(cudaFuncSetAttribute(k_shard<NT, EPT, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssm));
+                        CK(launch_cl(k_shard<NT, EPT, 2>, 2 * n, NT, ssm, 2, P, dj, episode));
+                    }
                 } else {
-                    k_shard<NT, EPT><<<n, NT, 0, g_stream>>>(P, dj, episode);
+                    CK(cudaFuncSetAttribute(k_shard<NT, EPT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssm));
+                    k_shard<NT, EPT, 1><<<n, NT, ssm, g_stream>>>(P, dj, episode);
                 }
                 LAUNCHED();
             }
