@@ -9,13 +9,13 @@
 //
 // Layout: the K states of a column are spread over the CTA (k = tid + i * NT, EPT elements per thread, in
 // registers); alpha of the previous grid and the working copies alphaHat_m / ab_m of the current grid live in
-// registers for the whole grid.  eMatGrid columns (a 2-deep ring) and the 32-SNP allele words of grids g-1 .. g+2
-// are staged in shared memory by 1-D bulk async copies (TMA engine, mbarrier completion); the small per-grid read
-// metadata (descriptors, emission tables, labels, uniforms) by cp.async.  beta columns are streamed with
-// L1-bypassing loads, alpha / beta / changed eMatGrid columns leave with streaming stores.  Per-read K-long sums
+// registers for the whole grid.  eMatGrid and beta columns (two ring buffers with three rotating tenants) and the
+// 32-SNP allele words of grids g-1 .. g+2 are staged in shared memory by 1-D bulk async copies (TMA engine,
+// mbarrier completion); the small per-grid read metadata (descriptors, emission tables, labels, uniforms, per-grid
+// scalars) by cp.async.  alpha / beta / changed eMatGrid columns leave with streaming stores.  Per-read K-long sums
 // use a shuffle butterfly + one shared-memory exchange; every thread ends with bit-identical totals and takes the
 // label decision redundantly.  Shared-memory columns have stride KA = NT * EPT >= K so the per-read loops need no
-// bounds checks (padding elements carry alpha = ab = 0).
+// bounds checks (padding elements carry alpha = ab = 0).  For K > 4096 a job runs on a two-CTA cluster (CL = 2).
 #pragma once
 
 #include "device_common.cuh"
@@ -467,9 +467,7 @@ __global__ void __launch_bounds__(NT, (NT * EPT <= 512 ? 4 : (NT * EPT <= 1024 ?
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ JobDev Js;
     constexpr int KA = NT * EPT;
-    constexpr int NW = NT / 32;
     const int tid = threadIdx.x;
-    const int lane = tid & 31, warp = tid >> 5;
     if (tid == 0) Js = jobs[blockIdx.x / CL];
     __syncthreads();
     const JobDev& J = Js;
@@ -786,7 +784,6 @@ __global__ void __launch_bounds__(NT, (NT * EPT <= 512 ? 4 : (NT * EPT <= 1024 ?
             auto init_ab = [&]() {
                 // alphaHat_m = alpha, betaHat_m = beta, ab_m = alpha * beta ; pC = colsums (gibbs-nipt.cpp:836-858)
                 double sv[NH];
-#pragma unroll
                 mbar_wait(&bar[5], n_useB & 1);
                 n_useB++;
                 beta_pending = false;
