@@ -199,7 +199,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="chr20_2Mb_1x_K4096", choices=sorted(WORKLOADS))
     ap.add_argument("--samples", type=int, default=0, help="samples per GPU per step (default: workload's)")
-    ap.add_argument("--e2e-steps", type=int, default=1)
+    ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3:
