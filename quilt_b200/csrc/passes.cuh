@@ -162,28 +162,18 @@ __global__ void __launch_bounds__(NT) k_fb_generic(BatchParams P, const JobDev* 
     double* alpha = J.alpha + (size_t)h * T * Kp;
     double* beta = J.beta + (size_t)h * T * Kp;
     double* c = J.c + h * T;
-    // The walk is unrolled by two with ping-pong register sets (column and per-step scalars of step g + 1 are loaded
-    // into the set step g does not use): a rotating copy "e = en" at the end of a step would make every load wait
-    // inside the step that issued it.
-    double a[EPT], eA[EPT], eB[EPT];
-    struct Sc {
-        double t0, t1, cg;
-    } sA = {0, 0, 0}, sB = {0, 0, 0};
-    Col<NT, EPT>::load(eA, eG, K, 0.0);
+    double a[EPT], e[EPT], en[EPT];
+    Col<NT, EPT>::load(e, eG, K, 0.0);
     double clast = 1;
-    auto fstep = [&](int g, double (&ec)[EPT], double (&en)[EPT], const Sc& sc, Sc& sn) {
-        if (g + 1 < T) {
-            Col<NT, EPT>::load(en, eG + (size_t)(g + 1) * Kp, K, 0.0);
-            sn.t0 = J.tm[2 * g];
-            sn.t1 = J.tm[2 * g + 1];
-        }
+    for (int g = 0; g < T; g++) {
+        if (g + 1 < T) Col<NT, EPT>::load(en, eG + (size_t)(g + 1) * Kp, K, 0.0);
         if (g == 0) {
 #pragma unroll
-            for (int i = 0; i < EPT; i++) a[i] = prior * ec[i];
+            for (int i = 0; i < EPT; i++) a[i] = prior * e[i];
         } else {
-            const double t0 = sc.t0, t1 = sc.t1;
+            const double t0 = J.tm[2 * (g - 1)], t1 = J.tm[2 * (g - 1) + 1];
 #pragma unroll
-            for (int i = 0; i < EPT; i++) a[i] = (tid + i * NT < K) ? ec[i] * (t0 * a[i] + t1 * prior) : 0.0;
+            for (int i = 0; i < EPT; i++) a[i] = (tid + i * NT < K) ? e[i] * (t0 * a[i] + t1 * prior) : 0.0;
         }
         double sv[1] = {Col<NT, EPT>::sum(a)};
         bsum.run(sv);
@@ -193,10 +183,8 @@ __global__ void __launch_bounds__(NT) k_fb_generic(BatchParams P, const JobDev* 
         Col<NT, EPT>::store(a, alpha + (size_t)g * Kp, K);
         if (tid == 0) c[g] = cg;
         clast = cg;
-    };
-    for (int g = 0; g < T; g += 2) {
-        fstep(g, eA, eB, sA, sB);
-        if (g + 1 < T) fstep(g + 1, eB, eA, sB, sA);
+#pragma unroll
+        for (int i = 0; i < EPT; i++) e[i] = en[i];
     }
     if (!do_backward) return;
     __syncthreads();
@@ -204,24 +192,15 @@ __global__ void __launch_bounds__(NT) k_fb_generic(BatchParams P, const JobDev* 
 #pragma unroll
     for (int i = 0; i < EPT; i++) b[i] = (tid + i * NT < K) ? clast : 0.0;
     Col<NT, EPT>::store(b, beta + (size_t)(T - 1) * Kp, K);
-    if (T >= 2) {
-        Col<NT, EPT>::load(eA, eG + (size_t)(T - 1) * Kp, K, 0.0);
-        sA.cg = ld_cg(c + T - 2);
-        sA.t0 = J.tm[2 * (T - 2)];
-        sA.t1 = J.tm[2 * (T - 2) + 1];
-    }
-    auto bstep = [&](int g, double (&ec)[EPT], double (&en)[EPT], const Sc& sc, Sc& sn) {
-        if (g >= 1) {
-            Col<NT, EPT>::load(en, eG + (size_t)g * Kp, K, 0.0);
-            sn.cg = ld_cg(c + g - 1);
-            sn.t0 = J.tm[2 * (g - 1)];
-            sn.t1 = J.tm[2 * (g - 1) + 1];
-        }
-        const double cg = sc.cg, t0 = sc.t0, t1 = sc.t1;
+    if (T >= 2) Col<NT, EPT>::load(e, eG + (size_t)(T - 1) * Kp, K, 0.0);
+    for (int g = T - 2; g >= 0; g--) {
+        if (g >= 1) Col<NT, EPT>::load(en, eG + (size_t)g * Kp, K, 0.0);
+        const double cg = ld_cg(c + g);
+        const double t0 = J.tm[2 * g], t1 = J.tm[2 * g + 1];
         double sv[1] = {0};
 #pragma unroll
         for (int i = 0; i < EPT; i++) {
-            b[i] = ec[i] * b[i];
+            b[i] = e[i] * b[i];
             sv[0] += prior * b[i];
         }
         bsum.run(sv);
@@ -229,10 +208,8 @@ __global__ void __launch_bounds__(NT) k_fb_generic(BatchParams P, const JobDev* 
 #pragma unroll
         for (int i = 0; i < EPT; i++) b[i] = (tid + i * NT < K) ? cg * (x + t0 * b[i]) : 0.0;
         Col<NT, EPT>::store(b, beta + (size_t)g * Kp, K);
-    };
-    for (int g = T - 2; g >= 0; g -= 2) {
-        bstep(g, eA, eB, sA, sB);
-        if (g - 1 >= 0) bstep(g - 1, eB, eA, sB, sA);
+#pragma unroll
+        for (int i = 0; i < EPT; i++) e[i] = en[i];
     }
 }
 
