@@ -29,6 +29,12 @@
  *
  * The functions never generate randomness: every uniform the reference draws
  * from R's RNG inside the .Call is an input ("RNG").
+ *
+ * Supported argument space of the GPU library (everything else returns
+ * QUILT_ERR_UNSUPPORTED / QUILT_ERR_BAD_ARG, never a CPU computation):
+ *   diploid calls (QUILT_F_SAMPLE_IS_DIPLOID, ff == 0)  K <= 8192
+ *   NIPT calls (three haplotypes, 0 <= ff < 1)           K <= 2048, no shard pass
+ *   32 SNPs per grid; shard pass with QUILT_F_SHARD_CHECK_EVERY_PAIR.
  */
 #ifndef QUILT_B200_H
 #define QUILT_B200_H

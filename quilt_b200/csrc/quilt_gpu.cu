@@ -416,6 +416,17 @@ struct QuiltGpuBatch {
 
 namespace {
 
+// reads with up to this many SNPs keep a 2^nb-entry emission table, longer ones a dense column (QUILT_B200_NBMAX: experiments)
+int nb_limit() {
+    static int v = -1;
+    if (v < 0) {
+        v = NBMAX;
+        const char* e = std::getenv("QUILT_B200_NBMAX");
+        if (e) v = std::max(1, std::min(NBMAX, std::atoi(e)));
+    }
+    return v;
+}
+
 // classify every read and lay out its emission table; host-side, O(sum J)
 int prepare_job(HostJob& j) {
     const QuiltGibbsArgs& a = j.a;
@@ -450,7 +461,7 @@ int prepare_job(HostJob& j) {
         int cnt = a.reads.offsets[r + 1] - o;
         if (cnt <= 0) return set_err(QUILT_ERR_BAD_ARG, "read without SNPs");
         if (cnt - 1 >= a.Jmax) cnt = a.Jmax + 1;
-        bool table = cnt <= NBMAX;
+        bool table = cnt <= nb_limit();
         bool run = true;
         for (int q = 0; q < cnt && table; q++) {
             const int s = a.reads.u[o + q];

@@ -8,7 +8,7 @@ namespace qb {
 // most 2^nb values, selected by the alleles of haplotype k at the read's nb SNPs.  For nb <= NBMAX
 // (and SNPs inside grids wif0-1 .. wif0+1) we keep the 2^nb-entry table instead of the K-long fp64
 // column (DESIGN.md "emission tables"); everything else falls back to a dense K-long column.
-constexpr int NBMAX = 8;
+constexpr int NBMAX = 9;
 constexpr double ONE_THRESH = 1.0 - 1e-12;  // rcpp_evaluate_read_variability, gibbs-nipt.cpp:349
 
 struct TabEnt {
@@ -25,7 +25,7 @@ struct ReadDesc {        // 32 bytes, 16-byte aligned (staged to shared memory w
     uint8_t nb;          // pattern bits (SNPs used = min(J + 1, Jmax + 1))
     int8_t g0rel;        // MODE_RUN: word index of the first SNP minus wif0 (-1, 0, +1)
     uint8_t b0;          // MODE_RUN: bit of the first SNP inside that word
-    uint8_t sel[NBMAX];  // MODE_GATHER: per SNP ((word - wif0 + 1) << 5) | bit        (byte offset 9)
+    uint8_t sel[8];      // MODE_GATHER (no longer produced by the host): per SNP ((word - wif0 + 1) << 5) | bit   (byte offset 9)
     uint8_t pad[3];
     uint32_t tnext;      // table-pool offset just after this read's table (cumulative; unchanged by dense reads)
     uint8_t pad2[8];
