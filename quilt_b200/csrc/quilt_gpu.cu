@@ -345,7 +345,7 @@ int with_geo(const Geo& g, F&& f) {
 
 // ------------------------------------------------------------------------------------------------ jobs
 struct JobLayoutIn {  // byte offsets inside the job's input region
-    size_t which, rs, roff, u, pRA, wif0, ts, dense_reads, runif_reads, runif_shard, tm, desc, H0, runif_block, runif_H_class, L_grid, end;
+    size_t which, rs, roff, u, pRA, wif0, ts, ginfo, dense_reads, runif_reads, runif_shard, tm, desc, H0, runif_block, runif_H_class, L_grid, end;
 };
 struct JobLayoutOut {
     size_t underflow, lik, hap, genM, genF, H, Hclass, cat, end;
@@ -359,7 +359,7 @@ struct HostJob {
     JobLayoutOut lo;
     size_t in_off = 0, out_off = 0;  // offsets of the job's regions in the batch arenas
     std::vector<ReadDesc> desc;
-    std::vector<int32_t> rs, ts, dense_reads;
+    std::vector<int32_t> rs, ts, ginfo, dense_reads;
     // debug copies (QUILT_F_RETURN_ALPHA / _EXTRA)
     std::vector<double> dbg_alpha, dbg_beta, dbg_eG, dbg_c, dbg_eMatRead;
 };
@@ -504,6 +504,37 @@ int prepare_job(HostJob& j) {
     while (g_cur < T) j.ts[++g_cur] = n_tab;
     j.n_tab = n_tab;
     j.n_dense = (int)j.dense_reads.size();
+    // staging chunks of the sweep kernel: greedy packing of every grid's reads into SW_MAXR reads / SW_MAXTAB entries
+    j.ginfo.assign((size_t)(T + 1) * 4, 0);
+    for (int g = 0; g <= T; g++) {
+        j.ginfo[4 * g + 0] = j.rs[g];
+        j.ginfo[4 * g + 1] = j.ts[g];
+        j.ginfo[4 * g + 3] = j.ts[g];
+    }
+    for (int g = 0; g < T; g++) {
+        const int r0 = j.rs[g], r1 = j.rs[g + 1];
+        int c0 = 0;
+        uint32_t tab0 = (uint32_t)j.ts[g];
+        while (r0 + c0 < r1) {
+            int n = 0;
+            uint32_t tend = tab0;
+            while (r0 + c0 + n < r1 && n < SW_MAXR) {
+                const uint32_t tn = j.desc[r0 + c0 + n].tnext;
+                if (tn - tab0 > (uint32_t)SW_MAXTAB) break;
+                tend = tn;
+                n++;
+            }
+            if (n == 0) return set_err(QUILT_ERR_UNSUPPORTED, "emission table larger than the staging buffer");
+            j.desc[r0 + c0].chunk_n = (uint16_t)n;
+            j.desc[r0 + c0].chunk_tend = tend;
+            if (c0 == 0) {
+                j.ginfo[4 * g + 2] = n;
+                j.ginfo[4 * g + 3] = (int32_t)tend;
+            }
+            tab0 = tend;
+            c0 += n;
+        }
+    }
     return QUILT_OK;
 }
 
@@ -520,6 +551,7 @@ void layout_in(HostJob& j) {
     L.pRA = o, o += al((size_t)j.nU * 16);
     L.wif0 = o, o += al((size_t)R * 4);
     L.ts = o, o += al((size_t)(T + 1) * 4);
+    L.ginfo = o, o += al((size_t)(T + 1) * 16);
     L.dense_reads = o, o += al((size_t)std::max(j.n_dense, 1) * 4);
     L.runif_reads = o, o += al((size_t)std::max(j.n_its, 1) * R * 8);
     L.runif_shard = o, o += al((size_t)std::max(j.n_ep, 1) * std::max(T - 1, 1) * 8);
@@ -584,6 +616,7 @@ void fill_in(const HostJob& j, char* base) {
     fill_pRA(j, reinterpret_cast<double*>(base + L.pRA));
     std::memcpy(base + L.wif0, a.reads.wif0, (size_t)R * 4);
     std::memcpy(base + L.ts, j.ts.data(), (size_t)(T + 1) * 4);
+    std::memcpy(base + L.ginfo, j.ginfo.data(), (size_t)(T + 1) * 16);
     if (j.n_dense) std::memcpy(base + L.dense_reads, j.dense_reads.data(), (size_t)j.n_dense * 4);
     if (j.n_its > 0) std::memcpy(base + L.runif_reads, a.runif_reads, (size_t)j.n_its * R * 8);
     if (j.n_ep > 0 && T > 1 && a.runif_shard) std::memcpy(base + L.runif_shard, a.runif_shard, (size_t)j.n_ep * (T - 1) * 8);
@@ -799,6 +832,7 @@ void make_jobdev(const QuiltGpuBatch* B, const Bucket& bk, const HostJob& j, int
     D->pRA = (const double*)(in + j.li.pRA);
     D->wif0 = (const int32_t*)(in + j.li.wif0);
     D->ts = (const int32_t*)(in + j.li.ts);
+    D->ginfo = (const int32_t*)(in + j.li.ginfo);
     D->dense_reads = (const int32_t*)(in + j.li.dense_reads);
     D->runif_reads = (const double*)(in + j.li.runif_reads);
     D->runif_shard = (const double*)(in + j.li.runif_shard);

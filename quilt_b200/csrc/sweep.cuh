@@ -487,7 +487,6 @@ __global__ void __launch_bounds__(NT, (NT * EPT <= 512 ? 4 : (NT * EPT <= 1024 ?
     uint32_t* Wr = reinterpret_cast<uint32_t*>(smem + L.off_W);          // [4][KA] ring of allele words
     uint16_t* spat = reinterpret_cast<uint16_t*>(smem + L.off_pat);      // [KA] allele patterns of gather-mode reads
     double* eGs = reinterpret_cast<double*>(smem + L.off_eG);            // [2][NH][KA]
-    uint32_t* rmask = reinterpret_cast<uint32_t*>(smem + L.off_rec);     // [6..7] chunk size / table end of an over-full grid
     const bool iterative = (P.flags & QUILT_F_GIBBS_INITIALIZE_ITERATIVELY) != 0;
     const bool record = (P.flags & QUILT_F_RECORD_READ_SET) != 0;
     const double one_over_K = P.one_over_K;
@@ -541,7 +540,7 @@ __global__ void __launch_bounds__(NT, (NT * EPT <= 512 ? 4 : (NT * EPT <= 1024 ?
     // ---- one package = everything grid g needs: eMatGrid columns, the allele words of grid g+1 (ring of 4:
     //      grid g uses words g-1 .. g+1 while package g+1 is already filling word g+2), and the read
     //      metadata of the grid when it fits one staging buffer
-    auto issue_pkg = [&](int g, int r0, int r1, int t0, int t1) {
+    auto issue_pkg = [&](int g, int r0, int r1, int t0, int fcn, int fct) {
         const int s = g & 1;
         const int n_g = r1 - r0;
         {
@@ -549,23 +548,22 @@ __global__ void __launch_bounds__(NT, (NT * EPT <= 512 ? 4 : (NT * EPT <= 1024 ?
             // package can be issued without a dependent global load), the transition pair into g, the previous c of g
             // one predicated 4-byte cp.async per lane of warp 1 (no divergent single-thread blocks: warp 0 already
             // carries the bulk-copy issue, and everything a single warp does alone delays the next block barrier)
-            unsigned char* sc = smem + L.off_sc + s * 64;
+            // block layout (96 bytes): ginfo rows g + 1 and g + 2 {first read, table offset, reads / table end of the
+            // first staging chunk}, transition pair, previous c
+            unsigned char* sc = smem + L.off_sc + s * 96;
             const int q = tid - 32;
-            if (q >= 0 && q < 8 + 2 * NH) {
+            if (q >= 0 && q < 12 + 2 * NH) {
                 const int32_t* src;
                 bool ok = true;
-                if (q < 2) {
-                    src = rs + g + 1 + q;
-                    ok = g + 1 + q <= T;
-                } else if (q < 4) {
-                    src = tsG + g + 1 + (q - 2);
-                    ok = g + 1 + (q - 2) <= T;
-                } else if (q < 8) {
-                    src = reinterpret_cast<const int32_t*>(tmG + 2 * (g - 1)) + (q - 4);
+                if (q < 8) {
+                    src = J.ginfo + 4 * (g + 1) + q;
+                    ok = g + 1 + (q >> 2) <= T;
+                } else if (q < 12) {
+                    src = reinterpret_cast<const int32_t*>(tmG + 2 * (g - 1)) + (q - 8);
                     ok = g >= 1;
                 } else {
-                    const int hh = (q - 8) >> 1;
-                    src = reinterpret_cast<const int32_t*>(cG + hh * T + g) + ((q - 8) & 1);
+                    const int hh = (q - 12) >> 1;
+                    src = reinterpret_cast<const int32_t*>(cG + hh * T + g) + ((q - 12) & 1);
                 }
                 if (ok) cp_async4(sc + 4 * q, src);
             }
@@ -581,20 +579,17 @@ __global__ void __launch_bounds__(NT, (NT * EPT <= 512 ? 4 : (NT * EPT <= 1024 ?
             if (g == 0) bulk_g2s(Wr, J.W + kbase, Kpl * 4, &bar[s]);
             if (g + 1 < T) bulk_g2s(Wr + ((g + 1) & 3) * KA, J.W + kbase + (size_t)(g + 1) * Kp, Kpl * 4, &bar[s]);
         }
-        bool small_done = false;
-        if (n_g > 0) {
-            const int nt = t1 - t0;
-            if (n_g <= SW_MAXR && nt <= SW_MAXTAB) {
-                stage_small(s, r0, n_g, t0, nt, true);
-                small_done = true;
-            }
-        }
-        if (!small_done) cp_async_commit();
+        // the first staging chunk of the grid (all of its reads unless the grid is over-full; host-computed packing)
+        if (n_g > 0)
+            stage_small(s, r0, fcn, t0, fct - t0, true);
+        else
+            cp_async_commit();
         // Pull the FOLLOWING grid's read metadata towards L2 (a window from its first read / table entry on): the
         // cp.async package above is waited for by the next block barrier (measured), so its latency is on the serial
         // chain; when the lines already sit in L2 that wait is an L2 hit, not a DRAM round trip.
         if (!(P.dbg & 8)) {
             constexpr int PF_READS = 32, PF_TAB = 512;
+            const int t1 = fct;  // (tables of the following grid start at or after the end of this grid's first chunk)
             const int nd = min(PF_READS, R - r1), ntb = min(PF_TAB, n_tab_total - t1);
             const int l_desc = (nd * 32 + 127) >> 7, l_tab = (ntb * 16 + 127) >> 7, l_u = (nd * 8 + 127) >> 7, l_h = (nd * 4 + 127) >> 7;
             int l = tid - 64;  // (warps 0 and 1 carry the bulk-copy issue and the scalar package)
@@ -661,27 +656,31 @@ __global__ void __launch_bounds__(NT, (NT * EPT <= 512 ? 4 : (NT * EPT <= 1024 ?
 
     // per-grid scalars arrive with the package (cp.async into the stage's scalar block): nothing on the serial chain
     // waits for a dependent global load
-    int cur_r0 = rs[0], cur_t0 = tsG[0];
-    issue_pkg(0, cur_r0, rs[1], cur_t0, tsG[1]);
+    int cur_r0 = J.ginfo[0], cur_t0 = J.ginfo[1], cur_fcn = J.ginfo[2], cur_fct = J.ginfo[3];
+    issue_pkg(0, cur_r0, rs[1], cur_t0, cur_fcn, cur_fct);
     issue_eG(0);
     // =============================================================== forward + read resampling
     for (int g = 0; g < T; g++) {
         wait_pkg(g);
         const int s = g & 1;
-        const int32_t* sci = reinterpret_cast<const int32_t*>(smem + L.off_sc + s * 64);
+        const int32_t* sci = reinterpret_cast<const int32_t*>(smem + L.off_sc + s * 96);
         const double* scd = reinterpret_cast<const double*>(sci);
         const int r0 = cur_r0, r1 = sci[0];
-        const int ts0 = cur_t0, ts1 = sci[2];
-        const int nx_r1 = sci[1], nx_t1 = sci[3];
-        const double tm_x = scd[2], tm_t1 = scd[3];
+        const int ts0 = cur_t0, ts1 = sci[1];
+        const int fcn = cur_fcn, fct = cur_fct;        // first staging chunk of this grid (already in shared memory)
+        const int nx_fcn = sci[2], nx_fct = sci[3];    // ... of the next grid
+        const int nx_r1 = sci[4];
+        const double tm_x = scd[4], tm_t1 = scd[5];
         const int n_g = r1 - r0;
         const bool has = n_g > 0;
         double* eg = eGs + (size_t)(s * NH) * KA;
         double c_old[NH];
 #pragma unroll
-        for (int h = 0; h < NH; h++) c_old[h] = scd[4 + h];
+        for (int h = 0; h < NH; h++) c_old[h] = scd[6 + h];
         cur_r0 = r1;
         cur_t0 = ts1;
+        cur_fcn = nx_fcn;
+        cur_fct = nx_fct;
         double ab[NH][EPT];
         const bool next_has = (g + 1 < T) && (nx_r1 > r1);
         if (has || g == 0) wait_eG(g);
@@ -695,7 +694,7 @@ __global__ void __launch_bounds__(NT, (NT * EPT <= 512 ? 4 : (NT * EPT <= 1024 ?
             eG_next_issued = true;
         }
         if (g + 1 < T) {
-            if (!(P.dbg & 2)) issue_pkg(g + 1, r1, nx_r1, ts1, nx_t1);
+            if (!(P.dbg & 2)) issue_pkg(g + 1, r1, nx_r1, ts1, nx_fcn, nx_fct);
             if (P.dbg & 4) cp_async_wait_all();  // experiment: does the next barrier already wait for the cp.async package?
             // pull the next grid's beta columns towards L2 (one 128-byte line per 16 doubles)
             if (nx_r1 > r1 && !(P.dbg & 1)) {
@@ -761,7 +760,7 @@ __global__ void __launch_bounds__(NT, (NT * EPT <= 512 ? 4 : (NT * EPT <= 1024 ?
             }
         }
         // am now holds alphaHat_t[:, g]; it stays in registers as the previous column of the next grid
-        if (g + 1 < T && (P.dbg & 2)) issue_pkg(g + 1, r1, nx_r1, ts1, nx_t1);  // experiment: issue after the forward step
+        if (g + 1 < T && (P.dbg & 2)) issue_pkg(g + 1, r1, nx_r1, ts1, nx_fcn, nx_fct);  // experiment: issue after the forward step
         bool changed = false;
         if (has) {
             const unsigned char* sm = smem + L.off_small[s];
@@ -964,30 +963,20 @@ __global__ void __launch_bounds__(NT, (NT * EPT <= 512 ? 4 : (NT * EPT <= 1024 ?
             };
 
             // ---------------------------------------------------------------- the grid's reads, chunk by chunk
-            const bool prestaged = (n_g <= SW_MAXR) && (ts1 - ts0 <= SW_MAXTAB);
             const bool special_its = iterative && iteration <= 1;  // sweeps with pass-through / initialisation reads
             int c0 = 0;
             uint32_t tab0 = (uint32_t)ts0;
+            int cn = fcn;                    // the first chunk arrived with the grid's package
+            uint32_t tend = (uint32_t)fct;
             while (c0 < n_g) {
-                int cn = n_g;
-                if (!prestaged) {
-                    // rare: a grid with more reads / table entries than one staging buffer holds
-                    __syncthreads();
-                    if (tid == 0) {
-                        int n = 0;
-                        uint32_t tend = tab0;
-                        while (c0 + n < n_g && n < SW_MAXR) {
-                            const uint32_t tn = J.desc[r0 + c0 + n].tnext;
-                            if (tn - tab0 > (uint32_t)SW_MAXTAB) break;
-                            tend = tn;
-                            n++;
-                        }
-                        rmask[6] = (uint32_t)n;
-                        rmask[7] = tend;
-                    }
-                    __syncthreads();
-                    cn = (int)rmask[6];
-                    stage_small(s, r0 + c0, cn, (int)tab0, (int)(rmask[7] - tab0), false);
+                if (c0 > 0) {
+                    // over-full grid: the next chunk (host-computed boundaries, kept in the descriptor of its first read)
+                    // is staged synchronously
+                    __syncthreads();  // every thread is done with the previous chunk's staged data
+                    const uint2 ch = *reinterpret_cast<const uint2*>(reinterpret_cast<const unsigned char*>(J.desc + r0 + c0) + 24);
+                    cn = (int)(ch.x & 0xffffu);
+                    tend = ch.y;
+                    stage_small(s, r0 + c0, cn, (int)tab0, (int)(tend - tab0), false);
                 }
                 for (int ir = 0; ir < cn; ir++) {
                     const uint4 dq = *reinterpret_cast<const uint4*>(descs + ir);
@@ -1077,7 +1066,7 @@ __global__ void __launch_bounds__(NT, (NT * EPT <= 512 ? 4 : (NT * EPT <= 1024 ?
                         }
                     }
                 }
-                if (!prestaged) tab0 = rmask[7];
+                tab0 = tend;
                 c0 += cn;
             }
 #undef QB_SUM
@@ -1155,7 +1144,7 @@ __global__ void __launch_bounds__(NT, (NT * EPT <= 512 ? 4 : (NT * EPT <= 1024 ?
 #pragma unroll
                 for (int h = 0; h < NH; h++) bulk_g2s(dst + (size_t)h * KA, eGg + ((size_t)h * T + g + 1) * Kp, Kpl * 8, &bar[q]);
             }
-            unsigned char* sc = smem + L.off_sc + (2 + q) * 64;
+            unsigned char* sc = smem + L.off_sc + 192 + q * 64;
             const int ql = tid - 32;
             if (ql >= 0 && ql < 8 + 2 * NH && (ql < 2 || ql >= 4)) {
                 const int32_t* src;
@@ -1190,7 +1179,7 @@ __global__ void __launch_bounds__(NT, (NT * EPT <= 512 ? 4 : (NT * EPT <= 1024 ?
                 n_use2++;
             }
             __syncthreads();  // the other threads' cp.async scalars are visible
-            const int32_t* sci = reinterpret_cast<const int32_t*>(smem + L.off_sc + (2 + q) * 64);
+            const int32_t* sci = reinterpret_cast<const int32_t*>(smem + L.off_sc + 192 + q * 64);
             const double* scd = reinterpret_cast<const double*>(sci);
             const bool has1 = sci[1] > sci[0];
             const double* eg = bstage(q);

@@ -28,7 +28,11 @@ struct ReadDesc {        // 32 bytes, 16-byte aligned (staged to shared memory w
     uint8_t sel[8];      // MODE_GATHER (no longer produced by the host): per SNP ((word - wif0 + 1) << 5) | bit   (byte offset 9)
     uint8_t pad[3];
     uint32_t tnext;      // table-pool offset just after this read's table (cumulative; unchanged by dense reads)
-    uint8_t pad2[8];
+    // staging chunks of the sweep kernel (host-computed greedy packing of a grid's reads into SW_MAXR reads /
+    // SW_MAXTAB table entries): set on the first read of every chunk
+    uint16_t chunk_n;    // reads in the chunk that starts at this read (0 elsewhere)
+    uint16_t pad2;
+    uint32_t chunk_tend; // table-pool offset just after the chunk's last table
 };
 static_assert(sizeof(ReadDesc) == 32, "ReadDesc must be 32 bytes");
 
@@ -64,6 +68,7 @@ struct JobDev {
     const double* pRA;     // [nU][2] (pR, pA) running values per read-SNP, computed on the host with libm pow()
     const int32_t* wif0;   // [R]
     const int32_t* ts;     // [T + 1] first table-pool entry of each grid's reads (table-mode reads only)
+    const int32_t* ginfo;  // [T + 1][4] per grid {rs, ts, reads in its first staging chunk, table end of that chunk}
     const int32_t* dense_reads;  // [n_dense] read indices stored as dense columns
     const double* runif_reads;  // [n_its][R]
     const double* runif_shard;  // [n_ep][T - 1]
