@@ -334,11 +334,8 @@ int with_geo(const Geo& g, F&& f) {
     QB_GEO(128, 4)
     QB_GEO(256, 4)
     QB_GEO(512, 4)
-    QB_GEO(512, 8)
+    QB_GEO(512, 8)  // experiments only (QUILT_B200_GEO=512x8): the comparison quoted in DESIGN.md
     QB_GEO(256, 16)
-    QB_GEO(256, 8)
-    QB_GEO(128, 8)
-    QB_GEO(64, 8)
 #undef QB_GEO
     return set_err(QUILT_ERR_UNSUPPORTED, "no kernel geometry");
 }
