@@ -312,12 +312,14 @@ bool pick_geo(int K, Geo* g, int NH = 2) {
         *g = {env_nt, env_ept, 1};
         return true;
     }
+    // eight elements per thread below K = 4096 (measured on B200 against 4 and 16 per thread: 7 % / 14 % / 21 % faster
+    // than the 4-per-thread geometries at K = 512 / 1024 / 2048, 16 per thread slower at every K <= 2048)
     if (K <= 512)
-        *g = {128, 4};
+        *g = {64, 8};
     else if (K <= 1024)
-        *g = {256, 4};
+        *g = {128, 8};
     else if (K <= 2048)
-        *g = {512, 4};
+        *g = {256, 8};
     else if (K <= 4096)
         *g = {256, 16};  // measured 19% faster than 512 x 8 on the K = 4096 benchmark
     else if (K <= 8192 && NH == 2)
@@ -331,11 +333,11 @@ template <typename F>
 int with_geo(const Geo& g, F&& f) {
 #define QB_GEO(NT_, EPT_) \
     if (g.NT == NT_ && g.EPT == EPT_) return f(std::integral_constant<int, NT_>(), std::integral_constant<int, EPT_>());
-    QB_GEO(128, 4)
-    QB_GEO(256, 4)
-    QB_GEO(512, 4)
-    QB_GEO(512, 8)  // experiments only (QUILT_B200_GEO=512x8): the comparison quoted in DESIGN.md
+    QB_GEO(64, 8)
+    QB_GEO(128, 8)
+    QB_GEO(256, 8)
     QB_GEO(256, 16)
+    QB_GEO(512, 8)  // experiments only (QUILT_B200_GEO=512x8): the comparison quoted in DESIGN.md
 #undef QB_GEO
     return set_err(QUILT_ERR_UNSUPPORTED, "no kernel geometry");
 }

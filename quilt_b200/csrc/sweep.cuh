@@ -551,7 +551,7 @@ __global__ void __launch_bounds__(NT, (NT * EPT <= 512 ? 4 : (NT * EPT <= 1024 ?
             // block layout (96 bytes): ginfo rows g + 1 and g + 2 {first read, table offset, reads / table end of the
             // first staging chunk}, transition pair, previous c
             unsigned char* sc = smem + L.off_sc + s * 96;
-            const int q = tid - 32;
+            const int q = (NT > 32) ? tid - 32 : tid;
             if (q >= 0 && q < 12 + 2 * NH) {
                 const int32_t* src;
                 bool ok = true;
@@ -1145,7 +1145,7 @@ __global__ void __launch_bounds__(NT, (NT * EPT <= 512 ? 4 : (NT * EPT <= 1024 ?
                 for (int h = 0; h < NH; h++) bulk_g2s(dst + (size_t)h * KA, eGg + ((size_t)h * T + g + 1) * Kp, Kpl * 8, &bar[q]);
             }
             unsigned char* sc = smem + L.off_sc + 192 + q * 64;
-            const int ql = tid - 32;
+            const int ql = (NT > 32) ? tid - 32 : tid;
             if (ql >= 0 && ql < 8 + 2 * NH && (ql < 2 || ql >= 4)) {
                 const int32_t* src;
                 if (ql < 2)

@@ -83,3 +83,15 @@ def test_no_rescale_and_no_record(gpu, oracle, small_world, small_reads):
     call = synth.make_call(small_world, small_reads.common, 47, K=200, first_iteration=False, flags=flags, n_burn_in=4, n_sample=1, block_its=())
     g, o = _run_both(gpu, oracle, call)
     _compare("no rescale / no record", g, o)
+
+
+def test_long_region_many_grids(gpu, oracle):
+    """T = 2500 common / 7500 all-SNP grids and ~27k reads (a 7.5 Mb window at 1x): larger offsets than the benchmark shape"""
+    w = synth.make_world(777, K_full=700, nSNPs=80_000, region_bp=7_500_000, all_snps_factor=3)
+    sr = synth.make_sample_reads(w, 778, coverage=0.55, region_bp=7_500_000)
+    call = synth.make_call(w, sr.common, 48, K=512, first_iteration=True)
+    g, o = _run_both(gpu, oracle, call)
+    _compare(f"long region common T={w.nGrids} R={sr.common.nReads}", g, o, state=False)
+    call = synth.make_call(w, sr.all, 49, K=256, all_snps=True, sort_haps=False, n_burn_in=5, n_sample=1, block_its=(2,))
+    g, o = _run_both(gpu, oracle, call)
+    _compare(f"long region all-SNP T={w.nGrids_all} R={sr.all.nReads}", g, o, state=False)

@@ -19,6 +19,8 @@ for c in cfgs:
             extra += ["--K", kv[2:]]
         elif kv.startswith("JOBS="):
             extra += ["--jobs", kv[5:]]
+        elif kv.startswith("FF="):
+            extra += ["--ff", kv[3:], "--coverage", "0.5"]
         elif "=" in kv:
             k, v = kv.split("=", 1)
             env["QUILT_B200_" + k] = v

@@ -14,13 +14,16 @@ ap.add_argument("--its", type=int, default=6)
 ap.add_argument("--all-snps", action="store_true")
 ap.add_argument("--iterative", action="store_true")
 ap.add_argument("--nsnps", type=int, default=32000)
+ap.add_argument("--ff", type=float, default=0.0, help="> 0: three-haplotype (NIPT) calls")
+ap.add_argument("--coverage", type=float, default=1.0)
 a = ap.parse_args()
 w = synth.make_world(20260118, K_full=max(a.K + 100, 5008), nSNPs=a.nsnps, region_bp=int(3_000_000 * a.nsnps / 32000), all_snps_factor=3 if a.all_snps else 0)
 calls = []
 for j in range(a.jobs):
-    sr = synth.make_sample_reads(w, 50 + j, coverage=1.0, region_bp=int(3_000_000 * a.nsnps / 32000))
+    sr = synth.make_sample_reads(w, 50 + j, coverage=a.coverage, region_bp=int(3_000_000 * a.nsnps / 32000), n_true_haps=3 if a.ff > 0 else 2,
+                                 hap_probs=(0.5, 0.5 - a.ff / 2, a.ff / 2) if a.ff > 0 else None)
     calls.append(synth.make_call(w, sr.all if a.all_snps else sr.common, 70 + j, K=a.K, all_snps=a.all_snps, first_iteration=a.iterative,
-                                 n_burn_in=a.its - 1, n_sample=1, block_its=(3,)))
+                                 n_burn_in=a.its - 1, n_sample=1, block_its=(3,), ff=a.ff))
 lib = api.GpuLib()
 b = api.Batch(lib, calls)
 for i in range(2):
