@@ -149,3 +149,12 @@ def test_bench_reference_arm_prints_one_json_line():
     assert d["impl"] == "reference" and d["unit"] == "samples/s" and d["value"] > 0
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+
+
+def test_rcpp_shim_type_checks_against_the_c_abi():
+    """shim/quilt_gpu_shim.cpp cannot be built for real here (no R / Rcpp); type-check it against a minimal stand-in for
+    <Rcpp.h> so that its use of include/quilt_b200.h (struct fields, entry points, flag names) is at least compiled"""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-Wall", "-I" + os.path.join(root, "tests", "rcpp_mock"), "-I" + os.path.join(root, "include"),
+                        os.path.join(root, "shim", "quilt_gpu_shim.cpp")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
