@@ -584,9 +584,8 @@ __global__ void __launch_bounds__(NT, (NT * EPT <= 512 ? 4 : (NT * EPT <= 1024 ?
             stage_small(s, r0, fcn, t0, fct - t0, true);
         else
             cp_async_commit();
-        // Pull the FOLLOWING grid's read metadata towards L2 (a window from its first read / table entry on): the
-        // cp.async package above is waited for by the next block barrier (measured), so its latency is on the serial
-        // chain; when the lines already sit in L2 that wait is an L2 hit, not a DRAM round trip.
+        // Pull the FOLLOWING grid's read metadata towards L2 (a window from its first read / table entry on), so that
+        // the cp.async package issued for it one grid later is served from L2 (measured: ~1 % of the sweep).
         if (!(P.dbg & 8)) {
             constexpr int PF_READS = 32, PF_TAB = 512;
             const int t1 = fct;  // (tables of the following grid start at or after the end of this grid's first chunk)
