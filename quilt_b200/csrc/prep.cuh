@@ -215,13 +215,21 @@ __global__ void __launch_bounds__(TAB_WARPS * 32) k_build_tables(BatchParams P, 
     __syncwarp();
     // 2. how many of the K haplotypes show each pattern
     // (lanes showing the same pattern elect one leader that adds their count: no shared-memory atomics)
-    for (int k0 = 0; k0 < P.K; k0 += 32) {
-        const int k = k0 + lane;
-        const bool in = k < P.K;
-        const uint32_t pat = in ? read_pattern_staged(d, Ws, Kp, k) : 0xffffffffu;
-        const uint32_t peers = __match_any_sync(0xffffffffu, pat);
-        if (in && lane == __ffs(peers) - 1) hs[pat] += __popc(peers);
-        __syncwarp();
+    // (four independent match.any per trip: the instruction is slow, its latency is what bounds this loop)
+    for (int k0 = 0; k0 < P.K; k0 += 128) {
+        uint32_t pat[4], peers[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int k = k0 + 32 * q + lane;
+            pat[q] = (k < P.K) ? read_pattern_staged(d, Ws, Kp, k) : 0xffffffffu;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q++) peers[q] = __match_any_sync(0xffffffffu, pat[q]);
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            if (pat[q] != 0xffffffffu && lane == __ffs(peers[q]) - 1) hs[pat[q]] += __popc(peers[q]);
+            __syncwarp();
+        }
     }
     // 3. rescale by the maximum over the haplotypes present, then floor (gibbs-small.cpp:235-262)
     bool degenerate = false;
