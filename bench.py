@@ -14,10 +14,14 @@ NCCL broadcast of the prepared reference and the max-reduction of the timed regi
 value      device-timed (CUDA events on the library stream), inputs resident in HBM before the timed region
 e2e        the same batch through quilt_gpu_gibbs_batch with HOST buffers: host preparation, H2D, kernels, D2H
 roofline   the sweep kernel: algorithmic bytes (8 K (5 nHap T + R) per job and sweep) / event time
+parity_gate  before anything is timed: one whole sample's calls (32 at the headline workload) through the CPU checker on
+           the host threads, compared with the staged batch's fetched outputs; any label / GT mismatch or
+           max |dDS|, |dGP| > 1e-4 voids the run (non-zero exit)
 cpu_baseline / --impl reference
-           the reference cannot be compiled in this image (needs R / Rcpp / RcppArmadillo), so the CPU arm is the
-           statement-order C++ oracle (kind "port"), one call per thread on all host cores, like the reference's
-           one-forked-worker-per-core model (QUILT/R/quilt.R:690-692)
+           the reference's OWN C++ for this path (oracle/_ref/libquiltref.so: the unmodified QUILT/src sources compiled
+           against the header-only RcppArmadillo stand-in, kind "reference"), one call per thread on all host cores
+           like the reference's one-forked-worker-per-core model (QUILT/R/quilt.R:690-692); if that library is absent
+           the statement-order oracle port is timed instead (kind "port")
 """
 from __future__ import annotations
 
@@ -129,22 +133,71 @@ def build_inputs(wl, rank, world_obj, log):
     return calls
 
 
-def cpu_arm(wl, world_obj, log, budget_calls_per_thread=1):
-    """Oracle timed on the host cores: each thread runs one common-SNP call and one all-SNP call of its own sample
-    concurrently with all the others; per-sample time = 8 t_iterative + 16 t_normal + 8 t_all (the QUILT2 schedule)."""
+def cpu_checker(prefer: str = "reference"):
+    """-> (library object with .gibbs(call), kind).  "reference" = oracle/_ref (the reference's own sources compiled against
+    the RcppArmadillo stand-in), "port" = the oracle restatement.  Test / baseline infrastructure only."""
+    if prefer == "reference":
+        try:
+            from oracle import ref_py
+
+            if ref_py.available():
+                return ref_py.Ref(), "reference"
+        except Exception:
+            pass
+    from oracle.oracle_py import Oracle
+
+    return Oracle(), "port"
+
+
+def host_cores() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def parity_gate(calls, results, log, prefer="reference"):
+    """CPU checker vs the GPU outputs on the given calls (one whole sample): exact labels / H_class / GT, DS and GP to 1e-4."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    chk, kind = cpu_checker(prefer)
+    threads = max(1, min(host_cores(), len(calls)))
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(max_workers=threads) as ex:
+        ref = list(ex.map(chk.gibbs, calls))
+    gate = {"calls": len(calls), "checker": kind, "label_mismatches": 0, "H_class_mismatches": 0, "gt_mismatches": 0, "underflow_mismatches": 0,
+            "max_dDS": 0.0, "max_dGP": 0.0, "tolerance": 1e-4}
+    for c, g, o in zip(calls, results, ref):
+        if bool(g.underflow_problem) != bool(o.underflow_problem):
+            gate["underflow_mismatches"] += 1
+            continue
+        if o.underflow_problem:
+            continue
+        gate["label_mismatches"] += int(np.sum(g.H != o.H))
+        gate["H_class_mismatches"] += int(np.sum(g.H_class != o.H_class))
+        gate["gt_mismatches"] += int(np.sum(np.argmax(g.genProbsM_t, axis=0) != np.argmax(o.genProbsM_t, axis=0)))
+        nh = 2 if c.ff == 0 else 3
+        gate["max_dDS"] = max(gate["max_dDS"], float(np.max(np.abs(g.hapProbs_t[:nh].sum(0) - o.hapProbs_t[:nh].sum(0)))))
+        gate["max_dGP"] = max(gate["max_dGP"], float(np.max(np.abs(g.genProbsM_t - o.genProbsM_t))), float(np.max(np.abs(g.genProbsF_t - o.genProbsF_t))))
+    gate["seconds"] = time.perf_counter() - t0
+    gate["passed"] = (gate["label_mismatches"] == 0 and gate["H_class_mismatches"] == 0 and gate["gt_mismatches"] == 0 and gate["underflow_mismatches"] == 0
+                      and gate["max_dDS"] <= 1e-4 and gate["max_dGP"] <= 1e-4)
+    log(f"parity gate ({kind}, {threads} threads, {gate['seconds']:.1f}s): {gate}")
+    return gate
+
+
+def cpu_arm(wl, world_obj, log, prefer="reference"):
+    """The CPU implementation timed on the host cores: each thread runs one common-SNP call and one all-SNP call of its own
+    sample concurrently with all the others (even threads: an iterative-initialisation call, odd threads: a normal one);
+    per-sample time = 8 t_iterative + 16 t_normal + 8 t_all (the QUILT2 schedule) — a bounded sample, extrapolated."""
     from concurrent.futures import ThreadPoolExecutor
 
     import psutil
 
-    from oracle.oracle_py import Oracle
     from quilt_b200 import synth
 
-    orc = Oracle()
-    cores = os.cpu_count() or 1
-    try:
-        cores = len(os.sched_getaffinity(0))
-    except Exception:
-        pass
+    orc, kind_impl = cpu_checker(prefer)
+    cores = host_cores()
     K = wl["K"]
     per_thread_gb = (8.0 * K * 20000 + 4.0 * K * 20000 + 3 * 2 * 8.0 * K * 3000) / 1e9 * 1.3 + 0.3
     mem_cap = max(1, int(psutil.virtual_memory().available / 1e9 / per_thread_gb))
@@ -155,7 +208,7 @@ def cpu_arm(wl, world_obj, log, budget_calls_per_thread=1):
     for t in range(threads):
         sr = synth.make_sample_reads(world_obj, 777000 + t, coverage=wl["coverage"], region_bp=wl["region_bp"], n_true_haps=3 if ff > 0 else 2,
                                      hap_probs=(0.5, 0.5 - ff / 2, ff / 2) if ff > 0 else None)
-        kind = "iterative" if t % 3 == 0 else "normal"
+        kind = "iterative" if t % 2 == 0 else "normal"
         jobs.append((kind, synth.make_call(world_obj, sr.common, 5000 + t, K=K, first_iteration=(kind == "iterative"), ff=ff)))
         if has_all:
             jobs.append(("all", synth.make_call(world_obj, sr.all, 6000 + t, K=K, all_snps=True, sort_haps=False, ff=ff)))
@@ -184,8 +237,11 @@ def cpu_arm(wl, world_obj, log, budget_calls_per_thread=1):
         "value": value,
         "unit": "samples/s",
         "cores": threads,
-        "kind": "port",
-        "sample": f"{threads} concurrent threads x (1 common-SNP call + 1 all-SNP call) of the same workload; per-sample time = 8*t_iterative + 16*t_normal + 8*t_all",
+        "kind": kind_impl,
+        "impl": ("oracle/_ref/libquiltref.so: unmodified QUILT/src sources compiled against the RcppArmadillo stand-in" if kind_impl == "reference"
+                 else "oracle/libquiltoracle.so: statement-order restatement"),
+        "sample": f"{threads} concurrent threads x (1 common-SNP call + 1 all-SNP call) of the same workload, timed once and EXTRAPOLATED to the "
+                  f"32-call schedule: per-sample time = 8*t_iterative + 16*t_normal + 8*t_all",
         "seconds_per_call": {"iterative": t_it, "normal": t_no, "all_snps": t_all},
         "host_cores": cores,
     }, wall
@@ -201,6 +257,8 @@ def main():
     ap.add_argument("--samples", type=int, default=0, help="samples per GPU per step (default: workload's)")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity-gate", action="store_true", help="experiments only: a line without the gate is not a benchmark result")
+    ap.add_argument("--cpu-impl", default="reference", choices=["reference", "port"], help="CPU arm / gate checker: oracle/_ref or the oracle port")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -238,7 +296,7 @@ def main():
         cb = None
         # each "step" is the bounded sample; warm-up steps would only repeat ~25 s of CPU work, one is enough for page-in
         for i in range(max(1, min(args.steps, 2))):
-            cb, wall = cpu_arm(wl, w, log)
+            cb, wall = cpu_arm(wl, w, log, args.cpu_impl)
             vals.append(cb["value"])
             walls.append(wall)
         v = statistics.mean(vals)
@@ -248,7 +306,8 @@ def main():
             "ms_per_step": 1e3 * statistics.mean(walls), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": config, "cpu_baseline": cb,
             "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "note": "the reference needs R/Rcpp/RcppArmadillo (absent): CPU arm = statement-order C++ oracle, one call per thread on all host cores",
+            "note": "CPU arm = " + cb["impl"] + "; one single-threaded call per host thread on all host cores (the reference has no OpenMP); "
+                    "the per-step value is extrapolated from one timed call of each kind per thread (see cpu_baseline.sample)",
         }
         print(json.dumps(line), flush=True)
         return 0
@@ -281,6 +340,12 @@ def main():
         batch.run()
         batch.sync()
         log(f"warmup {i}: {batch.timing()['total_ms']:.1f} ms")
+    # ---- parity gate (rank 0, its first sample): nothing below counts unless the GPU outputs match the CPU checker
+    gate = None
+    if rank == 0 and not args.no_parity_gate:
+        cps = config["calls_per_sample"]
+        gate = parity_gate(calls[:cps], batch.fetch()[:cps], log, args.cpu_impl)
+    dist.barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
     dist.barrier()
@@ -344,17 +409,20 @@ def main():
 
     cb = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cb, _ = cpu_arm(wl, w, log)
+        cb, _ = cpu_arm(wl, w, log, args.cpu_impl)
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": config, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cb,
-            "wall_ms_per_step": wall_per_step,
+            "wall_ms_per_step": wall_per_step, "parity_gate": gate,
         }
         print(json.dumps(line), flush=True)
     dist.barrier()
     dist.shutdown()
+    if gate is not None and not gate["passed"]:
+        log("PARITY GATE FAILED: the throughput above is void")
+        return 3
     return 0
 
 

@@ -35,6 +35,12 @@
  *   diploid calls (QUILT_F_SAMPLE_IS_DIPLOID, ff == 0)  K <= 8192
  *   NIPT calls (three haplotypes, 0 <= ff < 1)           K <= 2048, no shard pass
  *   32 SNPs per grid; shard pass with QUILT_F_SHARD_CHECK_EVERY_PAIR.
+ *
+ * Dependency of the diploid path on the reference's build: for two haplotypes the block resampler
+ * (gibbs-nipt-block.cpp:1636-1967) is skipped because every permutation score of the reference is NaN there — the
+ * third columns of its local matrices and c3 are ZERO-FILLED by Armadillo's constructors (Armadillo >= 10.5; the
+ * compiled reference in oracle/_ref confirms the state is left unchanged).  Against an Armadillo older than 10.5
+ * the reference reads uninitialised memory at that point and no implementation can match it.
  */
 #ifndef QUILT_B200_H
 #define QUILT_B200_H
@@ -59,6 +65,7 @@ extern "C" {
 #define QUILT_F_USE_SMOOTH_CM_IN_BLOCK_GIBBS (1u << 10)
 #define QUILT_F_RETURN_ALPHA                 (1u << 11)  /* debug: copy alpha/beta/c/eMatGrid out */
 #define QUILT_F_RETURN_EXTRA                 (1u << 12)  /* debug: copy eMatRead_t out            */
+#define QUILT_F_GIBBS_INITIALIZE_AT_FIRST_READ (1u << 13) /* first_read_for_gibbs_initialization is 0 and is not drawn (gibbs-nipt.cpp:2846) */
 
 /* production flag word for QUILT2 diploid common-SNP calls (functions.R:620-706) */
 #define QUILT_FLAGS_QUILT2_DIPLOID \
@@ -135,6 +142,18 @@ typedef struct QuiltGibbsArgs {
     int32_t shuffle_bin_radius;
     double  block_gibbs_quantile_prob;
     uint32_t flags;
+    /* Episode stream (optional, replaces runif_block / runif_shard / runif_H_class when non-NULL): R's unif_rand()
+     * stream as it stands right after the call's first two draws (runif(nReads * n_full_its), sample(nReads, 1);
+     * gibbs-nipt.cpp:2845-2848).  The library consumes it in the reference's own order — per block-Gibbs episode
+     * 6 x nReads (runif_proposed, drawn but unused), nReads (runif_block), nReads (runif_total, unused)
+     * (gibbs-nipt.cpp:3013-3018), then for NIPT one value per read whose H_class is 0/4/5/6/7
+     * (rcpp_sample_H_using_H_class, gibbs-nipt-block.cpp:213-246: a DATA-DEPENDENT count), then for the diploid
+     * shard pass nGrids - 1 values (gibbs-nipt-block.cpp:2054) — and reports in QuiltGibbsOut.n_unif_consumed how
+     * many values the reference would have drawn (episodes after an underflow early return draw nothing,
+     * gibbs-nipt.cpp:2959-2969), so that the caller can leave R's generator at exactly the reference's position.
+     * n_unif_stream >= n_episodes * (8 * nReads + (NIPT ? nReads : 0) + (shard ? nGrids - 1 : 0)).              */
+    const double* unif_stream;
+    int64_t n_unif_stream;
 } QuiltGibbsArgs;
 
 typedef struct QuiltGibbsOut {
@@ -152,6 +171,11 @@ typedef struct QuiltGibbsOut {
     double* c[3];                /* each [nGrids]                                            */
     double* eMatRead_t;          /* [K x nReads]                                             */
     int32_t* read_category;      /* [nReads]                                                 */
+    int32_t* H_sample_its;       /* optional [nReads x n_gibbs_sample_its]: the labels after each sampling sweep — the reference's
+                                    double_list_of_ending_read_labels[[1]][[i]] (gibbs-nipt.cpp:3104); column n_sample_its - 1 == H */
+    /* filled by every call */
+    int64_t n_unif_consumed;     /* values of unif_stream the reference would have drawn (0 without unif_stream) */
+    int32_t underflow_iteration; /* 0-based sweep whose underflow check failed (gibbs-nipt.cpp:2959-2969), -1 if none */
 } QuiltGibbsOut;
 
 /* ------------------------------------------------------------------ GPU library (libquiltgpu.so) */
@@ -190,15 +214,6 @@ int         quilt_gpu_set_device(int32_t device);
 const char* quilt_gpu_last_error(void);
 int64_t     quilt_gpu_kernel_launches(void);   /* cumulative count of this library's kernel launches */
 void        quilt_gpu_release_panel_cache(void);
-
-/* ------------------------------------------------------------------ CPU oracle (oracle/libquiltoracle.so)
- * Test infrastructure only: a statement-order restatement of the reference C++.  Same structs. */
-int quilt_oracle_gibbs(const QuiltGibbsArgs* args, QuiltGibbsOut* out);
-int quilt_oracle_make_eMatRead_t(const QuiltGibbsArgs* args, double* eMatRead_t, int32_t* read_category);
-int quilt_oracle_unpack_panel(const QuiltPanel* panel, int32_t K, const int32_t* which_haps_to_use,
-                              int32_t all_snps, uint32_t* words);
-int quilt_oracle_forward_backward(int32_t K, int32_t nGrids, const double* eMatGrid_t, const double* transMatRate_tc_H,
-                                  double* alphaHat_t, double* betaHat_t, double* c);
 
 #ifdef __cplusplus
 }

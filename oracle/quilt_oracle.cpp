@@ -5,16 +5,18 @@
 // __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
 // may load this library; the product path (quilt_b200/csrc) never does.
 //
-// PARITY STATUS: "parity unpinned" at the level of reference-generated vectors —
-// the reference cannot be built in this image (every QUILT/src/*.cpp includes
-// <RcppArmadillo.h>; R, Rcpp and Armadillo are absent) and its test-suite holds
-// no golden vectors for this path (all unit tests are R-mirror == Rcpp
-// differentials).  What pins this file instead: the reference tests' own
-// invariants re-expressed in tests/test_oracle_invariants.py (sparse category
-// 2/3 update == dense update; incremental forward == full forward; fast
-// backward == generic backward; compressed-panel emissions == inflated-panel
-// emissions; compressed genProbs == dense genProbs; in-place block/shard state
-// == from-scratch forward/backward).
+// PARITY STATUS: pinned to the reference ITSELF.  oracle/_ref/libquiltref.so is the
+// unmodified /root/reference/QUILT/src/{copied-from-stitch, gibbs-small, gibbs-nipt,
+// gibbs-nipt-block}.cpp compiled against the header-only RcppArmadillo stand-in of
+// oracle/refshim/; tests/test_ref_pins_oracle.py demands that this restatement and
+// that library agree BIT FOR BIT (labels, H_class, read categories, alpha / beta /
+// eMatGrid / c, hapProbs / genProbs, per-sweep likelihood table) on diploid and NIPT
+// calls, and the golden fixtures in tests/golden/ are the reference's outputs.  What
+// the stand-in cannot verify is real Armadillo's accumulation order (two interleaved
+// accumulators is what arrayops::accumulate / accu_proxy_linear do in non-fast-math
+// builds; stated below) — last-ulp differences there are inside the 1e-4 DS/GP
+// tolerance of north_star and do not reach the label decisions.  The reference
+// tests' own invariants are re-expressed in tests/test_oracle_invariants.py.
 //
 // Conventions that matter for bit-level agreement with the reference:
 //  * Armadillo evaluates element-wise expression templates one element at a
@@ -29,7 +31,7 @@
 //
 // Each function cites the reference file:line it follows.
 
-#include "../include/quilt_b200.h"
+#include "quilt_oracle.h"
 
 #include <algorithm>
 #include <cmath>
@@ -1474,13 +1476,15 @@ void sample_H_using_H_class(IVec& H_class, IVec& H, double ff, const double* run
 
 // ---------------------------------------------------------------- gibbs-nipt-block.cpp:1636-1967
 // block_approach = 6, consider_total_relabelling = false, resample_H_using_H_class = true (defaults, not overridden at gibbs-nipt.cpp:3025)
-void block_gibbs_resampler(State& S, const IVec& blocked_snps, const double* runif_block, const double* runif_H_class) {
+// returns the number of uniforms rcpp_sample_H_using_H_class consumed
+int block_gibbs_resampler(State& S, const IVec& blocked_snps, const double* runif_block, const double* runif_H_class) {
     const int K = S.K, nGrids = S.nGrids, nReads = S.nReads;
     const double ff = S.ff;
     const double prior = 1 / double(K);
     double log_prior_probs[3] = {std::log(0.5), std::log((1 - ff) / 2), std::log((ff / 2))};
     Considers C = make_gibbs_considers(blocked_snps, S.R.wif0, nReads, nGrids);
-    if (!C.ok) return;  // reference: out["..."] on an empty list would throw; unreachable for valid blocked_snps
+    if (!C.ok) return 0;  // reference: out["..."] on an empty list would throw; unreachable for valid blocked_snps
+    int n_used_H = 0;
     const int n_blocks = C.n_blocks;
     double logC_before[3] = {0, 0, 0};
     double logC_after[3];
@@ -1518,6 +1522,7 @@ void block_gibbs_resampler(State& S, const IVec& blocked_snps, const double* run
     if ((ff > 0) && true && true) {
         int n_used = 0;
         sample_H_using_H_class(S.H_class, S.H, ff, runif_H_class, n_used);
+        n_used_H = n_used;
         for (int h = 0; h < 3; h++) S.eMatGrid_t[h].fill(1);
         for (int h = 0; h < 3; h++) make_eMatGrid_t(S.eMatGrid_t[h], S.eMatRead_t, S.H, S.R, h + 1);
         for (int h = 0; h < 3; h++) {
@@ -1535,6 +1540,7 @@ void block_gibbs_resampler(State& S, const IVec& blocked_snps, const double* run
     for (int h = 0; h < S.nHaps; h++) run_backward_haploid(S.betaHat_t[h], S.c[h], S.eMatGrid_t[h], prior, S.tm);
     for (int h = 0; h < S.nHaps; h++)
         run_backward_haploid_QUILT_faster(S.betaHat_t[h], S.c[h], S.eMatGrid_t[h], S.tm, S.grid_has_read);
+    return n_used_H;
 }
 
 // ---------------------------------------------------------------- gibbs-nipt-block.cpp:1975-2355 (ff == 0 branch; shard is diploid-only, functions.R:2552-2556)
@@ -1856,6 +1862,12 @@ int quilt_oracle_gibbs(const QuiltGibbsArgs* a, QuiltGibbsOut* o) {
     const bool shard_check_every_pair = (a->flags & QUILT_F_SHARD_CHECK_EVERY_PAIR) != 0;
     const bool rare_common = (a->flags & QUILT_F_MAKE_EMATREAD_RARE_COMMON) != 0;
     o->underflow_problem = 0;
+    o->underflow_iteration = -1;
+    o->n_unif_consumed = 0;
+    // episode stream (include/quilt_b200.h): R's unif_rand() stream after the call's first two draws, consumed in the
+    // reference's order; pos counts what the reference would have drawn
+    const double* stream = a->unif_stream;
+    int64_t pos = 0;
 
     Mat genProbsM_t(3, nSNPsLocal), genProbsF_t(3, nSNPsLocal), hapProbs_t(3, nSNPsLocal);
     Mat genProbsM_t_local(3, nSNPsLocal), genProbsF_t_local(3, nSNPsLocal), hapProbs_t_local(3, nSNPsLocal);
@@ -1897,6 +1909,8 @@ int quilt_oracle_gibbs(const QuiltGibbsArgs* a, QuiltGibbsOut* o) {
             if ((a->ff == 0) & (q == 2)) check = is_finite_d(accu2(S.c[2].data(), nGrids));
             if (!check) {
                 o->underflow_problem = 1;
+                o->underflow_iteration = iteration;
+                o->n_unif_consumed = pos;
                 return QUILT_OK;
             }
         }
@@ -1909,12 +1923,30 @@ int quilt_oracle_gibbs(const QuiltGibbsArgs* a, QuiltGibbsOut* o) {
             IVec blocked_snps = define_blocked_snps_using_gamma_on_the_fly(
                 S, nSNPsLocal, a->smooth_cm, a->shuffle_bin_radius, a->L_grid, a->block_gibbs_quantile_prob,
                 (a->flags & QUILT_F_USE_SMOOTH_CM_IN_BLOCK_GIBBS) != 0);
-            const double* rb = a->runif_block + (size_t)episode * nReads;
-            const double* rh = a->runif_H_class ? a->runif_H_class + (size_t)episode * nReads : nullptr;
+            const double* rb;
+            const double* rh;
+            if (stream) {
+                // six runif(nReads) rows (runif_proposed), runif_block, runif_total (gibbs-nipt.cpp:3013-3018)
+                if (pos + 8 * (int64_t)nReads + (S.ff > 0 ? nReads : 0) > a->n_unif_stream) return QUILT_ERR_BAD_ARG;
+                rb = stream + pos + 6 * (int64_t)nReads;
+                pos += 8 * (int64_t)nReads;
+                rh = stream + pos;
+            } else {
+                rb = a->runif_block + (size_t)episode * nReads;
+                rh = a->runif_H_class ? a->runif_H_class + (size_t)episode * nReads : nullptr;
+            }
             if (S.ff > 0 && !rh) return QUILT_ERR_BAD_ARG;
-            block_gibbs_resampler(S, blocked_snps, rb, rh);
+            pos += block_gibbs_resampler(S, blocked_snps, rb, rh);
             if (do_shard_block_gibbs) {
-                const double* rs = a->runif_shard + (size_t)episode * (nGrids - 1);
+                const double* rs;
+                if (stream) {
+                    if (!shard_check_every_pair) return QUILT_ERR_UNSUPPORTED;  // runif(n_blocks - 1) with data-dependent n_blocks
+                    if (pos + (nGrids - 1) > a->n_unif_stream) return QUILT_ERR_BAD_ARG;
+                    rs = stream + pos;
+                    pos += nGrids - 1;  // block.cpp:2054 with n_blocks = nGrids (:2038-2040)
+                } else {
+                    rs = a->runif_shard + (size_t)episode * (nGrids - 1);
+                }
                 int rc = shard_block_gibbs_resampler(S, blocked_snps, shard_check_every_pair, rs);
                 if (rc != QUILT_OK) return rc;
             }
@@ -1941,6 +1973,9 @@ int quilt_oracle_gibbs(const QuiltGibbsArgs* a, QuiltGibbsOut* o) {
                     hapProbs_t.d[i] += relative_difference * hapProbs_t_local.d[i];
                 }
             }
+            // list_of_ending_read_labels.push_back(clone(H), "H") (gibbs-nipt.cpp:3104)
+            if (o->H_sample_its)
+                for (int r = 0; r < nReads; r++) o->H_sample_its[(size_t)i_result_it * nReads + r] = S.H[r];
             n_results_done++;
         }
     }
@@ -1981,6 +2016,7 @@ int quilt_oracle_gibbs(const QuiltGibbsArgs* a, QuiltGibbsOut* o) {
     if (o->read_category)
         for (int r = 0; r < nReads; r++) o->read_category[r] = S.read_category[r];
     (void)n_results_done;
+    o->n_unif_consumed = stream ? pos : 0;
     return QUILT_OK;
 }
 

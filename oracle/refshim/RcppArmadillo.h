@@ -746,6 +746,9 @@ struct RngSource {
     virtual int sample_int(int n) { return (int)(n * unif_rand() + 1); }   // Rcpp::sample(n, 1)(0), one-based
     virtual double unif_rand_for_weighted_sample() { return unif_rand(); } // the draw inside sample(x, 1, false, probs)
     virtual void set_seed(int) {}
+    // position of the stream (what saving / restoring .Random.seed does in real R); generators that support it override both
+    virtual long long save() { throw std::logic_error("refshim: this RngSource cannot save its state"); }
+    virtual void restore(long long) { throw std::logic_error("refshim: this RngSource cannot restore its state"); }
 };
 inline RngSource*& rng_slot() { static thread_local RngSource* p = nullptr; return p; }
 inline RngSource& rng() {
@@ -962,6 +965,7 @@ public:
     Vector(const T& size, const U& v) { attach(refshim::alloc(RTYPE, (size_t)size)); fill((stored_type)v); }
     template <class It, class = typename std::enable_if<std::is_pointer<It>::value>::type>
     Vector(It first, It last) { attach(refshim::alloc(RTYPE, (size_t)(last - first))); for (size_t i = 0; first != last; ++first, ++i) p[i] = (stored_type)*first; }
+    Vector(const std::vector<int>& v) { attach(refshim::alloc(RTYPE, v.size())); for (size_t i = 0; i < v.size(); ++i) p[i] = (stored_type)v[i]; }
     Vector(std::initializer_list<stored_type> il) { attach(refshim::alloc(RTYPE, il.size())); size_t i = 0; for (auto v : il) p[i++] = v; }
     Vector& operator=(const Vector& o) { sx = o.sx; p = o.p; return *this; }
     Vector& operator=(const SEXP& s) { attach(refshim::coerce(s, RTYPE)); return *this; }
@@ -1022,6 +1026,11 @@ public:
         sx->names = nm;
     }
     bool isNULL() const { return false; }
+    // attr("dim") / attr("names") read access (what the Rcpp shim needs)
+    std::vector<int> attr(const std::string& what) const {
+        if (what == "dim") return sx->dim;
+        throw exception("refshim Rcpp: attr('" + what + "') is not available");
+    }
     // sugar-ish element-wise assignment from an arma vector is not needed; names:
     void names_set(const std::vector<std::string>& nm) { sx->names = nm; }
 };
@@ -1468,6 +1477,16 @@ template <class eT> template <int RT> inline Row<eT>::Row(const Rcpp::Vector<RT>
 
 // R API bits the sources call directly
 inline double unif_rand() { return refshim::rng().unif_rand(); }
+inline int* INTEGER(const SEXP& s) { if (s->type != refshim::INTSXP && s->type != refshim::LGLSXP) throw std::logic_error("INTEGER() on a non-integer vector"); return (int*)s->data; }
+inline int* LOGICAL(const SEXP& s) { return (int*)s->data; }
+inline double* REAL(const SEXP& s) { if (s->type != refshim::REALSXP) throw std::logic_error("REAL() on a non-double vector"); return (double*)s->data; }
+inline unsigned char* RAW(const SEXP& s) { if (s->type != refshim::RAWSXP) throw std::logic_error("RAW() on a non-raw vector"); return (unsigned char*)s->data; }
+inline bool Rf_isNull(const SEXP& s) { return refshim::is_nil(s); }
+inline int Rf_length(const SEXP& s) { return refshim::is_nil(s) ? 0 : (int)s->n; }
+#define RcppExport extern "C"
+// BEGIN_RCPP / END_RCPP: real Rcpp turns C++ exceptions into R errors; here they propagate to the test as C++ exceptions
+#define BEGIN_RCPP try {
+#define END_RCPP   } catch (...) { throw; }
 inline void R_CheckUserInterrupt() {}
 #ifndef R_NaN
 #define R_NaN (std::numeric_limits<double>::quiet_NaN())

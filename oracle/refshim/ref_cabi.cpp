@@ -20,7 +20,7 @@
 #include <deque>
 #include <mutex>
 
-#include "../../include/quilt_b200.h"
+#include "marshal.h"
 
 // ---- declarations of the reference functions called below (the definitions live in the reference sources)
 Rcpp::List rcpp_forwardBackwardGibbsNIPT(
@@ -67,6 +67,8 @@ void rcpp_initialize_gibbs_forward_backward(const arma::cube& alphaMatCurrent_tc
 Rcpp::IntegerVector rcpp_int_expand(arma::ivec& hapc, const int nSNPs);
 int rcpp_simple_binary_matrix_search(int val, Rcpp::IntegerMatrix mat, int s1, int e1);
 
+using namespace refmarshal;
+
 namespace {
 
 thread_local std::string g_err;
@@ -77,7 +79,7 @@ thread_local std::string g_err;
 // Rcpp::sample(x, 1, false, probs) draws and are closed by the next request of another kind.
 class ScriptedRng : public refshim::RngSource {
 public:
-    enum Kind { RUNIF, RUNIF_DUMMY, SAMPLE_INT, WEIGHTED };
+    enum Kind { RUNIF, RUNIF_DUMMY, SAMPLE_INT, WEIGHTED, STREAM };
     struct Seg { Kind kind; const double* p; long n; int value; long used; };
     std::deque<Seg> segs;
     long n_runif_calls = 0, n_weighted = 0;
@@ -86,11 +88,26 @@ public:
     void push_dummy(long n) { segs.push_back(Seg{RUNIF_DUMMY, nullptr, n, 0, 0}); }
     void push_sample_int(int one_based_value) { segs.push_back(Seg{SAMPLE_INT, nullptr, 1, one_based_value, 0}); }
     void push_weighted(const double* p, long n) { segs.push_back(Seg{WEIGHTED, p, n, 0, 0}); }
+    // a flat unif_rand() stream that answers every later request in whatever order the reference makes them
+    void push_stream(const double* p, long n) { segs.push_back(Seg{STREAM, p, n, 0, 0}); }
+    long stream_used() const { return (!segs.empty() && segs.front().kind == STREAM) ? segs.front().used : 0; }
+    double* stream_take(long n) {
+        Seg& s = segs.front();
+        if (s.used + n > s.n) throw std::logic_error("ScriptedRng: the episode stream is too short");
+        double* q = const_cast<double*>(s.p) + s.used;
+        s.used += n;
+        return q;
+    }
 
     void skip_weighted() { while (!segs.empty() && segs.front().kind == WEIGHTED) segs.pop_front(); }
     double unif_rand() override { throw std::logic_error("ScriptedRng: bare unif_rand() is not scripted"); }
     void runif(int n, double* out) override {
         skip_weighted();
+        if (!segs.empty() && segs.front().kind == STREAM) {
+            std::memcpy(out, stream_take(n), sizeof(double) * (size_t)n);
+            ++n_runif_calls;
+            return;
+        }
         if (segs.empty()) throw std::logic_error("ScriptedRng: runif(" + std::to_string(n) + ") requested past the end of the script");
         Seg s = segs.front();
         segs.pop_front();
@@ -110,6 +127,7 @@ public:
         return s.value;
     }
     double unif_rand_for_weighted_sample() override {
+        if (!segs.empty() && segs.front().kind == STREAM) { ++n_weighted; return *stream_take(1); }
         if (segs.empty() || segs.front().kind != WEIGHTED) throw std::logic_error("ScriptedRng: weighted sample() does not match the scripted draw order");
         Seg& s = segs.front();
         if (s.used >= s.n) throw std::logic_error("ScriptedRng: more weighted sample() draws than scripted uniforms");
@@ -123,84 +141,6 @@ struct RngInstall {
     explicit RngInstall(refshim::RngSource* r) : prev(refshim::rng_slot()) { refshim::rng_slot() = r; }
     ~RngInstall() { refshim::rng_slot() = prev; }
 };
-
-// ------------------------------------------------------------------ marshalling helpers
-template <int RT, class T>
-Rcpp::Vector<RT> foreign_vector(const T* p, size_t n) {
-    return Rcpp::Vector<RT>(refshim::wrap_foreign(RT, const_cast<T*>(p), n));
-}
-template <int RT, class T>
-Rcpp::Matrix<RT> foreign_matrix(const T* p, int nr, int nc) {
-    SEXP s = refshim::wrap_foreign(RT, const_cast<T*>(p), (size_t)nr * nc);
-    s->dim = {nr, nc};
-    return Rcpp::Matrix<RT>(s);
-}
-
-// sampleReads as the R list of list(J, wif, bq, u) (test-drivers.R:222-227; bq / u are one-column integer matrices)
-Rcpp::List make_sampleReads(const QuiltReads& r) {
-    Rcpp::List out(r.nReads);
-    for (int i = 0; i < r.nReads; ++i) {
-        const int a = r.offsets[i], n = r.offsets[i + 1] - a;
-        Rcpp::IntegerMatrix bq(n, 1), u(n, 1);
-        for (int j = 0; j < n; ++j) { bq(j, 0) = r.bq[a + j]; u(j, 0) = r.u[a + j]; }
-        out[i] = Rcpp::List::create(n - 1, (int)r.wif0[i], bq, u);
-    }
-    return out;
-}
-
-struct PanelObjects {
-    arma::imat hapMatcher;
-    Rcpp::RawMatrix hapMatcherR;
-    arma::imat distinctHapsB;
-    arma::mat distinctHapsIE;
-    Rcpp::IntegerMatrix special_helper, special_matrix;
-    arma::imat rhb_t;
-    Rcpp::List rare_per_hap_info, rare_per_snp_info;
-    Rcpp::IntegerVector common_snp_index;
-    Rcpp::LogicalVector snp_is_common;
-    PanelObjects(const QuiltPanel* p, bool rare_common, int K, const int32_t* which)
-        : hapMatcher(1, 1),
-          hapMatcherR(foreign_matrix<Rcpp::RAWSXP>(p->hapMatcherR, p->K_full, p->nGrids)),
-          distinctHapsB(const_cast<int*>(p->distinctHapsB), (arma::uword)p->nMaxDH, (arma::uword)p->nGrids, false, true),
-          distinctHapsIE(const_cast<double*>(p->distinctHapsIE), (arma::uword)p->nMaxDH, (arma::uword)p->nSNPs, false, true),
-          special_helper(foreign_matrix<Rcpp::INTSXP>(p->eMatDH_special_matrix_helper, p->nGrids, 2)),
-          special_matrix(foreign_matrix<Rcpp::INTSXP>(p->eMatDH_special_matrix, p->n_special, 2)),
-          rhb_t(1, 1) {
-        if (rare_common) {
-            // rare_per_hap_info: list[K_full] of 1-based all-SNP indices; rare_per_snp_info: list[nSNPs_all] of
-            // c(-1, k...) with k 1-based WITHIN which_haps_to_use, appended in k order (rare_common.R:313-322)
-            rare_per_hap_info = Rcpp::List(p->K_full);
-            for (int h = 0; h < p->K_full; ++h) {
-                const int64_t a = p->rare_hap_offsets[h], b = p->rare_hap_offsets[h + 1];
-                Rcpp::IntegerVector v((int)(b - a));
-                for (int64_t j = a; j < b; ++j) v[j - a] = p->rare_hap_snps[j];
-                rare_per_hap_info[h] = v;
-            }
-            std::vector<std::vector<int> > per_snp((size_t)p->nSNPs_all, std::vector<int>(1, -1));
-            for (int k = 0; k < K; ++k) {
-                const int h = which[k] - 1;
-                for (int64_t j = p->rare_hap_offsets[h]; j < p->rare_hap_offsets[h + 1]; ++j) per_snp[(size_t)p->rare_hap_snps[j] - 1].push_back(k + 1);
-            }
-            rare_per_snp_info = Rcpp::List(p->nSNPs_all);
-            for (int s = 0; s < p->nSNPs_all; ++s) rare_per_snp_info[s] = Rcpp::wrap(per_snp[(size_t)s]);
-            common_snp_index = foreign_vector<Rcpp::INTSXP>(p->common_snp_index, (size_t)p->nSNPs_all);
-            snp_is_common = Rcpp::LogicalVector(p->nSNPs_all);
-            for (int s = 0; s < p->nSNPs_all; ++s) snp_is_common[s] = p->snp_is_common[s] ? 1 : 0;
-        } else {
-            // the reference's default arguments (gibbs-nipt.cpp:2455-2458)
-            rare_per_hap_info = Rcpp::List::create(0);
-            rare_per_snp_info = Rcpp::List::create(0);
-            common_snp_index = Rcpp::IntegerVector::create(0);
-            snp_is_common = Rcpp::LogicalVector::create(0);
-        }
-    }
-};
-
-Rcpp::IntegerVector make_grid(int nSNPs) {   // "grid32": SNP -> grid (quilt-prepare-reference.R:376-380)
-    Rcpp::IntegerVector g(nSNPs);
-    for (int i = 0; i < nSNPs; ++i) g[i] = i / 32;
-    return g;
-}
 
 template <class F>
 int guarded(F f) {
@@ -233,65 +173,15 @@ int quilt_ref_gibbs(const QuiltGibbsArgs* a, QuiltGibbsOut* o) {
         const bool return_extra = (a->flags & QUILT_F_RETURN_EXTRA) != 0;
         const int n_full = a->n_gibbs_burn_in_its + a->n_gibbs_sample_its;
 
-        Rcpp::List sampleReads = make_sampleReads(a->reads);
-        PanelObjects P(a->panel, rare_common, K, a->which_haps_to_use);
-
-        // scratch owned by R in production (quilt.R:729-762); hap 3 is 1 x 1 for diploid methods
-        arma::mat eMatRead_t = rare_common ? arma::mat(K, nReads, arma::fill::ones) : arma::mat(1, 1);   // rare_common.R:260, functions.R:2545-2550
-        arma::mat priorCurrent_m(K, 1);
-        priorCurrent_m.fill(1 / double(K));
-        arma::cube alphaMatCurrent_tc(K, nGrids - 1, 1);
-        alphaMatCurrent_tc.fill(1 / double(K));
-        arma::cube eHapsCurrent_tc(1, 1, 1);
-        arma::cube transMatRate_tc_H(const_cast<double*>(a->transMatRate_tc_H), 2, nGrids - 1, 1, true);
-        arma::mat blocks_for_output(1, 1);
-        const int k3 = diploid ? 1 : K, g3 = diploid ? 1 : nGrids;
-        arma::mat alphaHat_t1(K, nGrids), betaHat_t1(K, nGrids), eMatGrid_t1(K, nGrids);
-        arma::mat alphaHat_t2(K, nGrids), betaHat_t2(K, nGrids), eMatGrid_t2(K, nGrids);
-        arma::mat alphaHat_t3(k3, g3), betaHat_t3(k3, g3), eMatGrid_t3(k3, g3);
-        arma::mat gammaMT_t_local(1, 1), gammaMU_t_local(1, 1), gammaP_t_local(1, 1);
-        arma::cube hapSum_tc(1, 1, 1);
-
-        Rcpp::IntegerVector which_haps_to_use = foreign_vector<Rcpp::INTSXP>(a->which_haps_to_use, (size_t)K);
-        Rcpp::IntegerVector wif0 = foreign_vector<Rcpp::INTSXP>(a->reads.wif0, (size_t)nReads);
-        Rcpp::LogicalVector grid_has_read(nGrids);   // functions.R:314-316
-        for (int r = 0; r < nReads; ++r) grid_has_read[a->reads.wif0[r]] = 1;
-        Rcpp::IntegerVector L_grid = foreign_vector<Rcpp::INTSXP>(a->L_grid, (size_t)nGrids);
-        Rcpp::NumericVector smooth_cm = foreign_vector<Rcpp::REALSXP>(a->smooth_cm, (size_t)(nGrids - 1));
-        Rcpp::LogicalVector skip_read_iteration(n_full);
-        Rcpp::IntegerVector grid = make_grid(nSNPs);
-
-        using Rcpp::Named;
-        Rcpp::List param_list = Rcpp::List::create(   // functions.R:2566-2599
-            Named("return_alpha") = return_alpha, Named("return_extra") = return_extra, Named("return_genProbs") = true,
-            Named("return_gamma") = false, Named("return_hapProbs") = true, Named("return_p_store") = false,
-            Named("return_p1") = false, Named("return_gibbs_block_output") = false,
-            Named("return_advanced_gibbs_block_output") = false, Named("use_starting_read_labels") = true,
-            Named("verbose") = false, Named("run_fb_subset") = false, Named("haploid_gibbs_equal_weighting") = true,
-            Named("gibbs_initialize_iteratively") = (a->flags & QUILT_F_GIBBS_INITIALIZE_ITERATIVELY) != 0,
-            Named("gibbs_initialize_at_first_read") = false,
-            Named("use_smooth_cm_in_block_gibbs") = (a->flags & QUILT_F_USE_SMOOTH_CM_IN_BLOCK_GIBBS) != 0,
-            Named("use_small_eHapsCurrent_tc") = false, Named("sample_is_diploid") = diploid, Named("update_in_place") = false,
-            Named("do_shard_block_gibbs") = do_shard, Named("shard_check_every_pair") = shard_every_pair,
-            Named("force_reset_read_category_zero") = (a->flags & QUILT_F_FORCE_RESET_READ_CATEGORY_0) != 0,
-            Named("disable_read_category_usage") = (a->flags & QUILT_F_DISABLE_READ_CATEGORY_USAGE) != 0,
-            Named("calculate_gamma_on_the_fly") = true, Named("rescale_eMatRead_t") = (a->flags & QUILT_F_RESCALE_EMATREAD) != 0,
-            Named("pass_in_eMatRead_t") = rare_common, Named("make_eMatRead_t_rare_common") = rare_common,
-            Named("pass_in_alphaBeta") = true, Named("update_hapSum") = false,
-            Named("record_read_set") = (a->flags & QUILT_F_RECORD_READ_SET) != 0, Named("perform_block_gibbs") = perform_block_gibbs,
-            Named("use_eMatDH_special_symbols") = true);
-
-        Rcpp::IntegerVector H0(nReads);
-        for (int r = 0; r < nReads; ++r) H0[r] = a->H0[r];
-        Rcpp::List double_list_of_starting_read_labels = Rcpp::List::create(Rcpp::List::create(H0));
-        Rcpp::IntegerVector block_its(a->n_block_gibbs_iterations);
-        for (int i = 0; i < a->n_block_gibbs_iterations; ++i) block_its[i] = a->block_gibbs_iterations[i];
+        CallObjects C(a);
 
         // R's random stream in the reference's draw order (SURVEY.md section 8b "RNG")
         ScriptedRng rng;
         rng.push_runif(a->runif_reads, (long)nReads * n_full);                       // gibbs-nipt.cpp:2845
-        if (nReads > 0) rng.push_sample_int(a->first_read_for_gibbs_initialization + 1);   // :2848
-        if (perform_block_gibbs) {
+        if (nReads > 0 && !(a->flags & QUILT_F_GIBBS_INITIALIZE_AT_FIRST_READ)) rng.push_sample_int(a->first_read_for_gibbs_initialization + 1);   // :2848
+        if (a->unif_stream) {
+            rng.push_stream(a->unif_stream, (long)a->n_unif_stream);
+        } else if (perform_block_gibbs) {
             int episode = 0;
             for (int it = 0; it < n_full; ++it) {
                 bool hit = false;
@@ -312,21 +202,24 @@ int quilt_ref_gibbs(const QuiltGibbsArgs* a, QuiltGibbsOut* o) {
         RngInstall install(&rng);
 
         Rcpp::List out = rcpp_forwardBackwardGibbsNIPT(
-            sampleReads, eMatRead_t, priorCurrent_m, alphaMatCurrent_tc, eHapsCurrent_tc, transMatRate_tc_H, a->ff, blocks_for_output,
-            alphaHat_t1, betaHat_t1, alphaHat_t2, betaHat_t2, alphaHat_t3, betaHat_t3, eMatGrid_t1, eMatGrid_t2, eMatGrid_t3,
-            gammaMT_t_local, gammaMU_t_local, gammaP_t_local, hapSum_tc, P.hapMatcher, P.hapMatcherR, true, P.distinctHapsB,
-            P.distinctHapsIE, P.special_helper, P.special_matrix, P.rhb_t, a->panel->ref_error, which_haps_to_use, wif0, grid_has_read,
-            L_grid, smooth_cm, param_list, skip_read_iteration, a->Jmax, a->maxDifferenceBetweenReads, 1e10 /*maxEmissionMatrixDifference*/,
-            0 /*run_fb_grid_offset*/, grid, -1, -1, false /*generate_fb_snp_offsets*/, 1 /*suppressOutput*/, 1 /*n_gibbs_starts*/,
-            a->n_gibbs_sample_its, a->n_gibbs_burn_in_its, double_list_of_starting_read_labels, Rcpp::IntegerVector::create(0) /*seed_vector*/,
+            C.sampleReads, C.eMatRead_t, C.priorCurrent_m, C.alphaMatCurrent_tc, C.eHapsCurrent_tc, C.transMatRate_tc_H, a->ff, C.blocks_for_output,
+            C.alphaHat_t1, C.betaHat_t1, C.alphaHat_t2, C.betaHat_t2, C.alphaHat_t3, C.betaHat_t3, C.eMatGrid_t1, C.eMatGrid_t2, C.eMatGrid_t3,
+            C.gammaMT_t_local, C.gammaMU_t_local, C.gammaP_t_local, C.hapSum_tc, C.P.hapMatcher, C.P.hapMatcherR, true, C.P.distinctHapsB,
+            C.P.distinctHapsIE, C.P.special_helper, C.P.special_matrix, C.P.rhb_t, a->panel->ref_error, C.which_haps_to_use, C.wif0, C.grid_has_read,
+            C.L_grid, C.smooth_cm, C.param_list, C.skip_read_iteration, a->Jmax, a->maxDifferenceBetweenReads, 1e10 /*maxEmissionMatrixDifference*/,
+            0 /*run_fb_grid_offset*/, C.grid, -1, -1, false /*generate_fb_snp_offsets*/, 1 /*suppressOutput*/, 1 /*n_gibbs_starts*/,
+            a->n_gibbs_sample_its, a->n_gibbs_burn_in_its, C.double_list_of_starting_read_labels, Rcpp::IntegerVector::create(0) /*seed_vector*/,
             Rcpp::List::create(1, 2) /*prev_list_of_alphaBetaBlocks*/, -1, false /*do_block_resampling*/, -1 /*artificial_relabel*/,
-            a->class_sum_cutoff, a->shuffle_bin_radius, block_its, a->block_gibbs_quantile_prob, P.rare_per_hap_info, P.common_snp_index,
-            P.snp_is_common, P.rare_per_snp_info);
+            a->class_sum_cutoff, a->shuffle_bin_radius, C.block_its, a->block_gibbs_quantile_prob, C.P.rare_per_hap_info, C.P.common_snp_index,
+            C.P.snp_is_common, C.P.rare_per_snp_info);
 
         o->underflow_problem = Rcpp::as<bool>(out["underflow_problem"]) ? 1 : 0;
+        o->n_unif_consumed = a->unif_stream ? rng.stream_used() : 0;
+        o->underflow_iteration = o->underflow_problem ? -2 /* the reference does not say which sweep */ : -1;
         if (o->underflow_problem) return QUILT_OK;   // list(underflow_problem = TRUE) early return, gibbs-nipt.cpp:2963-2966
         rng.skip_weighted();
-        if (!rng.segs.empty()) throw std::logic_error("quilt_ref_gibbs: the reference consumed fewer random draws than scripted");
+        if (!rng.segs.empty() && rng.segs.front().kind != ScriptedRng::STREAM)
+            throw std::logic_error("quilt_ref_gibbs: the reference consumed fewer random draws than scripted");
 
         auto copy_mat = [&](const char* name, double* dst, size_t n) {
             if (!dst) return;
@@ -341,6 +234,15 @@ int quilt_ref_gibbs(const QuiltGibbsArgs* a, QuiltGibbsOut* o) {
             Rcpp::IntegerVector H = Rcpp::as<Rcpp::IntegerVector>(out["H"]);
             for (int r = 0; r < nReads; ++r) o->H[r] = H[r];
         }
+        if (o->H_sample_its && a->n_gibbs_sample_its > 0) {
+            // double_list_of_ending_read_labels[[1]][[i]]
+            Rcpp::List inner = Rcpp::as<Rcpp::List>(Rcpp::as<Rcpp::List>(out["double_list_of_ending_read_labels"])[0]);
+            if (inner.size() != a->n_gibbs_sample_its) throw std::logic_error("quilt_ref_gibbs: unexpected number of ending read label vectors");
+            for (int i = 0; i < a->n_gibbs_sample_its; ++i) {
+                Rcpp::IntegerVector Hi = Rcpp::as<Rcpp::IntegerVector>(inner[i]);
+                for (int r = 0; r < nReads; ++r) o->H_sample_its[(size_t)i * nReads + r] = Hi[r];
+            }
+        }
         if (o->H_class && (a->flags & QUILT_F_RECORD_READ_SET)) {
             Rcpp::IntegerVector Hc = Rcpp::as<Rcpp::IntegerVector>(out["H_class"]);
             for (int r = 0; r < nReads; ++r) o->H_class[r] = Hc[r];
@@ -350,9 +252,9 @@ int quilt_ref_gibbs(const QuiltGibbsArgs* a, QuiltGibbsOut* o) {
             std::memcpy(o->per_it_likelihoods, m.begin(), sizeof(double) * (size_t)m.size());
         }
         if (return_alpha) {
-            arma::mat* al[3] = {&alphaHat_t1, &alphaHat_t2, &alphaHat_t3};
-            arma::mat* be[3] = {&betaHat_t1, &betaHat_t2, &betaHat_t3};
-            arma::mat* eg[3] = {&eMatGrid_t1, &eMatGrid_t2, &eMatGrid_t3};
+            arma::mat* al[3] = {&C.alphaHat_t1, &C.alphaHat_t2, &C.alphaHat_t3};
+            arma::mat* be[3] = {&C.betaHat_t1, &C.betaHat_t2, &C.betaHat_t3};
+            arma::mat* eg[3] = {&C.eMatGrid_t1, &C.eMatGrid_t2, &C.eMatGrid_t3};
             const char* cn[3] = {"c1", "c2", "c3"};
             for (int h = 0; h < (diploid ? 2 : 3); ++h) {
                 if (o->alphaHat_t[h]) std::memcpy(o->alphaHat_t[h], al[h]->memptr(), sizeof(double) * (size_t)K * nGrids);

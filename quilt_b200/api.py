@@ -20,7 +20,8 @@ from . import cabi
 from .cabi import GibbsCall, GibbsResult, Panel, Reads
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libquiltgpu.so")
+# QUILT_B200_LIB: experiment builds only (tools/build_variant.py); the product library is libquiltgpu.so next to this file
+SO_PATH = os.environ.get("QUILT_B200_LIB") or os.path.join(_HERE, "libquiltgpu.so")
 
 
 class QuiltGpuError(RuntimeError):
@@ -108,6 +109,8 @@ class GpuLib(cabi._LibAPI):
         self._check(self.lib.quilt_gpu_gibbs_batch(len(calls), args, outs), "quilt_gpu_gibbs_batch")
         for i, r in enumerate(res):
             r.underflow_problem = bool(outs[i].underflow_problem)
+            r.n_unif_consumed = int(outs[i].n_unif_consumed)
+            r.underflow_iteration = int(outs[i].underflow_iteration)
         return res
 
 
@@ -147,6 +150,8 @@ class Batch:
         self.lib._check(self.lib.lib.quilt_gpu_batch_fetch(self._h, outs), "quilt_gpu_batch_fetch")
         for i, r in enumerate(res):
             r.underflow_problem = bool(outs[i].underflow_problem)
+            r.n_unif_consumed = int(outs[i].n_unif_consumed)
+            r.underflow_iteration = int(outs[i].underflow_iteration)
         return res
 
     def free(self):

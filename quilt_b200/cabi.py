@@ -27,6 +27,7 @@ F_RECORD_READ_SET = 1 << 9
 F_USE_SMOOTH_CM_IN_BLOCK_GIBBS = 1 << 10
 F_RETURN_ALPHA = 1 << 11
 F_RETURN_EXTRA = 1 << 12
+F_GIBBS_INITIALIZE_AT_FIRST_READ = 1 << 13
 
 FLAGS_QUILT2_DIPLOID = (
     F_SAMPLE_IS_DIPLOID
@@ -106,6 +107,8 @@ class QuiltGibbsArgs(C.Structure):
         ("shuffle_bin_radius", C.c_int32),
         ("block_gibbs_quantile_prob", C.c_double),
         ("flags", C.c_uint32),
+        ("unif_stream", _pd),
+        ("n_unif_stream", C.c_int64),
     ]
 
 
@@ -124,6 +127,9 @@ class QuiltGibbsOut(C.Structure):
         ("c", _pd * 3),
         ("eMatRead_t", _pd),
         ("read_category", _pi),
+        ("H_sample_its", _pi),
+        ("n_unif_consumed", C.c_int64),
+        ("underflow_iteration", C.c_int32),
     ]
 
 
@@ -254,6 +260,7 @@ class GibbsCall:
     runif_block: np.ndarray
     runif_shard: np.ndarray
     runif_H_class: Optional[np.ndarray] = None
+    unif_stream: Optional[np.ndarray] = None  # episode stream: replaces runif_block / runif_shard / runif_H_class (quilt_b200.h)
     ff: float = 0.0
     n_gibbs_burn_in_its: int = 20
     n_gibbs_sample_its: int = 1
@@ -286,6 +293,8 @@ class GibbsCall:
         self.runif_shard = np.ascontiguousarray(self.runif_shard, dtype=np.float64)
         if self.runif_H_class is not None:
             self.runif_H_class = np.ascontiguousarray(self.runif_H_class, dtype=np.float64)
+        if self.unif_stream is not None:
+            self.unif_stream = np.ascontiguousarray(self.unif_stream, dtype=np.float64)
         bgi = np.ascontiguousarray(np.asarray(self.block_gibbs_iterations, dtype=np.int32))
         self._keep = [bgi]
         a.panel = C.pointer(self.panel.c_struct())
@@ -308,6 +317,8 @@ class GibbsCall:
         a.runif_block = _ptr(self.runif_block, _pd)
         a.runif_shard = _ptr(self.runif_shard, _pd)
         a.runif_H_class = _ptr(self.runif_H_class, _pd)
+        a.unif_stream = _ptr(self.unif_stream, _pd)
+        a.n_unif_stream = 0 if self.unif_stream is None else int(self.unif_stream.shape[0])
         a.maxDifferenceBetweenReads = self.maxDifferenceBetweenReads
         a.Jmax = self.Jmax
         a.class_sum_cutoff = self.class_sum_cutoff
@@ -333,9 +344,14 @@ class GibbsResult:
     c: Optional[List[np.ndarray]] = None
     eMatRead_t: Optional[np.ndarray] = None
     read_category: Optional[np.ndarray] = None
+    H_sample_its: Optional[np.ndarray] = None  # [nReads, n_gibbs_sample_its] labels after each sampling sweep
+    n_unif_consumed: int = 0
+    underflow_iteration: int = -1
 
     @property
     def double_list_of_ending_read_labels(self):
+        if self.H_sample_its is not None:
+            return [[self.H_sample_its[:, i] for i in range(self.H_sample_its.shape[1])]]
         return [[self.H]]
 
     @property
@@ -364,6 +380,9 @@ def alloc_out(call: GibbsCall, o: QuiltGibbsOut) -> GibbsResult:
     o.H_class = _ptr(res.H_class, _pi)
     o.per_it_likelihoods = _ptr(res.per_it_likelihoods, _pd)
     o.read_category = _ptr(res.read_category, _pi)
+    if call.n_gibbs_sample_its > 0:
+        res.H_sample_its = np.zeros((R, call.n_gibbs_sample_its), dtype=np.int32, order="F")
+        o.H_sample_its = _ptr(res.H_sample_its, _pi)
     if call.flags & F_RETURN_ALPHA:
         res.alphaHat_t = [np.zeros((K, T), order="F") for _ in range(nh)]
         res.betaHat_t = [np.zeros((K, T), order="F") for _ in range(nh)]
@@ -407,6 +426,8 @@ class _LibAPI:
         if rc != OK:
             raise RuntimeError(f"{self.prefix}_gibbs failed with status {rc}: {self.last_error()}")
         res.underflow_problem = bool(o.underflow_problem)
+        res.n_unif_consumed = int(o.n_unif_consumed)
+        res.underflow_iteration = int(o.underflow_iteration)
         return res
 
     def make_eMatRead_t(self, call: GibbsCall):

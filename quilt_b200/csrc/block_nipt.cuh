@@ -377,7 +377,9 @@ __global__ void __launch_bounds__(NT) k_block_nipt(BatchParams P, const JobDev* 
     B.carve(J.blk, T);
     const double prior = P.one_over_K, one_over_K = P.one_over_K;
     const size_t hs = (size_t)T * Kp;
-    const double* __restrict__ runif_block = J.runif_block + (size_t)episode * R;
+    // episode-stream mode: six unused runif(R) rows precede runif_block at the episode's stream position (gibbs-nipt.cpp:3013-3018)
+    const double* __restrict__ runif_block =
+        J.ep_stream ? J.runif_block + (size_t)ld_cg(J.lik + LIK_EP_POS) + 6 * (size_t)R : J.runif_block + (size_t)episode * R;
     const int n_blocks = B.n_blocks[0];
     // ---- scalar state of thread 0 (the reference's logC_before / logC_after)
     double logC_before[3] = {0, 0, 0}, logC_after[3] = {0, 0, 0};
@@ -662,7 +664,9 @@ __global__ void __launch_bounds__(256) k_sample_H(BatchParams P, const JobDev* _
     if (*J.underflow) return;
     const int R = J.R, tid = threadIdx.x;
     const double ff = P.ff;
-    const double* __restrict__ ru = J.runif_H_class + (size_t)episode * R;
+    // episode-stream mode: the H_class draws follow the episode's 8 R block-Gibbs uniforms; the position then moves past them
+    const size_t ep_pos = J.ep_stream ? (size_t)ld_cg(J.lik + LIK_EP_POS) : 0;
+    const double* __restrict__ ru = J.ep_stream ? J.runif_block + ep_pos + 8 * (size_t)R : J.runif_H_class + (size_t)episode * R;
     const int per = (R + 255) / 256;
     const int a = min(tid * per, R), b = min(a + per, R);
     int n = 0;
@@ -696,6 +700,7 @@ __global__ void __launch_bounds__(256) k_sample_H(BatchParams P, const JobDev* _
             v = hc;  // classes 1, 2, 3 are the label itself
         J.H[r] = v;
     }
+    if (J.ep_stream && tid == 0) J.lik[LIK_EP_POS] = (double)(ep_pos + 8 * (size_t)R + (size_t)s_cnt[256]);
 }
 
 // beta[:, T-1] = c[T-1], then Rcpp_run_backward_haploid_QUILT_faster (copied-from-stitch.cpp:417-440).  grid = (jobs, NH)

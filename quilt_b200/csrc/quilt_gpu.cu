@@ -177,20 +177,94 @@ void parallel_for(int n, F&& f) {
     for (auto& t : th) t.join();
 }
 
+// std::lgamma writes the global signgam: results are unpacked on several host threads, so use the re-entrant form
+inline double lgamma_ts(double x) {
+    int sign = 0;
+    return ::lgamma_r(x, &sign);
+}
+
 // ------------------------------------------------------------------------------------------------ panel cache
+// The device copy of a prepared reference is reused across calls.  It is identified by its CONTENT (shapes, ref_error
+// and a 64-bit hash of every array), never by host addresses: a caller may rebuild the flat arrays per call (the Rcpp
+// shim converts the rare/common lists into call-local vectors) or reuse freed addresses for a different panel.  At most
+// PANEL_CACHE_MAX panels stay resident (least recently used is dropped).
+constexpr size_t PANEL_CACHE_MAX = 4;
+constexpr size_t PANEL_HASH_FULL = (size_t)256 << 20;  // arrays up to 256 MiB are hashed completely, larger ones in 4 KiB strides
+struct PanelKey {
+    int32_t K_full, nGrids, nSNPs, nMaxDH, n_special, nSNPs_all;
+    double ref_error;
+    uint64_t h[8];
+    bool operator==(const PanelKey& o) const { return std::memcmp(this, &o, sizeof(PanelKey)) == 0; }
+};
 struct PanelEntry {
-    QuiltPanel key;
+    PanelKey key;
     PanelDev dev;
     DBuf buf;
+    uint64_t last_use = 0;
 };
-std::vector<std::unique_ptr<PanelEntry>> g_panels;
+std::vector<std::shared_ptr<PanelEntry>> g_panels;  // a staged batch holds a reference: eviction never frees a panel in use
+uint64_t g_panel_clock = 0;
 
-bool same_panel(const QuiltPanel& a, const QuiltPanel& b) {
+uint64_t hash_bytes(const void* p, size_t n) {
+    if (!p || n == 0) return 0x9e3779b97f4a7c15ull;
+    const unsigned char* b = (const unsigned char*)p;
+    auto mix = [](uint64_t h, uint64_t v) {
+        h ^= v;
+        h *= 0xff51afd7ed558ccdull;
+        h ^= h >> 32;
+        return h;
+    };
+    uint64_t h = 0xcbf29ce484222325ull ^ (uint64_t)n;
+    auto run = [&](size_t a, size_t e) {
+        size_t i = a;
+        for (; i + 8 <= e; i += 8) {
+            uint64_t v;
+            std::memcpy(&v, b + i, 8);
+            h = mix(h, v);
+        }
+        for (; i < e; i++) h = mix(h, b[i]);
+    };
+    if (n <= PANEL_HASH_FULL) {
+        run(0, n);
+    } else {
+        const size_t stride = 64 << 10;  // 4 KiB out of every 64 KiB, plus the tail
+        for (size_t a = 0; a < n; a += stride) run(a, std::min(n, a + 4096));
+        run(n - 4096, n);
+    }
+    return h;
+}
+
+// two argument structs of ONE batch describe the same host arrays (both are alive at the same time, so addresses are meaningful here)
+bool same_panel_struct(const QuiltPanel& a, const QuiltPanel& b) {
     return a.K_full == b.K_full && a.nGrids == b.nGrids && a.nSNPs == b.nSNPs && a.nMaxDH == b.nMaxDH && a.hapMatcherR == b.hapMatcherR &&
            a.distinctHapsB == b.distinctHapsB && a.distinctHapsIE == b.distinctHapsIE && a.eMatDH_special_matrix == b.eMatDH_special_matrix &&
            a.n_special == b.n_special && a.eMatDH_special_matrix_helper == b.eMatDH_special_matrix_helper && a.ref_error == b.ref_error &&
            a.nSNPs_all == b.nSNPs_all && a.snp_is_common == b.snp_is_common && a.common_snp_index == b.common_snp_index &&
            a.rare_hap_offsets == b.rare_hap_offsets && a.rare_hap_snps == b.rare_hap_snps;
+}
+
+PanelKey panel_key(const QuiltPanel* p) {
+    PanelKey k;
+    std::memset(&k, 0, sizeof(k));
+    k.K_full = p->K_full;
+    k.nGrids = p->nGrids;
+    k.nSNPs = p->nSNPs;
+    k.nMaxDH = p->nMaxDH;
+    k.n_special = p->n_special;
+    k.nSNPs_all = p->nSNPs_all;
+    k.ref_error = p->ref_error;
+    const void* ptr[8] = {p->hapMatcherR, p->distinctHapsB, p->distinctHapsIE, p->eMatDH_special_matrix, p->eMatDH_special_matrix_helper,
+                          p->snp_is_common, p->common_snp_index, p->rare_hap_offsets};
+    const size_t nrare = (p->nSNPs_all > 0 && p->rare_hap_offsets) ? (size_t)std::max<int64_t>(p->rare_hap_offsets[p->K_full], 0) : 0;
+    const size_t len[8] = {(size_t)p->K_full * p->nGrids, (size_t)p->nMaxDH * p->nGrids * 4, (size_t)p->nMaxDH * p->nSNPs * 8,
+                           (size_t)std::max(p->n_special, 0) * 8, (size_t)p->nGrids * 8, (size_t)std::max(p->nSNPs_all, 0),
+                           (size_t)std::max(p->nSNPs_all, 0) * 4, p->nSNPs_all > 0 ? (size_t)(p->K_full + 1) * 8 : 0};
+    std::vector<std::thread> th;
+    for (int i = 0; i < 8; i++) th.emplace_back([&, i]() { k.h[i] = hash_bytes(ptr[i], len[i]); });
+    const uint64_t hr = hash_bytes(p->rare_hap_snps, nrare * 4);
+    for (auto& t : th) t.join();
+    k.h[7] ^= hr * 0x2545f4914f6cdd1dull;
+    return k;
 }
 
 // The kernels derive a haplotype's emission at a SNP from its allele bit: (1 - eps) if set, eps otherwise.  The
@@ -218,20 +292,33 @@ int check_distinctHapsIE(const QuiltPanel* p) {
     return QUILT_OK;
 }
 
-int get_panel(const QuiltPanel* p, PanelDev* out) {
-    for (auto& e : g_panels)
-        if (same_panel(e->key, *p)) {
-            *out = e->dev;
-            return QUILT_OK;
-        }
+int get_panel(const QuiltPanel* p, PanelDev* out, std::shared_ptr<PanelEntry>* keep = nullptr) {
     if (p->K_full <= 0 || p->nGrids <= 0 || p->nSNPs <= 0 || p->nMaxDH <= 0 || p->nMaxDH > 255 || !p->hapMatcherR || !p->distinctHapsB ||
         !p->distinctHapsIE || !p->eMatDH_special_matrix_helper)
         return set_err(QUILT_ERR_BAD_ARG, "bad panel");
     if (p->nGrids != (p->nSNPs + 31) / 32) return set_err(QUILT_ERR_UNSUPPORTED, "panel grid must be 32 SNPs per grid");
+    if (p->nSNPs_all > 0 && (!p->snp_is_common || !p->common_snp_index || !p->rare_hap_offsets)) return set_err(QUILT_ERR_BAD_ARG, "bad rare/common panel fields");
+    const PanelKey key = panel_key(p);
+    for (auto& e : g_panels)
+        if (e->key == key) {
+            e->last_use = ++g_panel_clock;
+            *out = e->dev;
+            if (keep) *keep = e;
+            return QUILT_OK;
+        }
     int rc = check_distinctHapsIE(p);
     if (rc != QUILT_OK) return rc;
-    auto e = std::make_unique<PanelEntry>();
-    e->key = *p;
+    while (g_panels.size() >= PANEL_CACHE_MAX) {
+        // drop the least recently used panel from the cache; its device memory goes when the last staged batch using it does
+        size_t lru = 0;
+        for (size_t i = 1; i < g_panels.size(); i++)
+            if (g_panels[i]->last_use < g_panels[lru]->last_use) lru = i;
+        CK(cudaStreamSynchronize(g_stream));
+        g_panels.erase(g_panels.begin() + (long)lru);
+    }
+    auto e = std::make_shared<PanelEntry>();
+    e->key = key;
+    e->last_use = ++g_panel_clock;
     const size_t b_hm = al((size_t)p->K_full * p->nGrids), b_db = al((size_t)p->nMaxDH * p->nGrids * 4);
     const int nsp = std::max(p->n_special, 1);
     const size_t b_sp = al((size_t)nsp * 2 * 4), b_he = al((size_t)p->nGrids * 2 * 4);
@@ -289,6 +376,7 @@ int get_panel(const QuiltPanel* p, PanelDev* out) {
         d += b_rs;
     }
     *out = D;
+    if (keep) *keep = e;
     g_panels.push_back(std::move(e));
     return QUILT_OK;
 }
@@ -347,7 +435,7 @@ struct JobLayoutIn {  // byte offsets inside the job's input region
     size_t which, rs, roff, u, pRA, wif0, ts, ginfo, dense_reads, runif_reads, runif_shard, tm, desc, H0, runif_block, runif_H_class, L_grid, end;
 };
 struct JobLayoutOut {
-    size_t underflow, lik, hap, genM, genF, H, Hclass, cat, end;
+    size_t underflow, lik, hap, genM, genF, H, Hclass, cat, Hs, end;
 };
 
 struct HostJob {
@@ -386,6 +474,7 @@ struct QuiltGpuBatch {
     std::vector<HostJob> jobs;
     std::vector<std::unique_ptr<Bucket>> buckets;
     PanelDev panel;
+    std::shared_ptr<PanelEntry> panel_ref;
     std::unique_ptr<DBuf> din_, dout_, slots_;
     std::unique_ptr<HBuf> hin_, hout_;
     DBuf& din() const { return *din_; }
@@ -537,6 +626,20 @@ int prepare_job(HostJob& j) {
     return QUILT_OK;
 }
 
+// upper bound of the episode-stream values one call can consume (quilt_b200.h, QuiltGibbsArgs.unif_stream)
+size_t episode_stream_need(const QuiltGibbsArgs& a) {
+    const bool diploid = (a.flags & QUILT_F_SAMPLE_IS_DIPLOID) != 0;
+    const bool shard = (a.flags & QUILT_F_DO_SHARD_BLOCK_GIBBS) != 0;
+    if (!(a.flags & QUILT_F_PERFORM_BLOCK_GIBBS)) return 0;
+    const size_t R = (size_t)a.reads.nReads;
+    return (size_t)a.n_block_gibbs_iterations * (8 * R + (diploid ? 0 : R) + (shard ? (size_t)std::max(a.nGrids - 1, 0) : 0));
+}
+// stream position of episode e for a DIPLOID call (static: no data-dependent draws)
+size_t diploid_episode_base(const QuiltGibbsArgs& a, int e) {
+    const bool shard = (a.flags & QUILT_F_DO_SHARD_BLOCK_GIBBS) != 0;
+    return (size_t)e * (8 * (size_t)a.reads.nReads + (shard ? (size_t)std::max(a.nGrids - 1, 0) : 0));
+}
+
 void layout_in(HostJob& j) {
     const QuiltGibbsArgs& a = j.a;
     const int R = j.R, T = a.nGrids;
@@ -558,8 +661,11 @@ void layout_in(HostJob& j) {
     L.desc = o, o += al((size_t)R * sizeof(ReadDesc));
     L.H0 = o, o += al((size_t)R * 4);
     const bool nipt_block = !(a.flags & QUILT_F_SAMPLE_IS_DIPLOID) && (a.flags & QUILT_F_PERFORM_BLOCK_GIBBS) && j.n_ep > 0;
-    L.runif_block = o, o += al(nipt_block ? (size_t)j.n_ep * R * 8 : 0);
-    L.runif_H_class = o, o += al(nipt_block ? (size_t)j.n_ep * R * 8 : 0);
+    // episode-stream mode (quilt_b200.h): the three-haplotype kernels walk the caller's flat stream themselves (the
+    // number of H_class draws per episode is data-dependent); it travels in the runif_block slot
+    const size_t nipt_stream = (nipt_block && a.unif_stream) ? episode_stream_need(a) : 0;
+    L.runif_block = o, o += al(nipt_block ? (nipt_stream ? nipt_stream * 8 : (size_t)j.n_ep * R * 8) : 0);
+    L.runif_H_class = o, o += al((nipt_block && !nipt_stream) ? (size_t)j.n_ep * R * 8 : 0);
     L.L_grid = o, o += al(nipt_block ? (size_t)T * 4 : 0);
     L.end = o;
     JobLayoutOut& O = j.lo;
@@ -572,6 +678,8 @@ void layout_in(HostJob& j) {
     O.H = o, o += al((size_t)R * 4);
     O.Hclass = o, o += al((size_t)R * 4);
     O.cat = o, o += al((size_t)R * 4);
+    // labels after each sampling sweep (double_list_of_ending_read_labels); with one sampling sweep they are H itself
+    O.Hs = o, o += al(a.n_gibbs_sample_its > 1 ? (size_t)a.n_gibbs_sample_its * R * 4 : 0);
     O.end = o;
 }
 
@@ -618,14 +726,23 @@ void fill_in(const HostJob& j, char* base) {
     std::memcpy(base + L.ginfo, j.ginfo.data(), (size_t)(T + 1) * 16);
     if (j.n_dense) std::memcpy(base + L.dense_reads, j.dense_reads.data(), (size_t)j.n_dense * 4);
     if (j.n_its > 0) std::memcpy(base + L.runif_reads, a.runif_reads, (size_t)j.n_its * R * 8);
-    if (j.n_ep > 0 && T > 1 && a.runif_shard) std::memcpy(base + L.runif_shard, a.runif_shard, (size_t)j.n_ep * (T - 1) * 8);
+    if (j.n_ep > 0 && T > 1 && a.unif_stream && (a.flags & QUILT_F_SAMPLE_IS_DIPLOID) && (a.flags & QUILT_F_DO_SHARD_BLOCK_GIBBS)) {
+        // episode stream, diploid: the shard uniforms of episode e follow its 8 * nReads block-Gibbs uniforms
+        for (int e = 0; e < j.n_ep; e++)
+            std::memcpy(base + L.runif_shard + (size_t)e * (T - 1) * 8, a.unif_stream + diploid_episode_base(a, e) + 8 * (size_t)R, (size_t)(T - 1) * 8);
+    } else if (j.n_ep > 0 && T > 1 && a.runif_shard)
+        std::memcpy(base + L.runif_shard, a.runif_shard, (size_t)j.n_ep * (T - 1) * 8);
     if (T > 1) std::memcpy(base + L.tm, a.transMatRate_tc_H, (size_t)(T - 1) * 16);
     std::memcpy(base + L.desc, j.desc.data(), (size_t)R * sizeof(ReadDesc));
     std::memcpy(base + L.H0, a.H0, (size_t)R * 4);
     const bool nipt_block = !(a.flags & QUILT_F_SAMPLE_IS_DIPLOID) && (a.flags & QUILT_F_PERFORM_BLOCK_GIBBS) && j.n_ep > 0;
     if (nipt_block) {
-        std::memcpy(base + L.runif_block, a.runif_block, (size_t)j.n_ep * R * 8);
-        std::memcpy(base + L.runif_H_class, a.runif_H_class, (size_t)j.n_ep * R * 8);
+        if (a.unif_stream) {
+            std::memcpy(base + L.runif_block, a.unif_stream, episode_stream_need(a) * 8);
+        } else {
+            std::memcpy(base + L.runif_block, a.runif_block, (size_t)j.n_ep * R * 8);
+            std::memcpy(base + L.runif_H_class, a.runif_H_class, (size_t)j.n_ep * R * 8);
+        }
         std::memcpy(base + L.L_grid, a.L_grid, (size_t)T * 4);
     }
 }
@@ -641,6 +758,12 @@ BucketKey bucket_key(const QuiltGibbsArgs& a) {
 int validate(const QuiltGibbsArgs& a) {
     if (!a.panel) return set_err(QUILT_ERR_BAD_ARG, "panel is NULL");
     if (a.K <= 0 || a.nGrids <= 0 || a.nSNPs <= 0) return set_err(QUILT_ERR_BAD_ARG, "bad K / nGrids / nSNPs");
+    if (!a.which_haps_to_use || (!a.transMatRate_tc_H && a.nGrids > 1)) return set_err(QUILT_ERR_BAD_ARG, "which_haps_to_use / transMatRate_tc_H is NULL");
+    if (a.reads.nReads < 0 || (a.reads.nReads > 0 && (!a.reads.offsets || !a.reads.u || !a.reads.bq || !a.reads.wif0 || !a.H0)))
+        return set_err(QUILT_ERR_BAD_ARG, "reads / H0 arrays are NULL");
+    if (a.n_gibbs_burn_in_its + a.n_gibbs_sample_its > 0 && a.reads.nReads > 0 && !a.runif_reads) return set_err(QUILT_ERR_BAD_ARG, "runif_reads is NULL");
+    if (a.unif_stream && (size_t)std::max<int64_t>(a.n_unif_stream, 0) < episode_stream_need(a))
+        return set_err(QUILT_ERR_BAD_ARG, "unif_stream is shorter than n_episodes * (8 nReads [+ nReads] [+ nGrids - 1])");
     if (a.nGrids != (a.nSNPs + 31) / 32) return set_err(QUILT_ERR_UNSUPPORTED, "grid must be 32 SNPs per grid (grid32)");
     if (a.K > 8192) return set_err(QUILT_ERR_UNSUPPORTED, "Ksubset > 8192 not supported");
     const bool diploid = (a.flags & QUILT_F_SAMPLE_IS_DIPLOID) != 0;
@@ -649,8 +772,8 @@ int validate(const QuiltGibbsArgs& a) {
         if (a.ff < 0 || a.ff >= 1) return set_err(QUILT_ERR_BAD_ARG, "ff outside [0, 1)");
         if (a.K > 2048) return set_err(QUILT_ERR_UNSUPPORTED, "three-haplotype (NIPT) calls support Ksubset <= 2048");
         if ((a.flags & QUILT_F_PERFORM_BLOCK_GIBBS) && a.n_block_gibbs_iterations > 0) {
-            if (!a.runif_block || !a.runif_H_class || !a.L_grid)
-                return set_err(QUILT_ERR_BAD_ARG, "NIPT block Gibbs needs runif_block, runif_H_class and L_grid");
+            if ((!a.unif_stream && (!a.runif_block || !a.runif_H_class)) || !a.L_grid)
+                return set_err(QUILT_ERR_BAD_ARG, "NIPT block Gibbs needs L_grid and either unif_stream or runif_block + runif_H_class");
         }
         if (a.flags & QUILT_F_DO_SHARD_BLOCK_GIBBS) return set_err(QUILT_ERR_UNSUPPORTED, "shard pass is diploid-only (functions.R:2552-2556)");
     }
@@ -663,7 +786,7 @@ int validate(const QuiltGibbsArgs& a) {
     if ((a.flags & QUILT_F_PERFORM_BLOCK_GIBBS) && a.n_block_gibbs_iterations > 0) {
         if ((a.flags & QUILT_F_DO_SHARD_BLOCK_GIBBS) && !(a.flags & QUILT_F_SHARD_CHECK_EVERY_PAIR))
             return set_err(QUILT_ERR_UNSUPPORTED, "shard pass without shard_check_every_pair not supported yet");
-        if ((a.flags & QUILT_F_DO_SHARD_BLOCK_GIBBS) && !a.runif_shard) return set_err(QUILT_ERR_BAD_ARG, "runif_shard missing");
+        if ((a.flags & QUILT_F_DO_SHARD_BLOCK_GIBBS) && !a.runif_shard && !a.unif_stream) return set_err(QUILT_ERR_BAD_ARG, "runif_shard missing");
     }
     if (a.Jmax < 0) return set_err(QUILT_ERR_BAD_ARG, "Jmax < 0");
     for (int k = 0; k < a.K; k++)
@@ -809,7 +932,7 @@ void make_jobdev(const QuiltGpuBatch* B, const Bucket& bk, const HostJob& j, int
     const char* in = (const char*)B->din().p + j.in_off;
     char* out = (char*)B->dout().p + j.out_off;
     D->R = j.R;
-    D->first_read = j.a.first_read_for_gibbs_initialization;
+    D->first_read = (j.a.flags & QUILT_F_GIBBS_INITIALIZE_AT_FIRST_READ) ? 0 : j.a.first_read_for_gibbs_initialization;
     D->n_dense = j.n_dense;
     D->alpha = (double*)(s + bk.o_alpha);
     D->beta = (double*)(s + bk.o_beta);
@@ -839,6 +962,7 @@ void make_jobdev(const QuiltGpuBatch* B, const Bucket& bk, const HostJob& j, int
     D->H0 = (const int32_t*)(in + j.li.H0);
     D->runif_block = (const double*)(in + j.li.runif_block);
     D->runif_H_class = (const double*)(in + j.li.runif_H_class);
+    D->ep_stream = (j.a.unif_stream && !(j.a.flags & QUILT_F_SAMPLE_IS_DIPLOID)) ? 1 : 0;
     D->L_grid = (const int32_t*)(in + j.li.L_grid);
     D->blk = (unsigned char*)(s + bk.o_blk);
     D->H = (int32_t*)(out + j.lo.H);
@@ -849,6 +973,7 @@ void make_jobdev(const QuiltGpuBatch* B, const Bucket& bk, const HostJob& j, int
     D->genM = (double*)(out + j.lo.genM);
     D->genF = (double*)(out + j.lo.genF);
     D->cat_out = (int32_t*)(out + j.lo.cat);
+    D->Hs = (int32_t*)(out + j.lo.Hs);
 }
 
 // grid = (ceil(R_max / 256), jobs): labels start from H0; read_category export
@@ -856,6 +981,14 @@ __global__ void __launch_bounds__(256) k_copy_H(const JobDev* __restrict__ jobs)
     const JobDev& J = jobs[blockIdx.y];
     const int r = blockIdx.x * 256 + threadIdx.x;
     if (r < J.R) J.H[r] = J.H0[r];
+    if (r == 0) J.lik[LIK_EP_POS] = 0.0;  // episode-stream position of the three-haplotype kernels
+}
+// labels after sampling sweep i (list_of_ending_read_labels.push_back(clone(H)), gibbs-nipt.cpp:3104); only launched when
+// there is more than one sampling sweep
+__global__ void __launch_bounds__(256) k_snapshot_H(const JobDev* __restrict__ jobs, int i) {
+    const JobDev& J = jobs[blockIdx.y];
+    const int r = blockIdx.x * 256 + threadIdx.x;
+    if (r < J.R) J.Hs[(size_t)i * J.R + r] = J.H[r];
 }
 __global__ void __launch_bounds__(256) k_export_cat(const JobDev* __restrict__ jobs) {
     const JobDev& J = jobs[blockIdx.y];
@@ -1000,6 +1133,10 @@ int run_wave_t(QuiltGpuBatch* B, Bucket& bk, int n, const JobDev* dj, bool timed
         }
         if (it >= P.n_burn) {
             const int n_sample = P.n_its - P.n_burn;
+            if (n_sample > 1) {
+                k_snapshot_H<<<dim3((bk.R_max + 255) / 256, n), 256, 0, g_stream>>>(dj, it - P.n_burn);
+                LAUNCHED();
+            }
             if (P.NH == 2)
                 k_happrobs<2><<<dim3(P.T, n), 256, 0, g_stream>>>(P, dj, it == P.n_burn, it == P.n_its - 1, 1.0 / double(n_sample));
             else
@@ -1123,9 +1260,9 @@ void fill_lik_row(const QuiltGibbsArgs& a, const double* rec, int iteration, int
     at(9) = at(7) + dH;
     const double rc[3] = {rec[3], rec[4], rec[5]};
     const int n = (int)(rc[0] + rc[1] + rc[2]);
-    double r = std::lgamma(1.0 * (n + 1.0));
+    double r = lgamma_ts(1.0 * (n + 1.0));
     for (int i = 0; i < 3; i++)
-        if (prior[i] > 0) r += rc[i] * std::log(prior[i]) - std::lgamma(1.0 * (rc[i] + 1.0));
+        if (prior[i] > 0) r += rc[i] * std::log(prior[i]) - lgamma_ts(1.0 * (rc[i] + 1.0));
     at(10) = r;
     at(11) = 1;
     double lp = 0;
@@ -1187,11 +1324,11 @@ static int stage_impl(int32_t n, const QuiltGibbsArgs* args, QuiltGpuBatch** bat
     B->jobs.resize(n);
     for (int i = 0; i < n; i++) {
         if ((rc = validate(args[i])) != QUILT_OK) return rc;
-        if (args[i].panel != args[0].panel && !same_panel(*args[i].panel, *args[0].panel))
+        if (args[i].panel != args[0].panel && !same_panel_struct(*args[i].panel, *args[0].panel))
             return set_err(QUILT_ERR_UNSUPPORTED, "all calls of a batch must share one panel");
         B->jobs[i].a = args[i];
     }
-    if ((rc = get_panel(args[0].panel, &B->panel)) != QUILT_OK) return rc;
+    if ((rc = get_panel(args[0].panel, &B->panel, &B->panel_ref)) != QUILT_OK) return rc;
     std::map<BucketKey, int> index;
     size_t in_total = 0, out_total = 0;
     {
@@ -1301,6 +1438,7 @@ int quilt_gpu_batch_run(QuiltGpuBatch* B) {
 }
 
 int quilt_gpu_batch_sync(QuiltGpuBatch* B) {
+    std::lock_guard<std::mutex> lk(g_mu);
     if (!B) return set_err(QUILT_ERR_BAD_ARG, "null batch");
     CK(cudaStreamSynchronize(g_stream));
     if (B->ran) {
@@ -1319,6 +1457,7 @@ int quilt_gpu_batch_sync(QuiltGpuBatch* B) {
 }
 
 int quilt_gpu_batch_timing(QuiltGpuBatch* B, double* total_ms, double* sweep_ms, int32_t* n_sweep_launches) {
+    std::lock_guard<std::mutex> lk(g_mu);
     if (!B) return set_err(QUILT_ERR_BAD_ARG, "null batch");
     if (total_ms) *total_ms = B->total_ms;
     if (sweep_ms) *sweep_ms = B->sweep_ms;
@@ -1348,11 +1487,36 @@ static void unpack_job(const QuiltGpuBatch* B, int i, QuiltGibbsOut* out) {
     const char* base = (const char*)B->hout().p + j.out_off;
     const int under = *reinterpret_cast<const int32_t*>(base + j.lo.underflow);
     o.underflow_problem = under ? 1 : 0;
+    {
+        // first sweep whose underflow check failed (gibbs-nipt.cpp:2959-2969) and, in episode-stream mode, how many
+        // stream values the reference would have drawn: the episodes of earlier sweeps only
+        const double* lik = reinterpret_cast<const double*>(base + j.lo.lik);
+        int it_u = -1;
+        if (under)
+            for (int it = 0; it < j.n_its && it_u < 0; it++)
+                if (lik[(size_t)it * LIK_N + 14] != 0.0) it_u = it;
+        o.underflow_iteration = it_u;
+        o.n_unif_consumed = 0;
+        if (a.unif_stream && (a.flags & QUILT_F_PERFORM_BLOCK_GIBBS)) {
+            if (a.flags & QUILT_F_SAMPLE_IS_DIPLOID) {
+                int n_done = 0;
+                for (int e = 0; e < a.n_block_gibbs_iterations; e++) {
+                    const int b = a.block_gibbs_iterations[e];
+                    if (b >= 0 && b < j.n_its && (it_u < 0 || b < it_u)) n_done++;
+                }
+                o.n_unif_consumed = (int64_t)diploid_episode_base(a, n_done);
+            } else {
+                o.n_unif_consumed = (int64_t)lik[LIK_EP_POS];
+            }
+        }
+    }
     const size_t n3 = (size_t)a.nSNPs * 3;
     if (o.hapProbs_t) std::memcpy(o.hapProbs_t, base + j.lo.hap, n3 * 8);
     if (o.genProbsM_t) std::memcpy(o.genProbsM_t, base + j.lo.genM, n3 * 8);
     if (o.genProbsF_t) std::memcpy(o.genProbsF_t, base + j.lo.genF, n3 * 8);
     if (o.H) std::memcpy(o.H, base + j.lo.H, (size_t)j.R * 4);
+    if (o.H_sample_its && a.n_gibbs_sample_its > 0)
+        std::memcpy(o.H_sample_its, base + (a.n_gibbs_sample_its > 1 ? j.lo.Hs : j.lo.H), (size_t)a.n_gibbs_sample_its * j.R * 4);
     if (o.H_class && (a.flags & QUILT_F_RECORD_READ_SET)) std::memcpy(o.H_class, base + j.lo.Hclass, (size_t)j.R * 4);
     if (o.read_category) std::memcpy(o.read_category, base + j.lo.cat, (size_t)j.R * 4);
     if (o.per_it_likelihoods) {

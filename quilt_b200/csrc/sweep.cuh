@@ -21,6 +21,32 @@
 #include "device_common.cuh"
 #include "types.h"
 
+// -DQB_CLK=1 builds an instrumented variant (tools/build_variant.py): thread 0 of every CTA accumulates clock64()
+// deltas per phase of the sweep and CTA 0 prints them after sweep QB_CLK_IT.  Never defined in the product build.
+#ifndef QB_CLK
+#define QB_CLK 0
+#endif
+#ifndef QB_CLK_IT
+#define QB_CLK_IT 5
+#endif
+#if QB_CLK
+#define QB_T(i)                                 \
+    do {                                        \
+        if (tid == 0) {                         \
+            const long long n_ = clock64();     \
+            clk[i] += n_ - tlast;               \
+            tlast = n_;                         \
+        }                                       \
+    } while (0)
+#define QB_N(i)                  \
+    do {                         \
+        if (tid == 0) clk[i]++;  \
+    } while (0)
+#else
+#define QB_T(i) ((void)0)
+#define QB_N(i) ((void)0)
+#endif
+
 namespace qb {
 
 constexpr int SW_MAXR = 48;     // reads staged in shared memory at a time (longer grids are processed in chunks)
@@ -509,6 +535,11 @@ __global__ void __launch_bounds__(NT, (NT * EPT <= 512 ? 4 : (NT * EPT <= 1024 ?
         fence_barrier_init();
     }
     if (tid < 16) cnt[tid] = 0;
+#if QB_CLK
+    __shared__ long long clk[24];
+    if (tid < 24) clk[tid] = 0;
+    long long tlast = clock64();
+#endif
     __syncthreads();
     const int n_tab_total = tsG[T];
     uint32_t n_use0 = 0, n_use1 = 0, n_use2 = 0;  // completed uses of each stage barrier -> wait parity
@@ -660,7 +691,9 @@ __global__ void __launch_bounds__(NT, (NT * EPT <= 512 ? 4 : (NT * EPT <= 1024 ?
     issue_eG(0);
     // =============================================================== forward + read resampling
     for (int g = 0; g < T; g++) {
+        QB_T(11);
         wait_pkg(g);
+        QB_T(0);
         const int s = g & 1;
         const int32_t* sci = reinterpret_cast<const int32_t*>(smem + L.off_sc + s * 96);
         const double* scd = reinterpret_cast<const double*>(sci);
@@ -704,6 +737,7 @@ __global__ void __launch_bounds__(NT, (NT * EPT <= 512 ? 4 : (NT * EPT <= 1024 ?
                 }
             }
         }
+        QB_T(1);
         double cnew[NH];
         if (g == 0) {
             // rcpp_reinitialize_in_iterations
@@ -759,6 +793,7 @@ __global__ void __launch_bounds__(NT, (NT * EPT <= 512 ? 4 : (NT * EPT <= 1024 ?
             }
         }
         // am now holds alphaHat_t[:, g]; it stays in registers as the previous column of the next grid
+        QB_T(2);
         if (g + 1 < T && (P.dbg & 2)) issue_pkg(g + 1, r1, nx_r1, ts1, nx_fcn, nx_fct);  // experiment: issue after the forward step
         bool changed = false;
         if (has) {
@@ -987,7 +1022,10 @@ __global__ void __launch_bounds__(NT, (NT * EPT <= 512 ? 4 : (NT * EPT <= 1024 ?
                         continue;
                     }
                     // ---- hot path: diploid, table-mode read on consecutive SNPs, normal regime
+                    QB_T(11);
                     if (!inited) init_ab();
+                    QB_T(3);
+                    QB_N(16);
                     ESrc S;
                     {
                         const int nb = (dq.y >> 16) & 0xff;
@@ -1020,7 +1058,9 @@ __global__ void __launch_bounds__(NT, (NT * EPT <= 512 ? 4 : (NT * EPT <= 1024 ?
                         sv[1] = s1;
                         (void)s2;
                     }
+                    QB_T(4);
                     bsum.run(sv);
+                    QB_T(5);
                     const FastDecision F = decide_diploid_fast(pC, sv[0], sv[1], hC, Us[ir], prior);
                     Decision D;
                     if (F.decided) {
@@ -1047,7 +1087,9 @@ __global__ void __launch_bounds__(NT, (NT * EPT <= 512 ? 4 : (NT * EPT <= 1024 ?
                             J.xprob[4 * (size_t)r + 3] = -1.0;
                         }
                     }
+                    QB_T(6);
                     if (D.change) {
+                        QB_N(17);
                         changed = true;
                         if (tid == 0) J.H[r] = D.hN + 1;
                         if (!S.cross) {
@@ -1063,6 +1105,7 @@ __global__ void __launch_bounds__(NT, (NT * EPT <= 512 ? 4 : (NT * EPT <= 1024 ?
                                 QB_UPD_LOOP(1, 1, 0, true)
                             }
                         }
+                        QB_T(7);
                     }
                 }
                 tab0 = tend;
@@ -1074,6 +1117,8 @@ __global__ void __launch_bounds__(NT, (NT * EPT <= 512 ? 4 : (NT * EPT <= 1024 ?
 #undef QB_UPD
 #undef QB_UPD_LABELS
 #undef QB_UPD_LOOP
+            QB_T(11);
+            QB_N(18);
             if (beta_pending) {
                 // no read of this grid was visited: consume the beta copy so that its buffer can move on
                 mbar_wait(&bar[5], n_useB & 1);
@@ -1114,7 +1159,9 @@ __global__ void __launch_bounds__(NT, (NT * EPT <= 512 ? 4 : (NT * EPT <= 1024 ?
             if (tid == 0) cG[h * T + g] = cnew[h];
             cfin[h] = cnew[h];
         }
+        QB_T(8);
     }
+    QB_T(11);
 
     // =============================================================== backward (Rcpp_run_backward_haploid_QUILT_faster)
     // the eMatGrid columns changed above were written through the generic proxy; order them before the
@@ -1209,6 +1256,7 @@ __global__ void __launch_bounds__(NT, (NT * EPT <= 512 ? 4 : (NT * EPT <= 1024 ?
 
     // =============================================================== epilogue: H_class, counts, -sum log c, underflow
     __syncthreads();
+    QB_T(9);
     for (int r = tid; r < R; r += NT) {
         const int h = J.H[r];
         atomicAdd(&cnt[h - 1], 1);
@@ -1262,6 +1310,14 @@ __global__ void __launch_bounds__(NT, (NT * EPT <= 512 ? 4 : (NT * EPT <= 1024 ?
         lik[14] = bad ? 1.0 : 0.0;
         if (bad) *J.underflow = 1;
     }
+#if QB_CLK
+    QB_T(10);
+    if (tid == 0 && blockIdx.x == 0 && iteration == QB_CLK_IT) {
+        printf("QBCLK it=%d T=%d R=%d wait_pkg=%lld issue=%lld fwd=%lld init_ab=%lld sums=%lld reduce=%lld decide=%lld update=%lld gridend=%lld backward=%lld epilogue=%lld other=%lld "
+               "visited=%lld changed=%lld grids_with_reads=%lld\n",
+               iteration, T, R, clk[0], clk[1], clk[2], clk[3], clk[4], clk[5], clk[6], clk[7], clk[8], clk[9], clk[10], clk[11], clk[16], clk[17], clk[18]);
+    }
+#endif
 }
 
 }  // namespace qb

@@ -39,6 +39,8 @@ static_assert(sizeof(ReadDesc) == 32, "ReadDesc must be 32 bytes");
 constexpr int LIK_N = 16;  // per-sweep bookkeeping record written by the sweep epilogue
 // lik[0..2] = -sum_g log c_h[g] ; lik[3..5] = #reads with label h ; lik[6..13] = #reads with H_class 0..7 ;
 // lik[14] = 1 if a non-finite sum(c_h) was seen (reference underflow check, gibbs-nipt.cpp:2959-2969)
+// slot 15 of row 0: position in the episode stream (QuiltGibbsArgs.unif_stream) of the three-haplotype kernels
+constexpr int LIK_EP_POS = 15;
 
 // one Gibbs call in flight on the device ("job"); pointers are device pointers
 struct JobDev {
@@ -78,6 +80,8 @@ struct JobDev {
     const double* runif_block;    // [n_ep][R]
     const double* runif_H_class;  // [n_ep][R]
     const int32_t* L_grid;        // [T]
+    int32_t ep_stream;            // 1: runif_block holds the caller's flat episode stream, walked with the position in lik[LIK_EP_POS]
+    int32_t pad1;
     unsigned char* blk;           // per-slot scratch of the block definition / resampler (layout: BlockScratch)
     // outputs / evolving small state
     int32_t* H;       // [R] 1-based labels
@@ -89,6 +93,7 @@ struct JobDev {
     double* genF;        // [3][nSNPs]
     double* hapLocal;    // [3][nSNPs] rare/common calls: the reference's never re-zeroed hapProbs_t_local (gibbs-small.cpp:711-867)
     int32_t* cat_out;    // [R] read_category export
+    int32_t* Hs;         // [n_sample][R] labels after each sampling sweep (n_sample > 1 only)
 };
 
 struct PanelDev {

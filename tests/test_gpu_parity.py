@@ -255,6 +255,62 @@ def test_gibbs_batch_mixed(gpu, oracle, small_world):
         _compare(f"batch job {i}", g, oracle.gibbs(c), state=False)
 
 
+def _with_stream(call, seed=99, slack=7):
+    """the same call with its episode uniforms supplied as one flat unif_rand() stream (QuiltGibbsArgs.unif_stream)"""
+    R, T = call.reads.nReads, call.nGrids
+    shard = bool(call.flags & cabi.F_DO_SHARD_BLOCK_GIBBS)
+    per = 8 * R + (R if call.ff > 0 else 0) + (T - 1 if shard else 0)
+    call.unif_stream = np.random.default_rng(seed).random(len(call.block_gibbs_iterations) * per + slack)
+    return call
+
+
+@pytest.mark.parametrize("kw", [dict(K=200, first_iteration=True), dict(K=300, first_iteration=False, ff=0.1), dict(K=150, first_iteration=True, ff=0.25),
+                                dict(K=200, first_iteration=False, n_sample=3)],
+                         ids=["diploid", "nipt_ff10", "nipt_ff25_iterative", "diploid_three_sampling_sweeps"])
+def test_episode_stream_mode(gpu, oracle, small_world, small_reads, kw):
+    """episode uniforms as one flat stream consumed in the reference's order: for NIPT the number of H_class draws per episode is
+    data-dependent, so the position of every later episode is; the library must report how far the reference would have read"""
+    call = _with_stream(synth.make_call(small_world, small_reads.common, 41, **kw))
+    g, o = gpu.gibbs(call), oracle.gibbs(call)
+    _compare(f"stream mode {kw}", g, o, state=False)
+    assert np.array_equal(g.H_sample_its, o.H_sample_its), "labels after each sampling sweep (double_list_of_ending_read_labels)"
+    assert g.n_unif_consumed == o.n_unif_consumed > 0
+    assert g.underflow_iteration == o.underflow_iteration == -1
+
+
+def test_underflow_iteration_and_stream_position(gpu, oracle, small_world):
+    sr = synth.make_sample_reads(small_world, 9, coverage=60.0, region_bp=300_000)
+    call = _with_stream(synth.make_call(small_world, sr.common, 26, K=100, first_iteration=False, maxDifferenceBetweenReads=1e300))
+    g, o = gpu.gibbs(call), oracle.gibbs(call)
+    assert g.underflow_problem and o.underflow_problem
+    assert g.underflow_iteration == o.underflow_iteration >= 0
+    assert g.n_unif_consumed == o.n_unif_consumed
+
+
+def test_panel_cache_is_keyed_by_content(gpu, oracle, small_world, small_reads):
+    """two different panels living at the SAME host addresses (the first one overwritten in place) must not share a device copy"""
+    w2 = synth.make_world(777, K_full=small_world.panel.K_full, nSNPs=small_world.panel.nSNPs, region_bp=300_000, all_snps_factor=3)
+    call = synth.make_call(small_world, small_reads.common, 43, K=150, first_iteration=False)
+    g1 = gpu.gibbs(call)
+    p1, p2 = small_world.panel, w2.panel
+    saved = {}
+    for f in ("hapMatcherR", "distinctHapsB", "distinctHapsIE", "special_helper"):
+        a, b = getattr(p1, f), getattr(p2, f)
+        if a.shape == b.shape:
+            saved[f] = a.copy()
+            a[...] = b
+    if len(saved) < 3:
+        pytest.skip("the two synthetic panels differ in shape")
+    try:
+        o2 = oracle.gibbs(call)
+        g2 = gpu.gibbs(call)
+        assert np.array_equal(g2.H, o2.H), "a stale device panel was used"
+        assert not np.array_equal(g1.hapProbs_t, g2.hapProbs_t)
+    finally:
+        for f, v in saved.items():
+            getattr(p1, f)[...] = v
+
+
 def test_underflow_reported(gpu, oracle, small_world, small_reads):
     """maxDifferenceBetweenReads huge + many reads per grid -> the reference reports underflow instead of failing"""
     sr = synth.make_sample_reads(small_world, 9, coverage=60.0, region_bp=300_000)

@@ -39,6 +39,7 @@ def _same(r, o, nh=None, state=False):
     assert np.array_equal(r.H, o.H)
     assert np.array_equal(r.H_class, o.H_class)
     assert np.array_equal(r.read_category, o.read_category)
+    assert np.array_equal(r.H_sample_its, o.H_sample_its)
     for f in ("hapProbs_t", "genProbsM_t", "genProbsF_t"):
         assert np.array_equal(getattr(r, f), getattr(o, f)), f
     assert np.array_equal(_lk(r.per_it_likelihoods), _lk(o.per_it_likelihoods))
