@@ -21,6 +21,8 @@
  *                                    QUILT/src/gibbs-small.cpp:69-105
  *   quilt_gpu_forward_backward    <- Rcpp_run_forward_haploid / Rcpp_run_backward_haploid
  *                                    QUILT/src/copied-from-stitch.cpp:340-409
+ *   quilt_gpu_select_haps         <- select_new_haps_mspbwt_v3 (heuristic_approach "A")
+ *                                    QUILT/R/mspbwt.R:230-474, called at QUILT/R/functions.R:856-868
  *
  * All real arrays are fp64, column-major (R / Armadillo), K is the fastest
  * dimension.  Integer arrays are int32 unless stated.  Indices are 0-based
@@ -198,6 +200,46 @@ int quilt_gpu_batch_timing(QuiltGpuBatch* batch, double* total_ms, double* sweep
 /* bytes moved by quilt_gpu_batch_stage (host -> device) and quilt_gpu_batch_fetch (device -> host), and the ALGORITHMIC bytes of
  * the sweep kernel launches of one run: sum over launches and jobs of 8 * K * (5 * nHap * nGrids + nReads) */
 int quilt_gpu_batch_bytes(QuiltGpuBatch* batch, int64_t* h2d_bytes, int64_t* d2h_bytes, double* sweep_algorithmic_bytes);
+
+/*
+ * Haplotype re-selection between Gibbs calls (select_new_haps_mspbwt_v3, QUILT/R/mspbwt.R:230-474).
+ *
+ * In-tree part, restated exactly: hap = round(hapProbs_t[h, ]) packed 32 SNPs per word (rcpp_int_contract, :277-278);
+ * the nIndices interleaved grid subsets seq(i, nGrids, nIndices) (:283); per subset the match table re-keyed to
+ * (index1, start1, end1, len1), ordered by (index1, -end1, -start1) and stripped of adjacent rows repeating
+ * (index1, start1) (:312-335); subsets concatenated and ordered by -len1 (:340-349); then, if the haplotypes found
+ * exceed Knew, the coverage-weighted ranking (:414-441) and the interleave / unique / first-Knew cut (:443-466);
+ * otherwise the haplotypes found in order of first appearance (:368-379).  Padding a short list with sample()
+ * (:381-399) draws from R's generator and stays with the caller: n_found < Knew tells it how many to add.
+ *
+ * Un-vendored part (mspbwt 0.1.0: map_Z_to_all_symbols, Rcpp_find_good_matches_without_a; parity UNPINNED — the
+ * package is not in the reference tree): its contract is re-derived from the call site
+ * (:284-310).  A word of Z maps to the row of distinctHapsB[, g] holding the same 32-SNP word (hapMatcherR's symbol);
+ * a word that is not in the panel's table matches no haplotype, and symbol 0 ("special") never matches.  Walking a
+ * subset left to right, every panel haplotype carries the length of its current run of identical symbols with Z;
+ * at a position the 2 * mspbwtL haplotypes with the longest runs (ties: lower haplotype index) are Z's neighbours;
+ * a run is reported as (start0, index0, len1) when it ENDS — next symbol differs or the subset ends — while its
+ * haplotype is a neighbour and len1 >= mspbwtM.
+ */
+typedef struct QuiltSelectArgs {
+    const QuiltPanel* panel;     /* hapMatcherR / distinctHapsB of the common-SNP panel                     */
+    int32_t nHap;                /* haplotypes of the sample: 2 (diploid) or 3 (nipt)                       */
+    const double* hapProbs_t;    /* [3 x nSNPs] column-major, as returned by the Gibbs call                 */
+    int32_t Knew;
+    int32_t mspbwt_nindices;     /* 4 (quilt.R:174)                                                         */
+    int32_t mspbwtL;             /* 3 (quilt.R:171)                                                         */
+    int32_t mspbwtM;             /* 1 (quilt.R:172)                                                         */
+} QuiltSelectArgs;
+/* which_haps_to_use [Knew] 1-based, first n_found entries valid; n_unique = haplotypes found before the cut */
+int quilt_gpu_select_haps(const QuiltSelectArgs* args, int32_t* which_haps_to_use, int32_t* n_found, int32_t* n_unique);
+/* Device-resident chaining: job j of `next` (staged, not yet run) follows job j of `prev` (run): select from prev's
+ * hapProbs_t on the device and write the list into next's which_haps_to_use, no host round trip.  A list shorter than
+ * next's Ksubset is completed from haplotypes not yet in it by a partial Fisher-Yates driven by pad_unif
+ * ([n_jobs x Ksubset] uniforms; statistically what sample() does at mspbwt.R:381-399, not R's bit stream).        */
+int quilt_gpu_batch_chain_select(QuiltGpuBatch* prev, QuiltGpuBatch* next, int32_t mspbwt_nindices, int32_t mspbwtL, int32_t mspbwtM,
+                                 const double* pad_unif);
+/* the haplotype list job `job` of a staged batch currently holds on the device (after a chained selection: the new list) */
+int quilt_gpu_batch_which_haps(QuiltGpuBatch* batch, int32_t job, int32_t* which_haps_to_use /*[Ksubset]*/);
 
 /* component entry points (parity tests of the individual reference functions) */
 int quilt_gpu_make_eMatRead_t(const QuiltGibbsArgs* args, double* eMatRead_t /*[K x nReads]*/,

@@ -32,8 +32,25 @@ class Oracle(cabi._LibAPI):
         self.lib = C.CDLL(_SO)
         cabi.declare(self.lib, self.prefix)
         pd, pu8 = C.POINTER(C.c_double), C.POINTER(C.c_uint8)
+        self.lib.quilt_oracle_select_haps_padded.argtypes = [C.POINTER(cabi.QuiltSelectArgs), pd, C.POINTER(C.c_int32)]
+        self.lib.quilt_oracle_select_haps_padded.restype = C.c_int
         self.lib.quilt_oracle_backward_pair.argtypes = [C.c_int32, C.c_int32, pd, pd, pd, pu8, pd, pd]
         self.lib.quilt_oracle_forward_one_pair.argtypes = [C.c_int32, C.c_int32, pd, pd, pu8, C.c_int32, pd, pd, C.c_int32]
+
+    def select_haps_padded(self, panel, hapProbs_t, Knew, pad_unif, nHap=2, mspbwt_nindices=4, mspbwtL=3, mspbwtM=1):
+        """selection + the chain-mode completion of a short list (quilt_gpu_batch_chain_select's rule)"""
+        hp = cabi.f64(hapProbs_t)
+        a = cabi.QuiltSelectArgs()
+        ps = panel.c_struct()
+        a.panel = C.pointer(ps)
+        a.nHap, a.hapProbs_t, a.Knew = nHap, cabi._ptr(hp, cabi._pd), Knew
+        a.mspbwt_nindices, a.mspbwtL, a.mspbwtM = mspbwt_nindices, mspbwtL, mspbwtM
+        pu = np.ascontiguousarray(pad_unif, dtype=np.float64)
+        which = np.zeros(Knew, dtype=np.int32)
+        rc = self.lib.quilt_oracle_select_haps_padded(C.byref(a), cabi._ptr(pu, cabi._pd), cabi._ptr(which, cabi._pi))
+        if rc != cabi.OK:
+            raise RuntimeError(f"quilt_oracle_select_haps_padded failed with status {rc}")
+        return which
 
     def backward_pair(self, eMatGrid_t, tm, c, grid_has_read):
         e, t = cabi.f64(eMatGrid_t), cabi.f64(tm)

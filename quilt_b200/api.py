@@ -61,6 +61,10 @@ class GpuLib(cabi._LibAPI):
         L.quilt_gpu_last_error.restype = C.c_char_p
         L.quilt_gpu_kernel_launches.restype = C.c_int64
         L.quilt_gpu_release_panel_cache.restype = None
+        L.quilt_gpu_batch_chain_select.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_double)]
+        L.quilt_gpu_batch_chain_select.restype = C.c_int
+        L.quilt_gpu_batch_which_haps.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_int32)]
+        L.quilt_gpu_batch_which_haps.restype = C.c_int
 
     # ---- housekeeping
     def last_error(self) -> str:
@@ -153,6 +157,19 @@ class Batch:
             r.n_unif_consumed = int(outs[i].n_unif_consumed)
             r.underflow_iteration = int(outs[i].underflow_iteration)
         return res
+
+    def chain_select_into(self, nxt: "Batch", pad_unif: np.ndarray, mspbwt_nindices: int = 4, mspbwtL: int = 3, mspbwtM: int = 1):
+        """select_new_haps_mspbwt_v3 on the device for every job of this (run) batch; the lists become the
+        which_haps_to_use of the corresponding jobs of `nxt` (staged, not yet run): no host round trip (QUILT/R/functions.R:856-868)"""
+        pu = np.ascontiguousarray(pad_unif, dtype=np.float64)
+        assert pu.size >= len(self.calls) * nxt.calls[0].K
+        self.lib._check(self.lib.lib.quilt_gpu_batch_chain_select(self._h, nxt._h, mspbwt_nindices, mspbwtL, mspbwtM, cabi._ptr(pu, cabi._pd)),
+                        "quilt_gpu_batch_chain_select")
+
+    def which_haps(self, job: int) -> np.ndarray:
+        out = np.zeros(self.calls[job].K, dtype=np.int32)
+        self.lib._check(self.lib.lib.quilt_gpu_batch_which_haps(self._h, job, cabi._ptr(out, cabi._pi)), "quilt_gpu_batch_which_haps")
+        return out
 
     def free(self):
         if self._h:

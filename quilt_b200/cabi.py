@@ -133,6 +133,18 @@ class QuiltGibbsOut(C.Structure):
     ]
 
 
+class QuiltSelectArgs(C.Structure):
+    _fields_ = [
+        ("panel", C.POINTER(QuiltPanel)),
+        ("nHap", C.c_int32),
+        ("hapProbs_t", _pd),
+        ("Knew", C.c_int32),
+        ("mspbwt_nindices", C.c_int32),
+        ("mspbwtL", C.c_int32),
+        ("mspbwtM", C.c_int32),
+    ]
+
+
 def _ptr(a: Optional[np.ndarray], typ):
     if a is None:
         return C.cast(None, typ)
@@ -410,6 +422,9 @@ def declare(lib: C.CDLL, prefix: str):
     getattr(lib, f"{prefix}_unpack_panel").restype = C.c_int
     getattr(lib, f"{prefix}_forward_backward").argtypes = [C.c_int32, C.c_int32, _pd, _pd, _pd, _pd, _pd]
     getattr(lib, f"{prefix}_forward_backward").restype = C.c_int
+    if hasattr(lib, f"{prefix}_select_haps"):
+        getattr(lib, f"{prefix}_select_haps").argtypes = [C.POINTER(QuiltSelectArgs), _pi, _pi, _pi]
+        getattr(lib, f"{prefix}_select_haps").restype = C.c_int
 
 
 class _LibAPI:
@@ -463,6 +478,23 @@ class _LibAPI:
         if rc != OK:
             raise RuntimeError(f"{self.prefix}_forward_backward failed with status {rc}: {self.last_error()}")
         return a, b, c
+
+    def select_haps(self, panel: Panel, hapProbs_t: np.ndarray, Knew: int, nHap: int = 2, mspbwt_nindices: int = 4, mspbwtL: int = 3, mspbwtM: int = 1):
+        """select_new_haps_mspbwt_v3 (QUILT/R/mspbwt.R:230-474) -> (which_haps_to_use[:n_found] 1-based, n_unique); the caller pads a
+        short list with sample() as mspbwt.R:381-399 does"""
+        hp = f64(hapProbs_t)
+        assert hp.shape == (3, panel.nSNPs)
+        a = QuiltSelectArgs()
+        ps = panel.c_struct()
+        a.panel = C.pointer(ps)
+        a.nHap, a.hapProbs_t, a.Knew = nHap, _ptr(hp, _pd), Knew
+        a.mspbwt_nindices, a.mspbwtL, a.mspbwtM = mspbwt_nindices, mspbwtL, mspbwtM
+        which = np.zeros(Knew, dtype=np.int32)
+        nf, nu = C.c_int32(), C.c_int32()
+        rc = getattr(self.lib, f"{self.prefix}_select_haps")(C.byref(a), _ptr(which, _pi), C.byref(nf), C.byref(nu))
+        if rc != OK:
+            raise RuntimeError(f"{self.prefix}_select_haps failed with status {rc}: {self.last_error()}")
+        return which[: nf.value].copy(), nu.value
 
     def last_error(self) -> str:
         return ""

@@ -28,6 +28,7 @@
 #include "../../include/quilt_b200.h"
 #include "block_nipt.cuh"
 #include "passes.cuh"
+#include "select.cuh"
 #include "prep.cuh"
 #include "sweep.cuh"
 #include "types.h"
@@ -321,7 +322,14 @@ int get_panel(const QuiltPanel* p, PanelDev* out, std::shared_ptr<PanelEntry>* k
     e->last_use = ++g_panel_clock;
     const size_t b_hm = al((size_t)p->K_full * p->nGrids), b_db = al((size_t)p->nMaxDH * p->nGrids * 4);
     const int nsp = std::max(p->n_special, 1);
-    const size_t b_sp = al((size_t)nsp * 2 * 4), b_he = al((size_t)p->nGrids * 2 * 4);
+    const size_t b_sp = al((size_t)nsp * 2 * 4), b_he = al((size_t)p->nGrids * 2 * 4), b_nu = al((size_t)p->nGrids * 4);
+    std::vector<int32_t> n_used((size_t)p->nGrids, 0);
+    for (int g = 0; g < p->nGrids; g++) {
+        const uint8_t* col = p->hapMatcherR + (size_t)g * p->K_full;
+        int m = 0;
+        for (int k = 0; k < p->K_full; k++) m = std::max<int>(m, col[k]);
+        n_used[(size_t)g] = std::min(m, p->nMaxDH);
+    }
     size_t b_ic = 0, b_ci = 0, b_ro = 0, b_rs = 0;
     int64_t n_rare = 0;
     if (p->nSNPs_all > 0) {
@@ -332,7 +340,7 @@ int get_panel(const QuiltPanel* p, PanelDev* out, std::shared_ptr<PanelEntry>* k
         b_ro = al((size_t)(p->K_full + 1) * 8);
         b_rs = al((size_t)std::max<int64_t>(n_rare, 1) * 4);
     }
-    CK(e->buf.alloc(b_hm + b_db + b_sp + b_he + b_ic + b_ci + b_ro + b_rs));
+    CK(e->buf.alloc(b_hm + b_db + b_sp + b_he + b_nu + b_ic + b_ci + b_ro + b_rs));
     char* d = (char*)e->buf.p;
     PanelDev& D = e->dev;
     D.K_full = p->K_full;
@@ -357,6 +365,9 @@ int get_panel(const QuiltPanel* p, PanelDev* out, std::shared_ptr<PanelEntry>* k
     D.helper = (const int32_t*)d;
     CK(cudaMemcpy(d, p->eMatDH_special_matrix_helper, (size_t)p->nGrids * 2 * 4, cudaMemcpyHostToDevice));
     d += b_he;
+    D.n_used = (const int32_t*)d;
+    CK(cudaMemcpy(d, n_used.data(), (size_t)p->nGrids * 4, cudaMemcpyHostToDevice));
+    d += b_nu;
     D.snp_is_common = nullptr;
     D.common_snp_index = nullptr;
     D.rare_off = nullptr;
@@ -483,6 +494,7 @@ struct QuiltGpuBatch {
     HBuf& hout() const { return *hout_; }
     size_t in_bytes = 0, out_bytes = 0;
     bool ran = false, fetched_raw = false;
+    bool chained = false;  // which_haps_to_use of the jobs were written on the device (quilt_gpu_batch_chain_select)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> sweep_events;
     double total_ms = 0, sweep_ms = 0;
@@ -1640,6 +1652,182 @@ int quilt_gpu_gibbs_batch(int32_t n, const QuiltGibbsArgs* args, QuiltGibbsOut* 
 }
 
 int quilt_gpu_gibbs(const QuiltGibbsArgs* args, QuiltGibbsOut* out) { return quilt_gpu_gibbs_batch(1, args, out); }
+
+// ------------------------------------------------------------------------------------------------ haplotype re-selection
+namespace {
+
+struct SelPlan {
+    SelParams P;
+    size_t per_job = 0;   // scratch bytes per job
+    size_t o_sym, o_runlen, o_rows, o_nrows, o_skey, o_sval, o_list, o_nlist, o_firstpos, o_tmp, o_ranked, o_tmp2, o_stage, o_pool, o_counts;
+};
+
+int make_sel_plan(const PanelDev& pd, int nHap, int Knew, int nIndices, int L, int M, int pad, SelPlan* pl) {
+    if (nHap < 1 || nHap > 3 || Knew < 1 || nIndices < 1 || L < 1 || M < 1) return set_err(QUILT_ERR_BAD_ARG, "bad selection arguments");
+    if (2 * L > SEL_MAXTOP) return set_err(QUILT_ERR_UNSUPPORTED, "mspbwtL > 8 not supported");
+    if (pd.Tc < nIndices) return set_err(QUILT_ERR_BAD_ARG, "fewer grids than mspbwt_nindices (the reference resets nindices to 1, quilt-prepare-reference.R:452-455)");
+    if (pd.K_full >= (1 << 24) || pd.Tc >= (1 << 20)) return set_err(QUILT_ERR_UNSUPPORTED, "panel too large for the packed match rows");
+    SelParams& P = pl->P;
+    std::memset(&P, 0, sizeof(P));
+    P.K_full = pd.K_full;
+    P.Tc = pd.Tc;
+    P.nSNPs = pd.nSNPsC;
+    P.nMaxDH = pd.nMaxDH;
+    P.nHap = nHap;
+    P.nIndices = nIndices;
+    P.L = L;
+    P.M = M;
+    P.Knew = Knew;
+    P.pad = pad;
+    const int n_pos_max = (pd.Tc + nIndices - 1) / nIndices;
+    P.rows_cap = n_pos_max * 2 * L;
+    int sc = 1;
+    while (sc < nIndices * P.rows_cap) sc <<= 1;
+    P.sort_cap = sc;
+    size_t o = 0;
+    auto take = [&](size_t n) {
+        const size_t r = o;
+        o += al(n);
+        return r;
+    };
+    const size_t hs = (size_t)nHap * sc;
+    pl->o_sym = take((size_t)nHap * pd.Tc * 4);
+    pl->o_runlen = take((size_t)nHap * nIndices * pd.K_full * 2);
+    pl->o_rows = take((size_t)nHap * nIndices * P.rows_cap * 8);
+    pl->o_nrows = take((size_t)nHap * nIndices * 4);
+    pl->o_skey = take((size_t)sc * 8);
+    pl->o_sval = take((size_t)sc * 4);
+    pl->o_list = take(hs * 8);
+    pl->o_nlist = take((size_t)nHap * 4);
+    pl->o_firstpos = take(((size_t)std::max(pd.K_full, pd.Tc) + 2) * 4);
+    pl->o_tmp = take(std::max(hs, (size_t)pd.K_full + 2) * 4);
+    pl->o_ranked = take(hs * 4);
+    pl->o_tmp2 = take(hs * 4);
+    pl->o_stage = take((size_t)sc * 8);
+    pl->o_pool = take(((size_t)pd.K_full + 2) * 4);
+    pl->o_counts = take(16);
+    pl->per_job = o;
+    return QUILT_OK;
+}
+
+void fill_sel_job(const SelPlan& pl, char* scratch, const double* hapProbs, int32_t* which_out, const double* pad_unif, SelJob* J) {
+    J->hapProbs = hapProbs;
+    J->which_out = which_out;
+    J->pad_unif = pad_unif;
+    J->sym = (int32_t*)(scratch + pl.o_sym);
+    J->runlen = (uint16_t*)(scratch + pl.o_runlen);
+    J->rows = (uint64_t*)(scratch + pl.o_rows);
+    J->nrows = (int32_t*)(scratch + pl.o_nrows);
+    J->skey = (uint64_t*)(scratch + pl.o_skey);
+    J->sval = (uint32_t*)(scratch + pl.o_sval);
+    J->list = (uint64_t*)(scratch + pl.o_list);
+    J->nlist = (int32_t*)(scratch + pl.o_nlist);
+    J->firstpos = (int32_t*)(scratch + pl.o_firstpos);
+    J->tmp = (int32_t*)(scratch + pl.o_tmp);
+    J->ranked = (int32_t*)(scratch + pl.o_ranked);
+    J->tmp2 = (int32_t*)(scratch + pl.o_tmp2);
+    J->stage = (uint64_t*)(scratch + pl.o_stage);
+    J->pool = (int32_t*)(scratch + pl.o_pool);
+    J->counts_out = (int32_t*)(scratch + pl.o_counts);
+}
+
+int launch_select(const SelPlan& pl, const PanelDev& pd, const SelJob* djobs, int n) {
+    const SelParams& P = pl.P;
+    k_sel_symbols<<<dim3(P.Tc, P.nHap, n), SEL_NT, 0, g_stream>>>(P, djobs, pd.distinctHapsB, pd.n_used);
+    LAUNCHED();
+    k_sel_match<<<dim3(P.nIndices, P.nHap, n), SEL_NT, 0, g_stream>>>(P, djobs, pd.hapMatcherR);
+    LAUNCHED();
+    k_sel_rank<<<n, SEL_RANK_NT, 0, g_stream>>>(P, djobs);
+    LAUNCHED();
+    CK(cudaGetLastError());
+    return QUILT_OK;
+}
+
+}  // namespace
+
+int quilt_gpu_select_haps(const QuiltSelectArgs* a, int32_t* which_haps_to_use, int32_t* n_found, int32_t* n_unique) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!a || !a->panel || !a->hapProbs_t || !which_haps_to_use || !n_found || !n_unique) return set_err(QUILT_ERR_BAD_ARG, "null argument");
+    int rc = ensure_device();
+    if (rc != QUILT_OK) return rc;
+    PanelDev pd;
+    std::shared_ptr<PanelEntry> keep;
+    if ((rc = get_panel(a->panel, &pd, &keep)) != QUILT_OK) return rc;
+    SelPlan pl;
+    if ((rc = make_sel_plan(pd, a->nHap, a->Knew, a->mspbwt_nindices, a->mspbwtL, a->mspbwtM, 0, &pl)) != QUILT_OK) return rc;
+    const size_t b_hp = al((size_t)3 * pd.nSNPsC * 8), b_w = al((size_t)a->Knew * 4);
+    DBuf buf;
+    CK(buf.alloc(pl.per_job + b_hp + b_w + al(sizeof(SelJob))));
+    char* d = (char*)buf.p;
+    CK(cudaMemcpyAsync(d + pl.per_job, a->hapProbs_t, (size_t)3 * pd.nSNPsC * 8, cudaMemcpyHostToDevice, g_stream));
+    SelJob J;
+    fill_sel_job(pl, d, (const double*)(d + pl.per_job), (int32_t*)(d + pl.per_job + b_hp), nullptr, &J);
+    SelJob* dj = (SelJob*)(d + pl.per_job + b_hp + b_w);
+    CK(cudaMemcpyAsync(dj, &J, sizeof(SelJob), cudaMemcpyHostToDevice, g_stream));
+    if ((rc = launch_select(pl, pd, dj, 1)) != QUILT_OK) return rc;
+    int32_t counts[2] = {0, 0};
+    CK(cudaMemcpyAsync(which_haps_to_use, J.which_out, (size_t)a->Knew * 4, cudaMemcpyDeviceToHost, g_stream));
+    CK(cudaMemcpyAsync(counts, J.counts_out, 8, cudaMemcpyDeviceToHost, g_stream));
+    CK(cudaStreamSynchronize(g_stream));
+    *n_found = counts[0];
+    *n_unique = counts[1];
+    return QUILT_OK;
+}
+
+int quilt_gpu_batch_chain_select(QuiltGpuBatch* prev, QuiltGpuBatch* next, int32_t nIndices, int32_t L, int32_t M, const double* pad_unif) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!prev || !next || !pad_unif) return set_err(QUILT_ERR_BAD_ARG, "null argument");
+    if (!prev->ran) return set_err(QUILT_ERR_BAD_ARG, "the previous batch has not been run");
+    if (prev->n != next->n) return set_err(QUILT_ERR_BAD_ARG, "chained batches must hold the same number of calls");
+    if (prev->panel_ref != next->panel_ref) return set_err(QUILT_ERR_BAD_ARG, "chained batches must share one panel");
+    const int n = prev->n;
+    const int K = next->jobs[0].a.K;
+    const int nHap = (prev->jobs[0].a.flags & QUILT_F_SAMPLE_IS_DIPLOID) ? 2 : 3;
+    for (int i = 0; i < n; i++) {
+        if (next->jobs[i].a.K != K) return set_err(QUILT_ERR_UNSUPPORTED, "chained calls must share one Ksubset");
+        if (prev->jobs[i].a.nSNPs != prev->panel.nSNPsC) return set_err(QUILT_ERR_BAD_ARG, "selection runs on common-SNP calls");
+        if (((prev->jobs[i].a.flags & QUILT_F_SAMPLE_IS_DIPLOID) ? 2 : 3) != nHap) return set_err(QUILT_ERR_UNSUPPORTED, "mixed ploidy in a chained batch");
+    }
+    SelPlan pl;
+    int rc = make_sel_plan(prev->panel, nHap, K, nIndices, L, M, 1, &pl);
+    if (rc != QUILT_OK) return rc;
+    // jobs are processed in groups so that the scratch stays bounded
+    const int group = std::max(1, std::min(n, (int)(((size_t)2 << 30) / pl.per_job)));
+    const size_t b_pu = al((size_t)group * K * 8), b_j = al((size_t)group * sizeof(SelJob));
+    DBuf buf;
+    CK(buf.alloc((size_t)group * pl.per_job + b_pu + b_j));
+    char* d = (char*)buf.p;
+    double* d_pu = (double*)(d + (size_t)group * pl.per_job);
+    SelJob* dj = (SelJob*)(d + (size_t)group * pl.per_job + b_pu);
+    std::vector<SelJob> hj((size_t)group);
+    for (int j0 = 0; j0 < n; j0 += group) {
+        const int m = std::min(group, n - j0);
+        CK(cudaMemcpyAsync(d_pu, pad_unif + (size_t)j0 * K, (size_t)m * K * 8, cudaMemcpyHostToDevice, g_stream));
+        for (int q = 0; q < m; q++) {
+            const HostJob& pj = prev->jobs[(size_t)(j0 + q)];
+            const HostJob& nj = next->jobs[(size_t)(j0 + q)];
+            const double* hp = (const double*)((const char*)prev->dout().p + pj.out_off + pj.lo.hap);
+            int32_t* which = (int32_t*)((char*)next->din().p + nj.in_off + nj.li.which);
+            fill_sel_job(pl, d + (size_t)q * pl.per_job, hp, which, d_pu + (size_t)q * K, &hj[(size_t)q]);
+        }
+        CK(cudaMemcpyAsync(dj, hj.data(), (size_t)m * sizeof(SelJob), cudaMemcpyHostToDevice, g_stream));
+        if ((rc = launch_select(pl, prev->panel, dj, m)) != QUILT_OK) return rc;
+        CK(cudaStreamSynchronize(g_stream));  // hj / the pinned-less uploads are reused by the next group
+    }
+    next->chained = true;
+    return QUILT_OK;
+}
+
+int quilt_gpu_batch_which_haps(QuiltGpuBatch* B, int32_t job, int32_t* which_haps_to_use) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!B || job < 0 || job >= B->n || !which_haps_to_use) return set_err(QUILT_ERR_BAD_ARG, "bad argument");
+    const HostJob& j = B->jobs[(size_t)job];
+    CK(cudaMemcpyAsync(which_haps_to_use, (const char*)B->din().p + j.in_off + j.li.which, (size_t)j.a.K * 4, cudaMemcpyDeviceToHost, g_stream));
+    CK(cudaStreamSynchronize(g_stream));
+    return QUILT_OK;
+}
+
+
 
 // ---- component entry points (parity tests of the individual reference functions)
 int quilt_gpu_make_eMatRead_t(const QuiltGibbsArgs* args, double* eMatRead_t, int32_t* read_category) {

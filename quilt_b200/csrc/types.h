@@ -106,6 +106,7 @@ struct PanelDev {
     const int32_t* common_snp_index;
     const int64_t* rare_off;
     const int32_t* rare_snps;
+    const int32_t* n_used;         // [Tc] rows of distinctHapsB in use per grid (= max symbol of hapMatcherR[, g])
     double ref_error;
 };
 
