@@ -6,7 +6,10 @@
 
 A "step" = every Gibbs call of one batch of synthetic samples at QUILT2 defaults: per sample 8 chains x
 (3 calls on the common SNPs + 1 call on all SNPs) = 32 calls, each 20 burn-in + 1 sampling sweep with shard
-passes after sweeps 3/6/9.  Workload at N = 1 = the configuration the metric is quoted on:
+passes after sweeps 3/6/9, AND the haplotype re-selection between the calls of a chain
+(select_new_haps_mspbwt_v3, functions.R:856-868): the calls are staged as four batches (call 1 / 2 / 3 of every chain,
+then the all-SNP calls) and each batch receives its which_haps_to_use from the previous one ON THE DEVICE
+(quilt_gpu_batch_chain_select) — hapProbs_t of the intermediate calls never travel to the host.  Workload at N = 1 = the configuration the metric is quoted on:
 chr20 2 Mb (+2x0.5 Mb buffer) at 1x, K = 4096 of a 5008-haplotype panel, 32 000 common / 96 000 total SNPs.
 Samples shard across ranks (weak scaling: the per-GPU batch is fixed); the only collectives are the one-time
 NCCL broadcast of the prepared reference and the max-reduction of the timed region.
@@ -133,6 +136,68 @@ def build_inputs(wl, rank, world_obj, log):
     return calls
 
 
+def split_stages(calls, wl):
+    """calls come chain-major (schedule.sample_calls: per chain n_seek_its common-SNP calls [+ the all-SNP call]); stage s holds
+    call s of every chain.  Intermediate common-SNP calls keep their probabilities on the device (only the last common call and
+    the all-SNP call of a chain are averaged by the caller, functions.R:999-1020 with n_burn_in_seek_its = 2)."""
+    from quilt_b200 import cabi
+
+    per_chain = 4 if wl["factor"] > 0 else 3
+    stages = [calls[s::per_chain] for s in range(per_chain)]
+    for s in range(2):
+        for c in stages[s]:
+            c.flags |= cabi.F_OUTPUT_NO_PROBS
+    return stages
+
+
+class ChainedStep:
+    """the staged batches of one step and the device-resident chain call -> select -> call -> select -> call -> select -> all-SNP call"""
+
+    def __init__(self, lib, stages, seed):
+        from quilt_b200 import api
+
+        self.lib = lib
+        self.stages = stages
+        self.batches = [api.Batch(lib, st) for st in stages]
+        rng = np.random.default_rng(seed)
+        self.pad = [rng.random(len(stages[s]) * stages[s + 1][0].K) for s in range(len(stages) - 1)]
+
+    def run(self):
+        for s, b in enumerate(self.batches):
+            if s > 0:
+                self.batches[s - 1].chain_select_into(b, self.pad[s - 1])
+            b.run()
+        for b in self.batches:
+            b.sync()  # (the elapsed times of a batch's events are read at sync)
+
+    def timing(self):
+        t = {"total_ms": 0.0, "sweep_ms": 0.0, "n_sweep_launches": 0, "select_ms": 0.0}
+        for s, b in enumerate(self.batches):
+            tm = b.timing()
+            t["total_ms"] += tm["total_ms"]
+            t["sweep_ms"] += tm["sweep_ms"]
+            t["n_sweep_launches"] += tm["n_sweep_launches"]
+            if s > 0:
+                t["select_ms"] += b.chain_ms()
+        t["total_ms"] += t["select_ms"]
+        return t
+
+    def bytes(self):
+        out = {"h2d_bytes": 0, "d2h_bytes": 0, "sweep_algorithmic_bytes": 0.0}
+        for b in self.batches:
+            for k, v in b.bytes().items():
+                out[k] += v
+        out["h2d_bytes"] += int(sum(p.nbytes for p in self.pad))
+        return out
+
+    def fetch(self):
+        return [b.fetch() for b in self.batches]
+
+    def free(self):
+        for b in self.batches:
+            b.free()
+
+
 def cpu_checker(prefer: str = "reference"):
     """-> (library object with .gibbs(call), kind).  "reference" = oracle/_ref (the reference's own sources compiled against
     the RcppArmadillo stand-in), "port" = the oracle restatement.  Test / baseline infrastructure only."""
@@ -156,17 +221,40 @@ def host_cores() -> int:
         return os.cpu_count() or 1
 
 
-def parity_gate(calls, results, log, prefer="reference"):
-    """CPU checker vs the GPU outputs on the given calls (one whole sample): exact labels / H_class / GT, DS and GP to 1e-4."""
+def parity_gate(step, n_chains, log, prefer="reference"):
+    """One whole sample (the first n_chains jobs of every stage) re-done on the CPU, stage by stage like the device chain: the CPU
+    checker runs the Gibbs calls (exact labels / H_class / GT, DS and GP to 1e-4 against the GPU outputs that are shipped), the oracle's
+    selection section re-derives every haplotype list from the CPU's own hapProbs_t and it must equal the list the device wrote."""
     from concurrent.futures import ThreadPoolExecutor
 
+    from oracle.oracle_py import Oracle
+
     chk, kind = cpu_checker(prefer)
-    threads = max(1, min(host_cores(), len(calls)))
+    orc = Oracle()
+    threads = max(1, min(host_cores(), n_chains))
     t0 = time.perf_counter()
-    with ThreadPoolExecutor(max_workers=threads) as ex:
-        ref = list(ex.map(chk.gibbs, calls))
+    gpu_res = step.fetch()
+    calls, results, ref = [], [], []
+    sel_mismatch, sel_checked = 0, 0
+    prev_cpu = None
+    for s, st in enumerate(step.stages):
+        cs = st[:n_chains]
+        if s > 0:
+            K = cs[0].K
+            for j, c in enumerate(cs):
+                dev_list = step.batches[s].which_haps(j)
+                want = orc.select_haps_padded(c.panel, prev_cpu[j].hapProbs_t, K, step.pad[s - 1][j * K:(j + 1) * K], nHap=2 if c.ff == 0 else 3)
+                sel_checked += 1
+                sel_mismatch += int(not np.array_equal(dev_list, want))
+                c.which_haps_to_use = dev_list  # the CPU call below runs on the list the device used
+        with ThreadPoolExecutor(max_workers=threads) as ex:
+            cpu = list(ex.map(chk.gibbs, cs))
+        prev_cpu = cpu
+        calls += cs
+        results += gpu_res[s][:n_chains]
+        ref += cpu
     gate = {"calls": len(calls), "checker": kind, "label_mismatches": 0, "H_class_mismatches": 0, "gt_mismatches": 0, "underflow_mismatches": 0,
-            "max_dDS": 0.0, "max_dGP": 0.0, "tolerance": 1e-4}
+            "max_dDS": 0.0, "max_dGP": 0.0, "tolerance": 1e-4, "selections_checked": sel_checked, "selection_mismatches": sel_mismatch}
     for c, g, o in zip(calls, results, ref):
         if bool(g.underflow_problem) != bool(o.underflow_problem):
             gate["underflow_mismatches"] += 1
@@ -175,13 +263,17 @@ def parity_gate(calls, results, log, prefer="reference"):
             continue
         gate["label_mismatches"] += int(np.sum(g.H != o.H))
         gate["H_class_mismatches"] += int(np.sum(g.H_class != o.H_class))
+        from quilt_b200 import cabi as _cabi
+
+        if c.flags & _cabi.F_OUTPUT_NO_PROBS:
+            continue  # probabilities of intermediate calls stay on the device; the NEXT stage's list check covers them
         gate["gt_mismatches"] += int(np.sum(np.argmax(g.genProbsM_t, axis=0) != np.argmax(o.genProbsM_t, axis=0)))
         nh = 2 if c.ff == 0 else 3
         gate["max_dDS"] = max(gate["max_dDS"], float(np.max(np.abs(g.hapProbs_t[:nh].sum(0) - o.hapProbs_t[:nh].sum(0)))))
         gate["max_dGP"] = max(gate["max_dGP"], float(np.max(np.abs(g.genProbsM_t - o.genProbsM_t))), float(np.max(np.abs(g.genProbsF_t - o.genProbsF_t))))
     gate["seconds"] = time.perf_counter() - t0
     gate["passed"] = (gate["label_mismatches"] == 0 and gate["H_class_mismatches"] == 0 and gate["gt_mismatches"] == 0 and gate["underflow_mismatches"] == 0
-                      and gate["max_dDS"] <= 1e-4 and gate["max_dGP"] <= 1e-4)
+                      and gate["selection_mismatches"] == 0 and gate["max_dDS"] <= 1e-4 and gate["max_dGP"] <= 1e-4)
     log(f"parity gate ({kind}, {threads} threads, {gate['seconds']:.1f}s): {gate}")
     return gate
 
@@ -331,20 +423,19 @@ def main():
     calls = build_inputs(wl, rank, w, log)
     n_samples = wl["samples"]
 
-    # ---- staged batch: inputs resident in HBM
+    # ---- staged batches: inputs resident in HBM; the haplotype lists of stages 2 .. 4 are produced on the device
     t0 = time.time()
-    batch = api.Batch(lib, calls)
+    stages = split_stages(calls, wl)
+    batch = ChainedStep(lib, stages, 4242 + rank)
     nbytes = batch.bytes()
-    log(f"staged {len(calls)} calls: h2d {nbytes['h2d_bytes'] / 1e9:.2f} GB in {time.time() - t0:.1f}s")
+    log(f"staged {len(calls)} calls in {len(stages)} chained batches: h2d {nbytes['h2d_bytes'] / 1e9:.2f} GB in {time.time() - t0:.1f}s")
     for i in range(args.warmup):
         batch.run()
-        batch.sync()
         log(f"warmup {i}: {batch.timing()['total_ms']:.1f} ms")
     # ---- parity gate (rank 0, its first sample): nothing below counts unless the GPU outputs match the CPU checker
     gate = None
     if rank == 0 and not args.no_parity_gate:
-        cps = config["calls_per_sample"]
-        gate = parity_gate(calls[:cps], batch.fetch()[:cps], log, args.cpu_impl)
+        gate = parity_gate(batch, 8, log, args.cpu_impl)
     dist.barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -352,14 +443,14 @@ def main():
     torch.cuda.synchronize()
     n0 = lib.kernel_launches()
     wall0 = time.perf_counter()
-    dev_ms, sweep_ms, sweep_launches = 0.0, 0.0, 0
+    dev_ms, sweep_ms, sweep_launches, select_ms = 0.0, 0.0, 0, 0.0
     for i in range(args.steps):
         batch.run()
-        batch.sync()
         tm = batch.timing()
         dev_ms += tm["total_ms"]
         sweep_ms += tm["sweep_ms"]
         sweep_launches += tm["n_sweep_launches"]
+        select_ms += tm["select_ms"]
     torch.cuda.synchronize()
     dist.barrier()
     wall_ms = 1e3 * (time.perf_counter() - wall0)
@@ -385,26 +476,34 @@ def main():
         "peak_source": peak_src,
         "algorithmic_bytes_per_launch": alg_bytes_per_run / max(launches_per_run, 1),
         "avg_launch_ms": 1e3 * avg_launch_s, "launches_per_step": launches_per_run, "share_of_step": sweep_ms / dev_ms,
+        "selection_ms_per_step": select_ms / args.steps,
         "note": "algorithmic bytes follow SURVEY.md §8(d) (dense fp64 eMatRead columns counted); the kernel moves fewer bytes "
                 "because emission columns are rebuilt from 2^nb-entry tables + bit-packed alleles, see DESIGN.md",
     }
+    batch_pad = batch.pad
     batch.free()
 
     # ---- e2e: host buffers in, host buffers out, every step
     # the caller's result buffers exist before the timed region (allocated and touched once, as a host that processes
     # batch after batch would keep them); everything else of the call is timed: job preparation, pinned staging, H2D,
     # kernels, D2H, unpacking into the caller's arrays
-    prep = lib.prepare(calls, touch=True)
+    # every step: the whole chain through quilt_gpu_gibbs_chain with HOST buffers — per stage job preparation, pinned staging, H2D,
+    # device-side selection of the haplotype lists from the previous stage, kernels, D2H, unpacking into the caller's arrays, one wave
+    # pipeline across the stages; the caller's argument / result structures exist before the timed region (a host that processes
+    # batch after batch keeps them, like R keeps its per-worker scratch, quilt.R:731-762)
+    preps = [lib.prepare(st, touch=True) for st in stages]
     e2e_s = []
+    n_under = 0
     for i in range(max(1, args.e2e_steps)):
         dist.barrier()
         t0 = time.perf_counter()
-        res = lib.run_prepared(prep)
+        res = api.run_chain_prepared(lib, preps, batch_pad)
         e2e_s.append(time.perf_counter() - t0)
+        n_under = sum(int(r.underflow_problem) for st_res in res for r in st_res)
     e2e_step = dist.max_over_ranks(statistics.mean(e2e_s))
-    n_under = sum(int(r.underflow_problem) for r in res)
     e2e = {"value": total_samples / e2e_step, "unit": "samples/s", "h2d_bytes_per_step": nbytes["h2d_bytes"], "d2h_bytes_per_step": nbytes["d2h_bytes"],
-           "ms_per_step": 1e3 * e2e_step, "steps": len(e2e_s), "underflow_calls": n_under}
+           "ms_per_step": 1e3 * e2e_step, "steps": len(e2e_s), "underflow_calls": n_under,
+           "path": "quilt_gpu_gibbs_chain: all stages of the call chain in one call (host buffers in / out, one wave pipeline, lists selected on the device)"}
     log(f"e2e: {1e3 * e2e_step:.1f} ms/step")
 
     cb = None

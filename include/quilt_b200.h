@@ -21,6 +21,10 @@
  *                                    QUILT/src/gibbs-small.cpp:69-105
  *   quilt_gpu_forward_backward    <- Rcpp_run_forward_haploid / Rcpp_run_backward_haploid
  *                                    QUILT/src/copied-from-stitch.cpp:340-409
+ *   quilt_gpu_haploid_dosage_versus_refs / _batch
+ *                                 <- Rcpp_haploid_dosage_versus_refs (full-panel haploid Li-Stephens pass)
+ *                                    QUILT/src/reference-single.cpp:2189-2413 (forward :878-1131, backward :1781-2179,
+ *                                    eMatDH :272-329, top matches :196-266), .Call seam QUILT/R/functions.R:2034-2070
  *   quilt_gpu_select_haps         <- select_new_haps_mspbwt_v3 (heuristic_approach "A")
  *                                    QUILT/R/mspbwt.R:230-474, called at QUILT/R/functions.R:856-868
  *
@@ -67,6 +71,8 @@ extern "C" {
 #define QUILT_F_USE_SMOOTH_CM_IN_BLOCK_GIBBS (1u << 10)
 #define QUILT_F_RETURN_ALPHA                 (1u << 11)  /* debug: copy alpha/beta/c/eMatGrid out */
 #define QUILT_F_RETURN_EXTRA                 (1u << 12)  /* debug: copy eMatRead_t out            */
+#define QUILT_F_OUTPUT_NO_PROBS              (1u << 14)  /* hapProbs_t / genProbs*_t stay on the device (intermediate call of a
+                                                            device-resident chain, quilt_gpu_batch_chain_select): not copied out */
 #define QUILT_F_GIBBS_INITIALIZE_AT_FIRST_READ (1u << 13) /* first_read_for_gibbs_initialization is 0 and is not drawn (gibbs-nipt.cpp:2846) */
 
 /* production flag word for QUILT2 diploid common-SNP calls (functions.R:620-706) */
@@ -238,8 +244,62 @@ int quilt_gpu_select_haps(const QuiltSelectArgs* args, int32_t* which_haps_to_us
  * ([n_jobs x Ksubset] uniforms; statistically what sample() does at mspbwt.R:381-399, not R's bit stream).        */
 int quilt_gpu_batch_chain_select(QuiltGpuBatch* prev, QuiltGpuBatch* next, int32_t mspbwt_nindices, int32_t mspbwtL, int32_t mspbwtM,
                                  const double* pad_unif);
+/* The same link with HOST buffers: quilt_gpu_gibbs_batch (waves pipelined: H2D / kernels / D2H overlap) whose calls take their
+ * which_haps_to_use from the device-resident results of `prev` (NULL: the lists in args are used).  With `kept` non-NULL the
+ * batch object survives the call (results resident on the device) so that it can be `prev` of the next link; free it with
+ * quilt_gpu_batch_free. */
+int quilt_gpu_gibbs_batch_chained(int32_t n, const QuiltGibbsArgs* args, QuiltGibbsOut* out, QuiltGpuBatch* prev, int32_t mspbwt_nindices,
+                                  int32_t mspbwtL, int32_t mspbwtM, const double* pad_unif, QuiltGpuBatch** kept);
+/* The whole chain in ONE call: stage s holds call s of every (sample, chain) pair (args[s][0 .. n), out[s][0 .. n)); from stage 1 on
+ * the lists come from stage s - 1 on the device (pad_unif[s - 1]: [n x Ksubset]).  A single wave pipeline spans the stages: the
+ * host prepares stage s + 1 and unpacks stage s while the GPU computes. */
+int quilt_gpu_gibbs_chain(int32_t n_stages, int32_t n, const QuiltGibbsArgs* const* args, QuiltGibbsOut* const* out, int32_t mspbwt_nindices,
+                          int32_t mspbwtL, int32_t mspbwtM, const double* const* pad_unif);
+/* device time (ms, CUDA events on the library stream) of the chained selection that filled this batch's lists */
+int quilt_gpu_batch_chain_timing(QuiltGpuBatch* batch, double* chain_ms);
 /* the haplotype list job `job` of a staged batch currently holds on the device (after a chained selection: the new list) */
 int quilt_gpu_batch_which_haps(QuiltGpuBatch* batch, int32_t job, int32_t* which_haps_to_use /*[Ksubset]*/);
+
+/*
+ * Full-panel haploid pass (QUILT1 / use_mspbwt = FALSE, truth-haplotype diagnostics): one haplotype's genotype likelihoods
+ * against ALL K_full panel haplotypes, per-grid emissions looked up from the (nMaxDH + 1)-entry table eMatDH by the
+ * hapMatcherR byte, "special" haplotypes (symbol 0) recomputed from their bits, lazy normalisation of the forward
+ * variables (only when the running minimum emission drops below the threshold), dosage through per-symbol gamma sums,
+ * best-matching haplotypes at the thinned grids.  Production settings (functions.R:2034-2070): use_eMatDH, hapMatcherR,
+ * special symbols, always_normalize = FALSE, normalize_emissions = TRUE, the "version 3" kernels.
+ */
+#define QUILT_HF_RETURN_DOSAGE   (1u << 0)
+#define QUILT_HF_RETURN_BETAHAT  (1u << 1)
+#define QUILT_HF_RETURN_GAMMA    (1u << 2)
+#define QUILT_HF_GET_BEST_HAPS   (1u << 3)   /* get_best_haps_from_thinned_sites */
+#define QUILT_HF_RETURN_ALPHAHAT (1u << 4)   /* (R passes full_alphaHat_t as scratch and may read it back) */
+typedef struct QuiltHaploidArgs {
+    const QuiltPanel* panel;
+    const double* gl;                        /* [2 x nSNPs] (ref, alt) likelihoods per SNP: make_gl_from_u_bq, reference-single.R:19-42 */
+    const double* transMatRate_t;            /* [2 x (nGrids - 1)] row 0 = no recombination, row 1 = recombination              */
+    const int32_t* gammaSmall_cols_to_get;   /* [nGrids] -1, or the 0-based thinned column collecting best haplotypes (quilt.R:719-721) */
+    int32_t n_thinned;                       /* number of thinned columns (max of the above + 1)                                 */
+    int32_t K_top_matches;                   /* 5 (quilt.R:115)                                                                  */
+    int32_t best_cap;                        /* capacity per thinned column of the best-haplotype outputs (ties can exceed K_top_matches) */
+    double  min_emission_prob_normalization_threshold;   /* 1e-100                                                                */
+    uint32_t flags;
+} QuiltHaploidArgs;
+typedef struct QuiltHaploidOut {
+    double* dosage;              /* [nSNPs]                 (QUILT_HF_RETURN_DOSAGE)                                   */
+    double* c;                   /* [nGrids]                                                                            */
+    double* alphaHat_t;          /* [K_full x nGrids]       (QUILT_HF_RETURN_ALPHAHAT) lazily normalised forward variables */
+    double* betaHat_t;           /* [K_full x nGrids]       (QUILT_HF_RETURN_BETAHAT)                                  */
+    double* gamma_t;             /* [K_full x nGrids]       (QUILT_HF_RETURN_GAMMA)                                    */
+    int32_t* best_haps;          /* [n_thinned x best_cap] 0-based haplotypes with gamma >= the K_top_matches-th largest, in haplotype order */
+    double*  best_haps_values;   /* [n_thinned x best_cap] their gamma                                                 */
+    int32_t* best_haps_count;    /* [n_thinned] how many qualified (entries beyond best_cap are dropped)               */
+} QuiltHaploidOut;
+int quilt_gpu_haploid_dosage_versus_refs(const QuiltHaploidArgs* args, QuiltHaploidOut* out);
+/* n independent passes over one panel (the haplotypes of many samples / chains): one CTA per pass */
+int quilt_gpu_haploid_dosage_versus_refs_batch(int32_t n, const QuiltHaploidArgs* args, QuiltHaploidOut* out);
+/* device time (ms) of the last batch call's kernels and the ALGORITHMIC bytes they stand for: per pass
+ * K_full * nGrids * (2 x 1 symbol byte + 8 alphaHat written + 8 alphaHat read) (+ 8 per returned matrix element) */
+int quilt_gpu_haploid_last_timing(double* kernel_ms, double* algorithmic_bytes);
 
 /* component entry points (parity tests of the individual reference functions) */
 int quilt_gpu_make_eMatRead_t(const QuiltGibbsArgs* args, double* eMatRead_t /*[K x nReads]*/,

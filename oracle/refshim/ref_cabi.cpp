@@ -16,6 +16,7 @@
 // the uniforms the flat ABI carries, replayed in the reference's own draw order; a draw the script does not
 // expect raises an error, so a stream misalignment cannot pass silently.
 #include <RcppArmadillo.h>
+#include <RcppEigen.h>
 
 #include <deque>
 #include <mutex>
@@ -63,6 +64,17 @@ void rcpp_initialize_gibbs_forward_backward(const arma::cube& alphaMatCurrent_tc
                                             const arma::mat& priorCurrent_m, int s, arma::mat& alphaHat_t, arma::mat& betaHat_t,
                                             arma::rowvec& c, arma::mat& eMatGrid_t, const bool run_fb_subset,
                                             const Rcpp::NumericVector alphaStart, const Rcpp::NumericVector betaEnd);
+
+void Rcpp_haploid_dosage_versus_refs(
+    const arma::mat& gl, arma::mat& arma_alphaHat_t, Eigen::Map<Eigen::MatrixXd> eigen_alphaHat_t, arma::mat& betaHat_t, arma::rowvec& c,
+    arma::mat& gamma_t, arma::mat& gammaSmall_t, Rcpp::List& best_haps_stuff_list, Rcpp::NumericVector& dosage, const arma::mat& transMatRate_t,
+    const arma::imat& rhb_t, double ref_error, const bool use_eMatDH, arma::imat& distinctHapsB, arma::mat& distinctHapsIE,
+    Rcpp::IntegerMatrix& eMatDH_special_matrix_helper, Rcpp::IntegerMatrix& eMatDH_special_matrix, const bool use_eMatDH_special_symbols,
+    arma::imat& hapMatcher, Rcpp::RawMatrix& hapMatcherR, bool use_hapMatcherR, Rcpp::IntegerVector& gammaSmall_cols_to_get,
+    const Rcpp::IntegerVector& eMatDH_special_grid_which, const Rcpp::List& eMatDH_special_values_list, const int K_top_matches,
+    const int suppressOutput, const double min_emission_prob_normalization_threshold, bool return_betaHat_t, bool return_dosage,
+    bool return_gamma_t, bool return_gammaSmall_t, bool get_best_haps_from_thinned_sites, bool is_version_2, bool is_version_3,
+    bool return_extra, bool always_normalize, bool use_eigen, const bool normalize_emissions);
 
 Rcpp::IntegerVector rcpp_int_expand(arma::ivec& hapc, const int nSNPs);
 int rcpp_simple_binary_matrix_search(int val, Rcpp::IntegerMatrix mat, int s1, int e1);
@@ -383,6 +395,67 @@ int quilt_ref_forward_backward(int32_t K, int32_t nGrids, const double* eMatGrid
         rcpp_initialize_gibbs_forward_backward(alphaMatCurrent_tc, transMatRate_tc_H, priorCurrent_m, 0, alphaHat_t, betaHat_t, c, eMatGrid_t,
                                                false, Rcpp::NumericVector(0), Rcpp::NumericVector(0));
         std::memcpy(c_out, c.memptr(), sizeof(double) * (size_t)nGrids);
+        return QUILT_OK;
+    });
+}
+
+
+// Rcpp_haploid_dosage_versus_refs with the production settings of functions.R:2034-2070 (use_eigen = TRUE -> the "version 3"
+// forward / backward, always_normalize = FALSE, normalize_emissions = TRUE, hapMatcherR + special symbols)
+int quilt_ref_haploid_dosage_versus_refs(const QuiltHaploidArgs* a, QuiltHaploidOut* o) {
+    if (!a || !o || !a->panel || !a->gl || !a->transMatRate_t) return QUILT_ERR_BAD_ARG;
+    return guarded([&]() -> int {
+        const QuiltPanel* p = a->panel;
+        const int K = p->K_full, T = p->nGrids, nS = p->nSNPs;
+        PanelObjects P(p, false, 0, nullptr);
+        arma::imat hapMatcher((arma::uword)K, 1);   // only its row count is read when hapMatcherR is in use (:2256)
+        arma::mat gl(const_cast<double*>(a->gl), 2, (arma::uword)nS, true);
+        arma::mat transMatRate_t(const_cast<double*>(a->transMatRate_t), 2, (arma::uword)(T - 1), true);
+        arma::mat arma_alphaHat_t(1, 1);
+        std::vector<double> alpha((size_t)K * T, 0.0);
+        Eigen::Map<Eigen::MatrixXd> eigen_alphaHat_t(alpha.data(), K, T);
+        const bool want_beta = (a->flags & QUILT_HF_RETURN_BETAHAT) != 0, want_gamma = (a->flags & QUILT_HF_RETURN_GAMMA) != 0;
+        const bool want_dosage = (a->flags & QUILT_HF_RETURN_DOSAGE) != 0, want_best = (a->flags & QUILT_HF_GET_BEST_HAPS) != 0;
+        arma::mat betaHat_t = want_beta ? arma::mat((arma::uword)K, (arma::uword)T) : arma::mat(1, 1);
+        arma::mat gamma_t = want_gamma ? arma::mat((arma::uword)K, (arma::uword)T) : arma::mat(1, 1);
+        arma::mat gammaSmall_t(1, 1);
+        arma::rowvec c((arma::uword)T);
+        c.fill(1.0);   // functions.R:2024
+        Rcpp::NumericVector dosage(nS);
+        Rcpp::IntegerVector cols(T);
+        for (int g = 0; g < T; ++g) cols[g] = a->gammaSmall_cols_to_get ? a->gammaSmall_cols_to_get[g] : -1;
+        Rcpp::List best(a->n_thinned > 0 ? a->n_thinned : 0);
+        // eMatDH_special_grid_which: 1-based index of the grid among the grids that hold special haplotypes, else 0
+        Rcpp::IntegerVector grid_which(T);
+        int n_sp_grids = 0;
+        for (int g = 0; g < T; ++g) {
+            const int s1 = p->eMatDH_special_matrix_helper[g], e1 = p->eMatDH_special_matrix_helper[T + g];
+            grid_which[g] = (s1 > 0 && e1 >= s1) ? ++n_sp_grids : 0;
+        }
+        Rcpp::List special_values_list(0);
+        arma::imat rhb_t(1, 1);
+        Rcpp_haploid_dosage_versus_refs(gl, arma_alphaHat_t, eigen_alphaHat_t, betaHat_t, c, gamma_t, gammaSmall_t, best, dosage, transMatRate_t, rhb_t,
+                                        p->ref_error, true, P.distinctHapsB, P.distinctHapsIE, P.special_helper, P.special_matrix, true, hapMatcher,
+                                        P.hapMatcherR, true, cols, grid_which, special_values_list, a->K_top_matches, 1,
+                                        a->min_emission_prob_normalization_threshold, want_beta, want_dosage, want_gamma, false, want_best,
+                                        false /*is_version_2*/, false, false, false /*always_normalize*/, true /*use_eigen*/, true /*normalize_emissions*/);
+        if (o->dosage) std::memcpy(o->dosage, dosage.begin(), sizeof(double) * (size_t)nS);
+        if (o->c) std::memcpy(o->c, c.memptr(), sizeof(double) * (size_t)T);
+        if (o->alphaHat_t) std::memcpy(o->alphaHat_t, alpha.data(), sizeof(double) * alpha.size());
+        if (o->betaHat_t && want_beta) std::memcpy(o->betaHat_t, betaHat_t.memptr(), sizeof(double) * (size_t)K * T);
+        if (o->gamma_t && want_gamma) std::memcpy(o->gamma_t, gamma_t.memptr(), sizeof(double) * (size_t)K * T);
+        if (want_best && o->best_haps_count) {
+            for (int t = 0; t < a->n_thinned; ++t) {
+                Rcpp::List e = Rcpp::as<Rcpp::List>(best[t]);
+                Rcpp::IntegerVector tm = Rcpp::as<Rcpp::IntegerVector>(e["top_matches"]);
+                Rcpp::NumericVector tv = Rcpp::as<Rcpp::NumericVector>(e["top_matches_values"]);
+                o->best_haps_count[t] = tm.size();
+                for (int i = 0; i < tm.size() && i < a->best_cap; ++i) {
+                    if (o->best_haps) o->best_haps[(size_t)t * a->best_cap + i] = tm[i];
+                    if (o->best_haps_values) o->best_haps_values[(size_t)t * a->best_cap + i] = tv[i];
+                }
+            }
+        }
         return QUILT_OK;
     });
 }

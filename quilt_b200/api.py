@@ -63,6 +63,13 @@ class GpuLib(cabi._LibAPI):
         L.quilt_gpu_release_panel_cache.restype = None
         L.quilt_gpu_batch_chain_select.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_double)]
         L.quilt_gpu_batch_chain_select.restype = C.c_int
+        L.quilt_gpu_gibbs_batch_chained.argtypes = [C.c_int32, pa, po, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_double),
+                                                   C.POINTER(C.c_void_p)]
+        L.quilt_gpu_gibbs_batch_chained.restype = C.c_int
+        L.quilt_gpu_gibbs_chain.argtypes = [C.c_int32, C.c_int32, C.POINTER(pa), C.POINTER(po), C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.POINTER(C.c_double))]
+        L.quilt_gpu_gibbs_chain.restype = C.c_int
+        L.quilt_gpu_batch_chain_timing.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+        L.quilt_gpu_batch_chain_timing.restype = C.c_int
         L.quilt_gpu_batch_which_haps.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_int32)]
         L.quilt_gpu_batch_which_haps.restype = C.c_int
 
@@ -118,6 +125,55 @@ class GpuLib(cabi._LibAPI):
         return res
 
 
+class KeptBatch:
+    """Handle of a batch whose results stay resident on the device after a host-buffer call (the `prev` of the next chained call)."""
+
+    def __init__(self, lib: GpuLib, handle):
+        self.lib, self._h = lib, handle
+
+    def free(self):
+        if self._h:
+            self.lib.lib.quilt_gpu_batch_free(self._h)
+            self._h = None
+
+
+def run_prepared_chained(lib: GpuLib, prep, prev: Optional[KeptBatch], pad_unif, keep: bool, mspbwt_nindices=4, mspbwtL=3, mspbwtM=1):
+    """quilt_gpu_gibbs_batch_chained: host buffers in / out with per-wave pipelining; the calls' haplotype lists come from the device-resident
+    results of `prev` (None: from the arguments).  -> (results, KeptBatch or None)"""
+    calls, args, outs, res = prep
+    kept = C.c_void_p()
+    pu = None if pad_unif is None else np.ascontiguousarray(pad_unif, dtype=np.float64)
+    lib._check(lib.lib.quilt_gpu_gibbs_batch_chained(len(calls), args, outs, prev._h if prev is not None else None, mspbwt_nindices, mspbwtL, mspbwtM,
+                                                     cabi._ptr(pu, cabi._pd), C.byref(kept) if keep else None), "quilt_gpu_gibbs_batch_chained")
+    for i, r in enumerate(res):
+        r.underflow_problem = bool(outs[i].underflow_problem)
+        r.n_unif_consumed = int(outs[i].n_unif_consumed)
+        r.underflow_iteration = int(outs[i].underflow_iteration)
+    return res, (KeptBatch(lib, kept) if keep and kept.value else None)
+
+
+def run_chain_prepared(lib: GpuLib, preps, pads, mspbwt_nindices=4, mspbwtL=3, mspbwtM=1):
+    """quilt_gpu_gibbs_chain: all stages of the call chain in one call (host buffers in / out).  preps: one lib.prepare(...) per stage;
+    pads: [n x Ksubset] uniforms per link.  -> list of result lists"""
+    ns = len(preps)
+    n = len(preps[0][0])
+    pa, po = C.POINTER(cabi.QuiltGibbsArgs), C.POINTER(cabi.QuiltGibbsOut)
+    a_arr = (pa * ns)(*[C.cast(p[1], pa) for p in preps])
+    o_arr = (po * ns)(*[C.cast(p[2], po) for p in preps])
+    pus = [np.ascontiguousarray(x, dtype=np.float64) for x in pads]
+    pd = C.POINTER(C.c_double)
+    p_arr = (pd * max(ns - 1, 1))(*[cabi._ptr(x, cabi._pd) for x in pus])
+    lib._check(lib.lib.quilt_gpu_gibbs_chain(ns, n, a_arr, o_arr, mspbwt_nindices, mspbwtL, mspbwtM, p_arr), "quilt_gpu_gibbs_chain")
+    out = []
+    for calls, args, outs, res in preps:
+        for i, r in enumerate(res):
+            r.underflow_problem = bool(outs[i].underflow_problem)
+            r.n_unif_consumed = int(outs[i].n_unif_consumed)
+            r.underflow_iteration = int(outs[i].underflow_iteration)
+        out.append(res)
+    return out
+
+
 class Batch:
     """Staged form: inputs resident in HBM after __init__, `run()` only launches kernels."""
 
@@ -165,6 +221,11 @@ class Batch:
         assert pu.size >= len(self.calls) * nxt.calls[0].K
         self.lib._check(self.lib.lib.quilt_gpu_batch_chain_select(self._h, nxt._h, mspbwt_nindices, mspbwtL, mspbwtM, cabi._ptr(pu, cabi._pd)),
                         "quilt_gpu_batch_chain_select")
+
+    def chain_ms(self) -> float:
+        v = C.c_double()
+        self.lib._check(self.lib.lib.quilt_gpu_batch_chain_timing(self._h, C.byref(v)), "quilt_gpu_batch_chain_timing")
+        return v.value
 
     def which_haps(self, job: int) -> np.ndarray:
         out = np.zeros(self.calls[job].K, dtype=np.int32)

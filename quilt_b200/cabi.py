@@ -28,6 +28,7 @@ F_USE_SMOOTH_CM_IN_BLOCK_GIBBS = 1 << 10
 F_RETURN_ALPHA = 1 << 11
 F_RETURN_EXTRA = 1 << 12
 F_GIBBS_INITIALIZE_AT_FIRST_READ = 1 << 13
+F_OUTPUT_NO_PROBS = 1 << 14
 
 FLAGS_QUILT2_DIPLOID = (
     F_SAMPLE_IS_DIPLOID
@@ -142,6 +143,36 @@ class QuiltSelectArgs(C.Structure):
         ("mspbwt_nindices", C.c_int32),
         ("mspbwtL", C.c_int32),
         ("mspbwtM", C.c_int32),
+    ]
+
+
+HF_RETURN_DOSAGE, HF_RETURN_BETAHAT, HF_RETURN_GAMMA, HF_GET_BEST_HAPS, HF_RETURN_ALPHAHAT = 1, 2, 4, 8, 16
+
+
+class QuiltHaploidArgs(C.Structure):
+    _fields_ = [
+        ("panel", C.POINTER(QuiltPanel)),
+        ("gl", _pd),
+        ("transMatRate_t", _pd),
+        ("gammaSmall_cols_to_get", _pi),
+        ("n_thinned", C.c_int32),
+        ("K_top_matches", C.c_int32),
+        ("best_cap", C.c_int32),
+        ("min_emission_prob_normalization_threshold", C.c_double),
+        ("flags", C.c_uint32),
+    ]
+
+
+class QuiltHaploidOut(C.Structure):
+    _fields_ = [
+        ("dosage", _pd),
+        ("c", _pd),
+        ("alphaHat_t", _pd),
+        ("betaHat_t", _pd),
+        ("gamma_t", _pd),
+        ("best_haps", _pi),
+        ("best_haps_values", _pd),
+        ("best_haps_count", _pi),
     ]
 
 
@@ -495,6 +526,41 @@ class _LibAPI:
         if rc != OK:
             raise RuntimeError(f"{self.prefix}_select_haps failed with status {rc}: {self.last_error()}")
         return which[: nf.value].copy(), nu.value
+
+    def haploid_dosage(self, panel: Panel, gl, transMatRate_t, cols_to_get=None, K_top_matches=5, best_cap=32, threshold=1e-100,
+                       flags=HF_RETURN_DOSAGE | HF_RETURN_BETAHAT | HF_RETURN_GAMMA | HF_RETURN_ALPHAHAT):
+        """Rcpp_haploid_dosage_versus_refs (reference-single.cpp:2189-2413) for one haplotype; -> dict of outputs"""
+        fn = getattr(self.lib, f"{self.prefix}_haploid_dosage_versus_refs")
+        fn.argtypes = [C.POINTER(QuiltHaploidArgs), C.POINTER(QuiltHaploidOut)]
+        fn.restype = C.c_int
+        glf, tm = f64(gl), f64(transMatRate_t)
+        K, T, nS = panel.K_full, panel.nGrids, panel.nSNPs
+        assert glf.shape == (2, nS) and tm.shape == (2, T - 1)
+        cols = np.full(T, -1, dtype=np.int32) if cols_to_get is None else np.ascontiguousarray(cols_to_get, dtype=np.int32)
+        n_thin = int(cols.max()) + 1 if cols.size and cols.max() >= 0 else 0
+        if n_thin > 0:
+            flags |= HF_GET_BEST_HAPS
+        a, o = QuiltHaploidArgs(), QuiltHaploidOut()
+        ps = panel.c_struct()
+        a.panel = C.pointer(ps)
+        a.gl, a.transMatRate_t, a.gammaSmall_cols_to_get = _ptr(glf, _pd), _ptr(tm, _pd), _ptr(cols, _pi)
+        a.n_thinned, a.K_top_matches, a.best_cap = n_thin, K_top_matches, best_cap
+        a.min_emission_prob_normalization_threshold, a.flags = threshold, flags
+        res = {"dosage": np.zeros(nS), "c": np.zeros(T)}
+        o.dosage, o.c = _ptr(res["dosage"], _pd), _ptr(res["c"], _pd)
+        for name, bit in (("alphaHat_t", HF_RETURN_ALPHAHAT), ("betaHat_t", HF_RETURN_BETAHAT), ("gamma_t", HF_RETURN_GAMMA)):
+            if flags & bit:
+                res[name] = np.zeros((K, T), order="F")
+                setattr(o, name, _ptr(res[name], _pd))
+        if n_thin > 0:
+            res["best_haps"] = np.full((n_thin, best_cap), -1, dtype=np.int32)
+            res["best_haps_values"] = np.zeros((n_thin, best_cap))
+            res["best_haps_count"] = np.zeros(n_thin, dtype=np.int32)
+            o.best_haps, o.best_haps_values, o.best_haps_count = _ptr(res["best_haps"], _pi), _ptr(res["best_haps_values"], _pd), _ptr(res["best_haps_count"], _pi)
+        rc = fn(C.byref(a), C.byref(o))
+        if rc != OK:
+            raise RuntimeError(f"{self.prefix}_haploid_dosage_versus_refs failed with status {rc}: {self.last_error()}")
+        return res
 
     def last_error(self) -> str:
         return ""

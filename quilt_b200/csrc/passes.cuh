@@ -49,102 +49,125 @@ __global__ void __launch_bounds__(256) k_init_iterative(BatchParams P, const Job
     }
 }
 
-// grid = (T, jobs), 256 threads: eMatGrid[:, g] of every haplotype = product of its reads' columns, in read order.
-// The grid's descriptors, labels and emission tables are staged in shared memory (chunked when a grid holds more
-// than MEG_MAXR reads / MEG_MAXTAB table entries); a thread keeps the three allele words a read can touch in
-// registers, so a table-mode factor costs a shift, a mask and one shared-memory load.
-constexpr int MEG_MAXR = 64;
-constexpr int MEG_MAXTAB = 1024;
+// grid = (T, jobs), 256 threads: eMatGrid[:, g] of every haplotype = product of its reads' columns, in read order
+// (rcpp_make_eMatGrid_t, bound = false).  The grid's descriptors, labels and emission tables are staged in shared memory in
+// the HOST-computed chunks the sweep kernel uses too (ginfo row of the grid, chunk fields of the descriptors: no serial scan
+// on the device); a thread works on four haplotypes at a time — their three allele words in registers, four independent
+// product chains per haplotype label — so a table-mode factor costs a shift, a mask and one shared-memory load.
 __global__ void __launch_bounds__(256) k_make_eG(BatchParams P, const JobDev* __restrict__ jobs) {
     __shared__ JobDev Js;
-    __shared__ __align__(16) ReadDesc sdesc[MEG_MAXR];
-    __shared__ double stab[MEG_MAXTAB];
-    __shared__ int sH[MEG_MAXR];
-    __shared__ int schunk[2];
+    __shared__ __align__(16) ReadDesc sdesc[SW_MAXR];
+    __shared__ double stab[SW_MAXTAB];
+    __shared__ int sH[SW_MAXR];
     const int tid = threadIdx.x;
     if (tid == 0) Js = jobs[blockIdx.y];
     __syncthreads();
     const JobDev& J = Js;
     const int g = blockIdx.x, K = P.K, Kp = P.Kp, T = P.T, NH = P.NH;
-    const int r0 = J.rs[g], r1 = J.rs[g + 1];
-    int c0 = r0;
-    uint32_t tab0 = (uint32_t)J.ts[g];
+    const int r0 = J.ginfo[4 * g], r1 = J.rs[g + 1];
+    const int n_g = r1 - r0;
+    int c0 = 0, cn = J.ginfo[4 * g + 2];
+    uint32_t tab0 = (uint32_t)J.ginfo[4 * g + 1], tend = (uint32_t)J.ginfo[4 * g + 3];
     bool first = true;
+    constexpr int G4 = 4;
     do {
-        // chunk [c0, c0 + cn) whose tables fit the staging buffer
-        __syncthreads();
-        if (tid == 0) {
-            int n = 0;
-            uint32_t tend = tab0;
-            while (c0 + n < r1 && n < MEG_MAXR) {
-                const uint32_t tn = J.desc[c0 + n].tnext;
-                if (tn - tab0 > (uint32_t)MEG_MAXTAB) break;
-                tend = tn;
-                n++;
-            }
-            schunk[0] = n;
-            schunk[1] = (int)tend;
+        if (c0 > 0) {
+            // later chunk of an over-full grid: its size / table end ride in the descriptor of its first read
+            const ReadDesc& d0 = J.desc[r0 + c0];
+            cn = d0.chunk_n;
+            tend = d0.chunk_tend;
         }
-        __syncthreads();
-        const int cn = schunk[0];
-        const uint32_t tend = (uint32_t)schunk[1];
-        for (int i = tid; i < cn * 2; i += 256) reinterpret_cast<uint4*>(sdesc)[i] = reinterpret_cast<const uint4*>(J.desc + c0)[i];
-        for (int i = tid; i < cn; i += 256) sH[i] = J.H[c0 + i];
+        __syncthreads();  // the previous chunk's staged data is no longer read
+        for (int i = tid; i < cn * 2; i += 256) reinterpret_cast<uint4*>(sdesc)[i] = reinterpret_cast<const uint4*>(J.desc + r0 + c0)[i];
+        for (int i = tid; i < cn; i += 256) sH[i] = J.H[r0 + c0 + i];
         for (int i = tid; i < (int)(tend - tab0); i += 256) stab[i] = J.tabs[tab0 + i].E;
         __syncthreads();
-        for (int k = tid; k < Kp; k += 256) {
-            double e[3] = {1.0, 1.0, 1.0};
-            if (!first) {
-                for (int h = 0; h < NH; h++) e[h] = J.eG[((size_t)h * T + g) * Kp + k];
+        for (int kb = tid; kb < Kp; kb += 256 * G4) {
+            double e[G4][3];
+            uint32_t wm[G4], w0[G4], wp[G4];
+#pragma unroll
+            for (int q = 0; q < G4; q++) {
+                const int k = kb + q * 256;
+                const bool in = k < Kp;
+                for (int h = 0; h < 3; h++) e[q][h] = (first || !in || h >= NH) ? 1.0 : J.eG[((size_t)h * T + g) * Kp + k];
+                const bool live = k < K && cn > 0;
+                wm[q] = (live && g > 0) ? J.W[(size_t)(g - 1) * Kp + k] : 0u;
+                w0[q] = live ? J.W[(size_t)g * Kp + k] : 0u;
+                wp[q] = (live && g + 1 < T) ? J.W[(size_t)(g + 1) * Kp + k] : 0u;
             }
-            if (k < K && cn > 0) {
-                const uint32_t wm = (g > 0) ? J.W[(size_t)(g - 1) * Kp + k] : 0u;
-                const uint32_t w0 = J.W[(size_t)g * Kp + k];
-                const uint32_t wp = (g + 1 < T) ? J.W[(size_t)(g + 1) * Kp + k] : 0u;
-                for (int ir = 0; ir < cn; ir++) {
-                    const uint4 dq = *reinterpret_cast<const uint4*>(sdesc + ir);
-                    const int mode = (dq.y >> 8) & 0xff, nb = (dq.y >> 16) & 0xff;
-                    double E;
-                    if (mode == MODE_DENSE) {
-                        E = J.dense[(size_t)dq.x * Kp + k].E;
-                    } else {
-                        uint32_t pat;
-                        if (mode == MODE_RUN) {
-                            const int g0rel = (int)(int8_t)(dq.y >> 24);
-                            const uint32_t b0 = dq.z & 0xff;
-                            const uint32_t lo = g0rel < 0 ? wm : (g0rel == 0 ? w0 : wp);
-                            const uint32_t hi = g0rel < 0 ? w0 : wp;
-                            pat = __funnelshift_r(lo, (b0 + nb > 32) ? hi : 0u, b0) & ((1u << nb) - 1u);
+            // (padding haplotypes K <= k < Kp carry zero words; whatever factors they pick up are discarded at the store: padding stays 1)
+            for (int ir = 0; ir < cn; ir++) {
+                const uint4 dq = *reinterpret_cast<const uint4*>(sdesc + ir);
+                const int mode = (dq.y >> 8) & 0xff, nb = (dq.y >> 16) & 0xff;
+                const int h = sH[ir] - 1;
+                double E[G4];
+                // every branch below is uniform over the CTA (it depends on the read only), so the per-haplotype work is a shift,
+                // a mask, one shared-memory load and one multiply
+                if (mode == MODE_RUN) {
+                    const int g0rel = (int)(int8_t)(dq.y >> 24);
+                    const uint32_t b0 = dq.z & 0xff, mask = (1u << nb) - 1u;
+                    const double* tb = stab + (dq.x - tab0);
+                    if (b0 + nb <= 32) {
+                        if (g0rel == 0) {
+#pragma unroll
+                            for (int q = 0; q < G4; q++) E[q] = tb[(w0[q] >> b0) & mask];
+                        } else if (g0rel < 0) {
+#pragma unroll
+                            for (int q = 0; q < G4; q++) E[q] = tb[(wm[q] >> b0) & mask];
                         } else {
-                            const uint8_t* sel = reinterpret_cast<const uint8_t*>(sdesc + ir) + 9;
-                            pat = 0;
-                            for (int q = 0; q < nb; q++) {
-                                const int wr = sel[q] >> 5, b = sel[q] & 31;
-                                const uint32_t w = wr == 0 ? wm : (wr == 1 ? w0 : wp);
-                                pat |= ((w >> b) & 1u) << q;
-                            }
+#pragma unroll
+                            for (int q = 0; q < G4; q++) E[q] = tb[(wp[q] >> b0) & mask];
                         }
-                        E = stab[dq.x - tab0 + pat];
+                    } else if (g0rel < 0) {
+#pragma unroll
+                        for (int q = 0; q < G4; q++) E[q] = tb[__funnelshift_r(wm[q], w0[q], b0) & mask];
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < G4; q++) E[q] = tb[__funnelshift_r(g0rel == 0 ? w0[q] : wp[q], wp[q], b0) & mask];
                     }
-                    const int h = sH[ir] - 1;
-                    if (h == 0)
-                        e[0] *= E;
-                    else if (h == 1)
-                        e[1] *= E;
-                    else if (h == 2)
-                        e[2] *= E;
+                } else if (mode == MODE_DENSE) {
+#pragma unroll
+                    for (int q = 0; q < G4; q++) {
+                        const int k = kb + q * 256;
+                        E[q] = (k < K) ? J.dense[(size_t)dq.x * Kp + k].E : 1.0;
+                    }
+                } else {
+                    const uint8_t* sel = reinterpret_cast<const uint8_t*>(sdesc + ir) + 9;
+                    const double* tb = stab + (dq.x - tab0);
+#pragma unroll
+                    for (int q = 0; q < G4; q++) {
+                        uint32_t pat = 0;
+                        for (int b = 0; b < nb; b++) {
+                            const int wr = sel[b] >> 5, bit = sel[b] & 31;
+                            const uint32_t w = wr == 0 ? wm[q] : (wr == 1 ? w0[q] : wp[q]);
+                            pat |= ((w >> bit) & 1u) << b;
+                        }
+                        E[q] = tb[pat];
+                    }
+                }
+                if (h == 0) {
+#pragma unroll
+                    for (int q = 0; q < G4; q++) e[q][0] *= E[q];
+                } else if (h == 1) {
+#pragma unroll
+                    for (int q = 0; q < G4; q++) e[q][1] *= E[q];
+                } else if (h == 2) {
+#pragma unroll
+                    for (int q = 0; q < G4; q++) e[q][2] *= E[q];
                 }
             }
-            for (int h = 0; h < NH; h++) J.eG[((size_t)h * T + g) * Kp + k] = e[h];
+#pragma unroll
+            for (int q = 0; q < G4; q++) {
+                const int k = kb + q * 256;
+                if (k < Kp)
+                    for (int h = 0; h < NH; h++) J.eG[((size_t)h * T + g) * Kp + k] = (k < K) ? e[q][h] : 1.0;
+            }
         }
         first = false;
         c0 += cn;
         tab0 = tend;
-        if (cn == 0 && c0 < r1) {
-            // a single read whose table exceeds the staging buffer cannot occur (2^NBMAX <= MEG_MAXTAB)
-            break;
-        }
-    } while (c0 < r1);
+        if (cn == 0) break;  // (empty grid: one pass wrote the ones)
+    } while (c0 < n_g);
 }
 
 // generic forward + backward of one haplotype.  grid = (jobs, NH).  If ext_* are given they replace the job's

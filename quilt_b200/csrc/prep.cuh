@@ -60,32 +60,36 @@ __global__ void __launch_bounds__(256) k_unpack_common(PanelDev P, const JobDev*
 }
 
 // all-SNP axis: bits of the common SNPs come from the common-axis words (rare_common.R:229-230), rare bits are
-// or-ed in afterwards by k_scatter_rare.  grid = (ceil(Kp / 256), T_all, jobs)
-__global__ void __launch_bounds__(256) k_assemble_all(PanelDev P, const JobDev* __restrict__ jobs, int K, int Kp) {
+// or-ed in afterwards by k_scatter_rare.  Where the 32 SNPs of an all-SNP grid sit on the common axis is panel-only
+// information: it is decoded ONCE per panel at upload (PanelDev::asm_src / asm_cg0: source bit inside one of the TWO
+// common-axis words an all-SNP grid can touch — 32 consecutive SNPs hold at most 32 consecutive common SNPs), so a thread
+// does two coalesced word loads and 32 shift / mask steps per grid, no dependent index loads and no barrier.
+// grid = (ceil(Kp / 256), ceil(T_all / ASM_GPB), jobs): a CTA column of 256 haplotypes walks ASM_GPB consecutive grids.
+constexpr int ASM_GPB = 8;
+__global__ void __launch_bounds__(256) k_assemble_all(PanelDev P, const JobDev* __restrict__ jobs, int K, int Kp, int T_all) {
     const JobDev& J = jobs[blockIdx.z];
-    const uint32_t* Wc = J.Wc;
-    const int G = blockIdx.y;
+    const uint32_t* __restrict__ Wc = J.Wc;
     const int k = blockIdx.x * 256 + threadIdx.x;
     if (k >= Kp) return;
-    uint32_t w = 0;
-    if (k < K) {
-        int cg_prev = -1;
-        uint32_t cw = 0;
-        for (int b = 0; b < 32; b++) {
-            const int s = 32 * G + b;
-            if (s >= P.nSNPs_all) break;
-            if (__ldg(P.snp_is_common + s)) {
-                const int cs = __ldg(P.common_snp_index + s) - 1;
-                const int cg = cs >> 5;
-                if (cg != cg_prev) {
-                    cw = Wc[(size_t)cg * Kp + k];
-                    cg_prev = cg;
-                }
-                w |= ((cw >> (cs & 31)) & 1u) << b;
+    const int G0 = blockIdx.y * ASM_GPB, G1 = min(G0 + ASM_GPB, T_all);
+    for (int G = G0; G < G1; G++) {
+        uint32_t w = 0;
+        if (k < K) {
+            const int cg0 = __ldg(P.asm_cg0 + G);
+            const uint32_t c0 = Wc[(size_t)cg0 * Kp + k];
+            const uint32_t c1 = (cg0 + 1 < P.Tc) ? Wc[(size_t)(cg0 + 1) * Kp + k] : 0u;
+            const int8_t* __restrict__ src = P.asm_src + 32 * (size_t)G;
+#pragma unroll
+            for (int b4 = 0; b4 < 32; b4 += 4) {
+                const char4 s4 = *reinterpret_cast<const char4*>(src + b4);
+                const int sv[4] = {s4.x, s4.y, s4.z, s4.w};
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+                    if (sv[q] >= 0) w |= ((((sv[q] >> 5) ? c1 : c0) >> (sv[q] & 31)) & 1u) << (b4 + q);
             }
         }
+        J.W[(size_t)G * Kp + k] = w;
     }
-    J.W[(size_t)G * Kp + k] = w;
 }
 
 // rare_per_hap_info (rare_common.R:202-322): grid = (ceil(K / 256), jobs)

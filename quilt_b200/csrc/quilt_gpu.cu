@@ -29,6 +29,7 @@
 #include "block_nipt.cuh"
 #include "passes.cuh"
 #include "select.cuh"
+#include "haploid.cuh"
 #include "prep.cuh"
 #include "sweep.cuh"
 #include "types.h"
@@ -132,24 +133,45 @@ struct BufCache {
             free_.erase(free_.begin() + best);
             return b;
         }
-        free_.clear();  // nothing fits: drop the cached ones before growing
+        // nothing fits: grow.  Several batches are alive at once in a call chain, so the other cached buffers stay (they fit the
+        // other stages); only when the cache is full does the smallest one go.
+        if (free_.size() >= CAP) {
+            int small = 0;
+            for (int i = 1; i < (int)free_.size(); i++)
+                if (free_[i]->bytes < free_[small]->bytes) small = i;
+            free_.erase(free_.begin() + small);
+        }
         std::unique_ptr<B> b(new B());
         *err = b->alloc(n);
+        if (*err != cudaSuccess) {
+            free_.clear();  // out of memory: drop everything cached and try once more
+            *err = b->alloc(n);
+        }
         return b;
     }
+    static constexpr size_t CAP = 8;
     void release(std::unique_ptr<B> b) {
         if (b && b->p) free_.push_back(std::move(b));
-        while (free_.size() > 3) free_.erase(free_.begin());
+        while (free_.size() > CAP) free_.erase(free_.begin());
     }
     void clear() { free_.clear(); }
 };
-BufCache<DBuf> g_dcache_in, g_dcache_out, g_dcache_slots;
+BufCache<DBuf> g_dcache_in, g_dcache_out;
+// The wave state (alpha / beta / eMatGrid / allele words / tables of the jobs in flight) is scratch that only lives while
+// a batch runs.  Batches run one after the other on the library stream, so ALL staged batches share one arena (grown to
+// the largest request): several batches can be staged at once — the stages of a device-resident call chain — without
+// multiplying tens of GB of state.  JobDev records are rebuilt at every run (upload_jobdevs), so the arena may move.
+DBuf g_slots;
 BufCache<HBuf> g_hcache_in, g_hcache_out;
 
 int host_threads() {
     static int n = 0;
     if (n == 0) {
         n = (int)std::thread::hardware_concurrency();
+        // one process per GPU on a shared host (torchrun sets LOCAL_WORLD_SIZE): share the cores instead of oversubscribing them
+        const char* lws = std::getenv("LOCAL_WORLD_SIZE");
+        const int ranks_here = lws ? std::max(1, std::atoi(lws)) : 1;
+        n = std::max(2, n / ranks_here);
         const char* e = std::getenv("QUILT_B200_HOST_THREADS");
         if (e) n = std::atoi(e);
         if (n < 1) n = 1;
@@ -330,8 +352,10 @@ int get_panel(const QuiltPanel* p, PanelDev* out, std::shared_ptr<PanelEntry>* k
         for (int k = 0; k < p->K_full; k++) m = std::max<int>(m, col[k]);
         n_used[(size_t)g] = std::min(m, p->nMaxDH);
     }
-    size_t b_ic = 0, b_ci = 0, b_ro = 0, b_rs = 0;
+    size_t b_ic = 0, b_ci = 0, b_ro = 0, b_rs = 0, b_as = 0, b_ac = 0;
     int64_t n_rare = 0;
+    std::vector<int8_t> asm_src;
+    std::vector<int32_t> asm_cg0;
     if (p->nSNPs_all > 0) {
         if (!p->snp_is_common || !p->common_snp_index || !p->rare_hap_offsets) return set_err(QUILT_ERR_BAD_ARG, "bad rare/common panel fields");
         n_rare = p->rare_hap_offsets[p->K_full];
@@ -339,8 +363,28 @@ int get_panel(const QuiltPanel* p, PanelDev* out, std::shared_ptr<PanelEntry>* k
         b_ci = al((size_t)p->nSNPs_all * 4);
         b_ro = al((size_t)(p->K_full + 1) * 8);
         b_rs = al((size_t)std::max<int64_t>(n_rare, 1) * 4);
+        // where the SNPs of every all-SNP grid sit on the common axis (k_assemble_all)
+        const int T_all = (p->nSNPs_all + 31) / 32;
+        asm_src.assign((size_t)T_all * 32, (int8_t)-1);
+        asm_cg0.assign((size_t)T_all, 0);
+        for (int G = 0; G < T_all; G++) {
+            int cg0 = -1;
+            for (int b = 0; b < 32; b++) {
+                const int s = 32 * G + b;
+                if (s >= p->nSNPs_all || !p->snp_is_common[s]) continue;
+                const int cs = p->common_snp_index[s] - 1;
+                if (cs < 0 || cs >= p->nSNPs) return set_err(QUILT_ERR_BAD_ARG, "common_snp_index out of range");
+                if (cg0 < 0) cg0 = cs >> 5;
+                const int wsel = (cs >> 5) - cg0;
+                if (wsel < 0 || wsel > 1) return set_err(QUILT_ERR_BAD_ARG, "common_snp_index is not increasing along the all-SNP axis");
+                asm_src[(size_t)G * 32 + b] = (int8_t)((wsel << 5) | (cs & 31));
+            }
+            asm_cg0[(size_t)G] = std::max(cg0, 0);
+        }
+        b_as = al(asm_src.size());
+        b_ac = al(asm_cg0.size() * 4);
     }
-    CK(e->buf.alloc(b_hm + b_db + b_sp + b_he + b_nu + b_ic + b_ci + b_ro + b_rs));
+    CK(e->buf.alloc(b_hm + b_db + b_sp + b_he + b_nu + b_ic + b_ci + b_ro + b_rs + b_as + b_ac));
     char* d = (char*)e->buf.p;
     PanelDev& D = e->dev;
     D.K_full = p->K_full;
@@ -368,6 +412,8 @@ int get_panel(const QuiltPanel* p, PanelDev* out, std::shared_ptr<PanelEntry>* k
     D.n_used = (const int32_t*)d;
     CK(cudaMemcpy(d, n_used.data(), (size_t)p->nGrids * 4, cudaMemcpyHostToDevice));
     d += b_nu;
+    D.asm_src = nullptr;
+    D.asm_cg0 = nullptr;
     D.snp_is_common = nullptr;
     D.common_snp_index = nullptr;
     D.rare_off = nullptr;
@@ -385,6 +431,12 @@ int get_panel(const QuiltPanel* p, PanelDev* out, std::shared_ptr<PanelEntry>* k
         D.rare_snps = (const int32_t*)d;
         if (n_rare > 0) CK(cudaMemcpy(d, p->rare_hap_snps, (size_t)n_rare * 4, cudaMemcpyHostToDevice));
         d += b_rs;
+        D.asm_src = (const int8_t*)d;
+        CK(cudaMemcpy(d, asm_src.data(), asm_src.size(), cudaMemcpyHostToDevice));
+        d += b_as;
+        D.asm_cg0 = (const int32_t*)d;
+        CK(cudaMemcpy(d, asm_cg0.data(), asm_cg0.size() * 4, cudaMemcpyHostToDevice));
+        d += b_ac;
     }
     *out = D;
     if (keep) *keep = e;
@@ -445,8 +497,14 @@ int with_geo(const Geo& g, F&& f) {
 struct JobLayoutIn {  // byte offsets inside the job's input region
     size_t which, rs, roff, u, pRA, wif0, ts, ginfo, dense_reads, runif_reads, runif_shard, tm, desc, H0, runif_block, runif_H_class, L_grid, end;
 };
+// Results live in two device zones: zone A is copied to the host, zone B (endB bytes per job) never leaves the device.
+// genProbsM_t / genProbsF_t go to zone B whenever there is ONE sampling sweep — they are then an exact function of
+// hapProbs_t (gibbs-small.cpp:621-633) and the host re-forms them when unpacking (two thirds of the bulk D2H saved);
+// with QUILT_F_OUTPUT_NO_PROBS hapProbs_t stays in zone B as well (intermediate call of a device-resident chain).
 struct JobLayoutOut {
     size_t underflow, lik, hap, genM, genF, H, Hclass, cat, Hs, end;
+    size_t endB = 0;
+    bool hap_dev_only = false, gen_dev_only = false;
 };
 
 struct HostJob {
@@ -455,7 +513,7 @@ struct HostJob {
     int bucket = -1;
     JobLayoutIn li;
     JobLayoutOut lo;
-    size_t in_off = 0, out_off = 0;  // offsets of the job's regions in the batch arenas
+    size_t in_off = 0, out_off = 0, outB_off = 0;  // offsets of the job's regions in the batch arenas
     std::vector<ReadDesc> desc;
     std::vector<int32_t> rs, ts, ginfo, dense_reads;
     // debug copies (QUILT_F_RETURN_ALPHA / _EXTRA)
@@ -486,7 +544,10 @@ struct QuiltGpuBatch {
     std::vector<std::unique_ptr<Bucket>> buckets;
     PanelDev panel;
     std::shared_ptr<PanelEntry> panel_ref;
-    std::unique_ptr<DBuf> din_, dout_, slots_;
+    std::unique_ptr<DBuf> din_, dout_;
+    size_t slot_arena_bytes = 0;  // what this batch needs of the shared wave-state arena (g_slots)
+    DBuf doutB;  // zone B of the results (device only)
+    size_t outB_bytes = 0;
     std::unique_ptr<HBuf> hin_, hout_;
     DBuf& din() const { return *din_; }
     DBuf& dout() const { return *dout_; }
@@ -494,6 +555,7 @@ struct QuiltGpuBatch {
     HBuf& hout() const { return *hout_; }
     size_t in_bytes = 0, out_bytes = 0;
     bool ran = false, fetched_raw = false;
+    double chain_ms = 0;   // device time of the selection that produced this batch's haplotype lists
     bool chained = false;  // which_haps_to_use of the jobs were written on the device (quilt_gpu_batch_chain_select)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> sweep_events;
@@ -502,7 +564,6 @@ struct QuiltGpuBatch {
     ~QuiltGpuBatch() {
         g_dcache_in.release(std::move(din_));
         g_dcache_out.release(std::move(dout_));
-        g_dcache_slots.release(std::move(slots_));
         g_hcache_in.release(std::move(hin_));
         g_hcache_out.release(std::move(hout_));
         if (ev0) cudaEventDestroy(ev0);
@@ -684,9 +745,21 @@ void layout_in(HostJob& j) {
     o = 0;
     O.underflow = o, o += 256;
     O.lik = o, o += al((size_t)std::max(j.n_its, 1) * LIK_N * 8);
-    O.hap = o, o += al((size_t)a.nSNPs * 24);
-    O.genM = o, o += al((size_t)a.nSNPs * 24);
-    O.genF = o, o += al((size_t)a.nSNPs * 24);
+    O.hap_dev_only = (a.flags & QUILT_F_OUTPUT_NO_PROBS) != 0;
+    O.gen_dev_only = O.hap_dev_only || a.n_gibbs_sample_its == 1;
+    size_t ob = 0;
+    if (O.hap_dev_only)
+        O.hap = ob, ob += al((size_t)a.nSNPs * 24);
+    else
+        O.hap = o, o += al((size_t)a.nSNPs * 24);
+    if (O.gen_dev_only) {
+        O.genM = ob, ob += al((size_t)a.nSNPs * 24);
+        O.genF = ob, ob += al((size_t)a.nSNPs * 24);
+    } else {
+        O.genM = o, o += al((size_t)a.nSNPs * 24);
+        O.genF = o, o += al((size_t)a.nSNPs * 24);
+    }
+    O.endB = ob;
     O.H = o, o += al((size_t)R * 4);
     O.Hclass = o, o += al((size_t)R * 4);
     O.cat = o, o += al((size_t)R * 4);
@@ -763,7 +836,7 @@ typedef std::tuple<int, int, int, int, uint32_t, int, int, double, double, doubl
 
 BucketKey bucket_key(const QuiltGibbsArgs& a) {
     std::vector<int> bi(a.block_gibbs_iterations, a.block_gibbs_iterations + a.n_block_gibbs_iterations);
-    return BucketKey(a.K, a.nGrids, a.nSNPs, a.shuffle_bin_radius, a.flags, a.n_gibbs_burn_in_its, a.n_gibbs_sample_its, a.ff,
+    return BucketKey(a.K, a.nGrids, a.nSNPs, a.shuffle_bin_radius, a.flags & ~(uint32_t)QUILT_F_OUTPUT_NO_PROBS, a.n_gibbs_burn_in_its, a.n_gibbs_sample_its, a.ff,
                      a.maxDifferenceBetweenReads, a.class_sum_cutoff, a.block_gibbs_quantile_prob, a.Jmax, bi);
 }
 
@@ -981,9 +1054,10 @@ void make_jobdev(const QuiltGpuBatch* B, const Bucket& bk, const HostJob& j, int
     D->Hclass = (int32_t*)(out + j.lo.Hclass);
     D->lik = (double*)(out + j.lo.lik);
     D->underflow = (int32_t*)(out + j.lo.underflow);
-    D->hapProbs = (double*)(out + j.lo.hap);
-    D->genM = (double*)(out + j.lo.genM);
-    D->genF = (double*)(out + j.lo.genF);
+    char* outB = (char*)B->doutB.p + j.outB_off;
+    D->hapProbs = (double*)((j.lo.hap_dev_only ? outB : out) + j.lo.hap);
+    D->genM = (double*)((j.lo.gen_dev_only ? outB : out) + j.lo.genM);
+    D->genF = (double*)((j.lo.gen_dev_only ? outB : out) + j.lo.genF);
     D->cat_out = (int32_t*)(out + j.lo.cat);
     D->Hs = (int32_t*)(out + j.lo.Hs);
 }
@@ -1014,7 +1088,7 @@ int run_prep(QuiltGpuBatch* B, Bucket& bk, int n, const JobDev* dj) {
     if (P.rare_common) {
         k_unpack_common<<<dim3(kb, B->panel.Tc, n), 256, 0, g_stream>>>(B->panel, dj, P.K, P.Kp, 1);
         LAUNCHED();
-        k_assemble_all<<<dim3(kb, P.T, n), 256, 0, g_stream>>>(B->panel, dj, P.K, P.Kp);
+        k_assemble_all<<<dim3(kb, (P.T + ASM_GPB - 1) / ASM_GPB, n), 256, 0, g_stream>>>(B->panel, dj, P.K, P.Kp, P.T);
         LAUNCHED();
         k_scatter_rare<<<dim3((P.K + 255) / 256, n), 256, 0, g_stream>>>(B->panel, dj, P.K, P.Kp);
         LAUNCHED();
@@ -1235,6 +1309,17 @@ int run_wave(QuiltGpuBatch* B, Bucket& bk, int w0, int n, bool timed, bool prep_
     return QUILT_OK;
 }
 
+// the shared wave-state arena is large enough for this batch and its buckets point into it
+int ensure_slots(QuiltGpuBatch* B) {
+    if (g_slots.bytes < B->slot_arena_bytes) {
+        CK(cudaStreamSynchronize(g_stream));  // nothing may still be running in the old arena
+        g_slots.release();
+        CK(g_slots.alloc(B->slot_arena_bytes));
+    }
+    for (auto& bk : B->buckets) bk->slots = (char*)g_slots.p;
+    return QUILT_OK;
+}
+
 int run_bucket(QuiltGpuBatch* B, Bucket& bk, bool timed, bool prep_only = false) {
     const int nj = (int)bk.jobs.size();
     int rc = upload_jobdevs(B, bk);
@@ -1314,7 +1399,7 @@ void quilt_gpu_release_panel_cache(void) {
     g_panels.clear();
     g_dcache_in.clear();
     g_dcache_out.clear();
-    g_dcache_slots.clear();
+    g_slots.release();
     g_hcache_in.clear();
     g_hcache_out.clear();
 }
@@ -1342,7 +1427,7 @@ static int stage_impl(int32_t n, const QuiltGibbsArgs* args, QuiltGpuBatch** bat
     }
     if ((rc = get_panel(args[0].panel, &B->panel, &B->panel_ref)) != QUILT_OK) return rc;
     std::map<BucketKey, int> index;
-    size_t in_total = 0, out_total = 0;
+    size_t in_total = 0, out_total = 0, outB_total = 0;
     {
         // descriptor building is O(sum J) per job and independent across jobs
         std::vector<int> rcs(n, QUILT_OK);
@@ -1379,11 +1464,15 @@ static int stage_impl(int32_t n, const QuiltGibbsArgs* args, QuiltGpuBatch** bat
             HostJob& j = B->jobs[ji];
             j.in_off = in_total;
             j.out_off = out_total;
+            j.outB_off = outB_total;
             in_total += j.li.end;
             out_total += j.lo.end;
+            outB_total += j.lo.endB;
         }
     B->in_bytes = in_total;
     B->out_bytes = out_total;
+    B->outB_bytes = outB_total;
+    CK(B->doutB.alloc(outB_total));
     {
         cudaError_t e;
         B->din_ = g_dcache_in.acquire(in_total, &e);
@@ -1403,7 +1492,7 @@ static int stage_impl(int32_t n, const QuiltGibbsArgs* args, QuiltGpuBatch** bat
     }
     size_t free_b = 0, total_b = 0;
     CK(cudaMemGetInfo(&free_b, &total_b));
-    for (auto& c : g_dcache_slots.free_) free_b += c->bytes;  // a cached arena will be reused or dropped
+    free_b += g_slots.bytes;  // the shared wave-state arena is reused (or regrown) by this batch
     size_t budget = (size_t)(free_b * 0.94);
     size_t arena = 0;
     for (auto& bk : B->buckets) {
@@ -1411,15 +1500,10 @@ static int stage_impl(int32_t n, const QuiltGibbsArgs* args, QuiltGpuBatch** bat
         if ((rc = setup_bucket(B.get(), *bk, &mb)) != QUILT_OK) return rc;
         arena = std::max(arena, (size_t)bk->n_slots * bk->slot_bytes);
     }
-    {
-        cudaError_t e;
-        B->slots_ = g_dcache_slots.acquire(arena, &e);
-        CK(e);
-        for (auto& bk : B->buckets) bk->slots = (char*)B->slots_->p;
-    }
+    B->slot_arena_bytes = arena;
     CK(cudaEventCreate(&B->ev0));
     CK(cudaEventCreate(&B->ev1));
-    CK(cudaStreamSynchronize(g_stream));
+    if (upload) CK(cudaStreamSynchronize(g_stream));  // (the pipelined paths prepare a batch while earlier waves still run)
     *batch = B.release();
     return QUILT_OK;
 }
@@ -1437,7 +1521,12 @@ int quilt_gpu_batch_run(QuiltGpuBatch* B) {
         cudaEventDestroy(p.second);
     }
     B->sweep_events.clear();
+    {
+        int rc = ensure_slots(B);
+        if (rc != QUILT_OK) return rc;
+    }
     CK(cudaMemsetAsync(B->dout().p, 0, B->out_bytes, g_stream));
+    if (B->outB_bytes) CK(cudaMemsetAsync(B->doutB.p, 0, B->outB_bytes, g_stream));
     CK(cudaEventRecord(B->ev0, g_stream));
     for (auto& bk : B->buckets) {
         int rc = run_bucket(B, *bk, true);
@@ -1523,9 +1612,42 @@ static void unpack_job(const QuiltGpuBatch* B, int i, QuiltGibbsOut* out) {
         }
     }
     const size_t n3 = (size_t)a.nSNPs * 3;
-    if (o.hapProbs_t) std::memcpy(o.hapProbs_t, base + j.lo.hap, n3 * 8);
-    if (o.genProbsM_t) std::memcpy(o.genProbsM_t, base + j.lo.genM, n3 * 8);
-    if (o.genProbsF_t) std::memcpy(o.genProbsF_t, base + j.lo.genF, n3 * 8);
+    if (!j.lo.hap_dev_only) {
+        const double* hp = reinterpret_cast<const double*>(base + j.lo.hap);
+        if (o.hapProbs_t) std::memcpy(o.hapProbs_t, hp, n3 * 8);
+        if (!j.lo.gen_dev_only) {
+            if (o.genProbsM_t) std::memcpy(o.genProbsM_t, base + j.lo.genM, n3 * 8);
+            if (o.genProbsF_t) std::memcpy(o.genProbsF_t, base + j.lo.genF, n3 * 8);
+        } else if (!under) {
+            // one sampling sweep: genProbs are the products of the haplotype probabilities, in the reference's own
+            // expression order (gibbs-small.cpp:621-633; device twin: k_happrobs) — bit-identical to what the device holds
+            // (the common-SNP variant also fills genProbsF_t for diploid samples, from a zero third haplotype, :627-633; the
+            //  rare/common variant leaves it zero there, :838-846)
+            const bool nipt = !(a.flags & QUILT_F_SAMPLE_IS_DIPLOID) || !(a.flags & QUILT_F_MAKE_EMATREAD_RARE_COMMON);
+            for (int s = 0; s < a.nSNPs; s++) {
+                const double h0 = hp[3 * (size_t)s], h1 = hp[3 * (size_t)s + 1], h2 = hp[3 * (size_t)s + 2];
+                if (o.genProbsM_t) {
+                    double* g = o.genProbsM_t + 3 * (size_t)s;
+                    g[0] = (1 - h0) * (1 - h1);
+                    g[1] = h0 * (1 - h1) + h1 * (1 - h0);
+                    g[2] = h0 * h1;
+                }
+                if (o.genProbsF_t) {
+                    double* g = o.genProbsF_t + 3 * (size_t)s;
+                    if (nipt) {
+                        g[0] = (1 - h0) * (1 - h2);
+                        g[1] = h0 * (1 - h2) + h2 * (1 - h0);
+                        g[2] = h0 * h2;
+                    } else {
+                        g[0] = g[1] = g[2] = 0.0;
+                    }
+                }
+            }
+        } else {
+            if (o.genProbsM_t) std::memset(o.genProbsM_t, 0, n3 * 8);
+            if (o.genProbsF_t) std::memset(o.genProbsF_t, 0, n3 * 8);
+        }
+    }
     if (o.H) std::memcpy(o.H, base + j.lo.H, (size_t)j.R * 4);
     if (o.H_sample_its && a.n_gibbs_sample_its > 0)
         std::memcpy(o.H_sample_its, base + (a.n_gibbs_sample_its > 1 ? j.lo.Hs : j.lo.H), (size_t)a.n_gibbs_sample_its * j.R * 4);
@@ -1566,89 +1688,186 @@ int quilt_gpu_batch_fetch(QuiltGpuBatch* B, QuiltGibbsOut* out) {
     return QUILT_OK;
 }
 
+namespace {
+// device-resident haplotype re-selection for a subset of jobs (defined with the selection code below): job ids[i] of `next`
+// receives the list selected from job ids[i] of `prev`; asynchronous on the library stream
+struct ChainSpec {
+    QuiltGpuBatch* prev = nullptr;
+    int nIndices = 4, L = 3, M = 1;
+    const double* pad_unif = nullptr;  // [n_jobs x Ksubset], row = job id
+};
+int chain_select_subset(const ChainSpec& cs, QuiltGpuBatch* next, const int* ids, int m);
+int chain_check(const ChainSpec& cs, QuiltGpuBatch* next);
+}  // namespace
+
 // Host buffers in, host buffers out.  Waves are pipelined: while the kernels of wave w run, the host fills the pinned
 // input block of wave w + 1 (one H2D copy per wave on a copy stream) and unpacks the results of wave w - 1 (one D2H copy
-// per wave on a second copy stream), so staging overlaps compute instead of preceding / following it.
-int quilt_gpu_gibbs_batch(int32_t n, const QuiltGibbsArgs* args, QuiltGibbsOut* out) {
-    std::lock_guard<std::mutex> lk(g_mu);
-    if (!out) return set_err(QUILT_ERR_BAD_ARG, "null out");
-    QuiltGpuBatch* B = nullptr;
-    int rc = stage_impl(n, args, &B, false);
-    if (rc != QUILT_OK) return rc;
+// per wave on a second copy stream), so staging overlaps compute instead of preceding / following it.  With a chain
+// specification every wave's haplotype lists are selected on the device from the previous batch's hapProbs_t right after
+// the wave's inputs have landed; with `kept` the batch (device results included) survives the call for the next link.
+namespace {
+// One pipeline over the waves of one OR SEVERAL batches (the stages of a call chain): per wave host fill -> H2D (copy
+// stream) -> [device-side selection of the haplotype lists] -> kernels -> D2H (copy stream) -> host unpack of the
+// PREVIOUS wave.  Because the waves of consecutive stages are one sequence, the job preparation of stage s + 1 and the
+// unpacking of stage s's last wave run while the GPU is busy with stage s / s + 1.
+struct WavePipe {
     struct Wave {
+        QuiltGpuBatch* B;
+        QuiltGibbsOut* out;
         Bucket* bk;
         int w0, n;
         cudaEvent_t ev_in = nullptr, ev_done = nullptr, ev_out = nullptr;
     };
     std::vector<Wave> waves;
-    for (auto& bk : B->buckets)
-        for (int w0 = 0; w0 < (int)bk->jobs.size(); w0 += bk->n_slots) waves.push_back({bk.get(), w0, std::min(bk->n_slots, (int)bk->jobs.size() - w0)});
-    auto cleanup = [&](int code) {
-        cudaStreamSynchronize(g_stream);
-        cudaStreamSynchronize(g_copy_in);
-        cudaStreamSynchronize(g_copy_out);
+    size_t unpacked = 0;
+    ~WavePipe() {
         for (auto& w : waves) {
             if (w.ev_in) cudaEventDestroy(w.ev_in);
             if (w.ev_done) cudaEventDestroy(w.ev_done);
             if (w.ev_out) cudaEventDestroy(w.ev_out);
         }
+    }
+    int unpack_through(size_t upto) {  // waves [unpacked, upto)
+        for (; unpacked < upto; unpacked++) {
+            Wave& w = waves[unpacked];
+            CK(cudaEventSynchronize(w.ev_out));
+            parallel_for(w.n, [&](int i) { unpack_job(w.B, w.bk->jobs[w.w0 + i], w.out); });
+        }
+        return QUILT_OK;
+    }
+    int push_batch(QuiltGpuBatch* B, QuiltGibbsOut* out, const ChainSpec* chain) {
+        int rc = ensure_slots(B);
+        if (rc != QUILT_OK) return rc;
+        CK(cudaMemsetAsync(B->dout().p, 0, B->out_bytes, g_stream));
+        if (B->outB_bytes) CK(cudaMemsetAsync(B->doutB.p, 0, B->outB_bytes, g_stream));
+        for (auto& bk : B->buckets) {
+            bool uploaded = false;
+            for (int w0 = 0; w0 < (int)bk->jobs.size(); w0 += bk->n_slots) {
+                waves.push_back(Wave{B, out, bk.get(), w0, std::min(bk->n_slots, (int)bk->jobs.size() - w0)});
+                Wave& w = waves.back();
+                const HostJob& first = B->jobs[w.bk->jobs[w.w0]];
+                const HostJob& last = B->jobs[w.bk->jobs[w.w0 + w.n - 1]];
+                const size_t in_lo = first.in_off, in_hi = last.in_off + last.li.end;
+                const size_t out_lo = first.out_off, out_hi = last.out_off + last.lo.end;
+                // host: this wave's inputs into the pinned block (runs while the previous wave computes)
+                char* hin = (char*)B->hin().p;
+                parallel_for(w.n, [&](int i) {
+                    const HostJob& j = B->jobs[w.bk->jobs[w.w0 + i]];
+                    fill_in(j, hin + j.in_off);
+                });
+                CK(cudaEventCreateWithFlags(&w.ev_in, cudaEventDisableTiming));
+                CK(cudaEventCreateWithFlags(&w.ev_done, cudaEventDisableTiming));
+                CK(cudaEventCreateWithFlags(&w.ev_out, cudaEventDisableTiming));
+                CK(cudaMemcpyAsync((char*)B->din().p + in_lo, hin + in_lo, in_hi - in_lo, cudaMemcpyHostToDevice, g_copy_in));
+                CK(cudaEventRecord(w.ev_in, g_copy_in));
+                CK(cudaStreamWaitEvent(g_stream, w.ev_in, 0));
+                if (!uploaded) {
+                    if ((rc = upload_jobdevs(B, *w.bk)) != QUILT_OK) return rc;
+                    uploaded = true;
+                }
+                if (chain && (rc = chain_select_subset(*chain, B, w.bk->jobs.data() + w.w0, w.n)) != QUILT_OK) return rc;
+                if ((rc = run_wave(B, *w.bk, w.w0, w.n, false, false)) != QUILT_OK) return rc;
+                CK(cudaEventRecord(w.ev_done, g_stream));
+                CK(cudaStreamWaitEvent(g_copy_out, w.ev_done, 0));
+                CK(cudaMemcpyAsync((char*)B->hout().p + out_lo, (const char*)B->dout().p + out_lo, out_hi - out_lo, cudaMemcpyDeviceToHost, g_copy_out));
+                CK(cudaEventRecord(w.ev_out, g_copy_out));
+                // host: results of the waves before this one (their D2H finishes while this wave computes)
+                if ((rc = unpack_through(waves.size() - 1)) != QUILT_OK) return rc;
+            }
+        }
+        B->ran = true;
+        B->chained = chain != nullptr;
+        return QUILT_OK;
+    }
+    int drain() {
+        int rc = unpack_through(waves.size());
+        if (rc != QUILT_OK) return rc;
+        CK(cudaGetLastError());
+        return QUILT_OK;
+    }
+};
+void sync_all_streams() {
+    cudaStreamSynchronize(g_stream);
+    cudaStreamSynchronize(g_copy_in);
+    cudaStreamSynchronize(g_copy_out);
+}
+}  // namespace
+
+static int gibbs_batch_impl(int32_t n, const QuiltGibbsArgs* args, QuiltGibbsOut* out, const ChainSpec* chain, QuiltGpuBatch** kept) {
+    if (!out) return set_err(QUILT_ERR_BAD_ARG, "null out");
+    QuiltGpuBatch* B = nullptr;
+    int rc = stage_impl(n, args, &B, false);
+    if (rc != QUILT_OK) return rc;
+    if (chain) rc = chain_check(*chain, B);
+    {
+        WavePipe pipe;
+        if (rc == QUILT_OK) rc = pipe.push_batch(B, out, chain);
+        if (rc == QUILT_OK) rc = pipe.drain();
+        sync_all_streams();
+    }
+    if (kept && rc == QUILT_OK)
+        *kept = B;
+    else
         delete B;
-        return code;
-    };
-#define CKP(call)                                                                                        \
-    do {                                                                                                 \
-        cudaError_t e__ = (call);                                                                        \
-        if (e__ != cudaSuccess)                                                                          \
-            return cleanup(set_err(QUILT_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__) + " @" + std::to_string(__LINE__))); \
-    } while (0)
-    CKP(cudaMemsetAsync(B->dout().p, 0, B->out_bytes, g_stream));
-    Bucket* uploaded = nullptr;
-    auto unpack_wave = [&](const Wave& w) {
-        parallel_for(w.n, [&](int i) { unpack_job(B, w.bk->jobs[w.w0 + i], out); });
-    };
-    for (size_t wi = 0; wi < waves.size(); wi++) {
-        Wave& w = waves[wi];
-        const HostJob& first = B->jobs[w.bk->jobs[w.w0]];
-        const HostJob& last = B->jobs[w.bk->jobs[w.w0 + w.n - 1]];
-        const size_t in_lo = first.in_off, in_hi = last.in_off + last.li.end;
-        const size_t out_lo = first.out_off, out_hi = last.out_off + last.lo.end;
-        // host: this wave's inputs into the pinned block (runs while the previous wave computes)
-        char* hin = (char*)B->hin().p;
-        parallel_for(w.n, [&](int i) {
-            const HostJob& j = B->jobs[w.bk->jobs[w.w0 + i]];
-            fill_in(j, hin + j.in_off);
-        });
-        CKP(cudaEventCreateWithFlags(&w.ev_in, cudaEventDisableTiming));
-        CKP(cudaEventCreateWithFlags(&w.ev_done, cudaEventDisableTiming));
-        CKP(cudaEventCreateWithFlags(&w.ev_out, cudaEventDisableTiming));
-        CKP(cudaMemcpyAsync((char*)B->din().p + in_lo, hin + in_lo, in_hi - in_lo, cudaMemcpyHostToDevice, g_copy_in));
-        CKP(cudaEventRecord(w.ev_in, g_copy_in));
-        CKP(cudaStreamWaitEvent(g_stream, w.ev_in, 0));
-        if (uploaded != w.bk) {
-            rc = upload_jobdevs(B, *w.bk);
-            if (rc != QUILT_OK) return cleanup(rc);
-            uploaded = w.bk;
+    return rc;
+}
+
+int quilt_gpu_gibbs_batch(int32_t n, const QuiltGibbsArgs* args, QuiltGibbsOut* out) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    return gibbs_batch_impl(n, args, out, nullptr, nullptr);
+}
+
+int quilt_gpu_gibbs_batch_chained(int32_t n, const QuiltGibbsArgs* args, QuiltGibbsOut* out, QuiltGpuBatch* prev, int32_t nIndices, int32_t L, int32_t M,
+                                  const double* pad_unif, QuiltGpuBatch** kept) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (kept) *kept = nullptr;
+    if (!prev) return gibbs_batch_impl(n, args, out, nullptr, kept);
+    if (!pad_unif) return set_err(QUILT_ERR_BAD_ARG, "pad_unif is NULL");
+    ChainSpec cs;
+    cs.prev = prev;
+    cs.nIndices = nIndices;
+    cs.L = L;
+    cs.M = M;
+    cs.pad_unif = pad_unif;
+    return gibbs_batch_impl(n, args, out, &cs, kept);
+}
+
+// The whole call chain of a set of (sample, chain) pairs in one call: stage s holds call s of every pair; from stage 1 on the
+// haplotype lists are selected on the device from stage s - 1 (pad_unif[s - 1]: [n x Ksubset]).  One wave pipeline spans all
+// stages, so preparing stage s + 1 on the host and unpacking stage s overlap the kernels.
+int quilt_gpu_gibbs_chain(int32_t n_stages, int32_t n, const QuiltGibbsArgs* const* args, QuiltGibbsOut* const* out, int32_t nIndices, int32_t L,
+                          int32_t M, const double* const* pad_unif) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (n_stages < 1 || n < 1 || !args || !out) return set_err(QUILT_ERR_BAD_ARG, "bad chain arguments");
+    std::vector<std::unique_ptr<QuiltGpuBatch>> Bs;
+    int rc = QUILT_OK;
+    {
+        WavePipe pipe;
+        for (int s = 0; s < n_stages && rc == QUILT_OK; s++) {
+            if (!args[s] || !out[s] || (s > 0 && (!pad_unif || !pad_unif[s - 1]))) {
+                rc = set_err(QUILT_ERR_BAD_ARG, "null stage arguments");
+                break;
+            }
+            QuiltGpuBatch* B = nullptr;
+            rc = stage_impl(n, args[s], &B, false);  // host preparation: the GPU is busy with the previous stage meanwhile
+            if (rc != QUILT_OK) break;
+            Bs.emplace_back(B);
+            ChainSpec cs;
+            if (s > 0) {
+                cs.prev = Bs[(size_t)s - 1].get();
+                cs.nIndices = nIndices;
+                cs.L = L;
+                cs.M = M;
+                cs.pad_unif = pad_unif[s - 1];
+                rc = chain_check(cs, B);
+                if (rc != QUILT_OK) break;
+            }
+            rc = pipe.push_batch(B, out[s], s > 0 ? &cs : nullptr);
         }
-        rc = run_wave(B, *w.bk, w.w0, w.n, false, false);
-        if (rc != QUILT_OK) return cleanup(rc);
-        CKP(cudaEventRecord(w.ev_done, g_stream));
-        CKP(cudaStreamWaitEvent(g_copy_out, w.ev_done, 0));
-        CKP(cudaMemcpyAsync((char*)B->hout().p + out_lo, (const char*)B->dout().p + out_lo, out_hi - out_lo, cudaMemcpyDeviceToHost, g_copy_out));
-        CKP(cudaEventRecord(w.ev_out, g_copy_out));
-        // host: results of the previous wave (its D2H finishes while this wave computes)
-        if (wi > 0) {
-            CKP(cudaEventSynchronize(waves[wi - 1].ev_out));
-            unpack_wave(waves[wi - 1]);
-        }
+        if (rc == QUILT_OK) rc = pipe.drain();
+        sync_all_streams();
     }
-    if (!waves.empty()) {
-        CKP(cudaEventSynchronize(waves.back().ev_out));
-        unpack_wave(waves.back());
-    }
-    CKP(cudaGetLastError());
-#undef CKP
-    B->ran = true;
-    return cleanup(QUILT_OK);
+    return rc;
 }
 
 int quilt_gpu_gibbs(const QuiltGibbsArgs* args, QuiltGibbsOut* out) { return quilt_gpu_gibbs_batch(1, args, out); }
@@ -1774,47 +1993,99 @@ int quilt_gpu_select_haps(const QuiltSelectArgs* a, int32_t* which_haps_to_use, 
     return QUILT_OK;
 }
 
-int quilt_gpu_batch_chain_select(QuiltGpuBatch* prev, QuiltGpuBatch* next, int32_t nIndices, int32_t L, int32_t M, const double* pad_unif) {
-    std::lock_guard<std::mutex> lk(g_mu);
-    if (!prev || !next || !pad_unif) return set_err(QUILT_ERR_BAD_ARG, "null argument");
+namespace {
+
+DBuf g_sel_scratch;  // scratch of the chained selection (grown on demand; kernels on the library stream are serialised)
+
+int chain_check(const ChainSpec& cs, QuiltGpuBatch* next) {
+    QuiltGpuBatch* prev = cs.prev;
+    if (!prev || !next) return set_err(QUILT_ERR_BAD_ARG, "null batch");
     if (!prev->ran) return set_err(QUILT_ERR_BAD_ARG, "the previous batch has not been run");
     if (prev->n != next->n) return set_err(QUILT_ERR_BAD_ARG, "chained batches must hold the same number of calls");
     if (prev->panel_ref != next->panel_ref) return set_err(QUILT_ERR_BAD_ARG, "chained batches must share one panel");
-    const int n = prev->n;
     const int K = next->jobs[0].a.K;
     const int nHap = (prev->jobs[0].a.flags & QUILT_F_SAMPLE_IS_DIPLOID) ? 2 : 3;
-    for (int i = 0; i < n; i++) {
-        if (next->jobs[i].a.K != K) return set_err(QUILT_ERR_UNSUPPORTED, "chained calls must share one Ksubset");
-        if (prev->jobs[i].a.nSNPs != prev->panel.nSNPsC) return set_err(QUILT_ERR_BAD_ARG, "selection runs on common-SNP calls");
-        if (((prev->jobs[i].a.flags & QUILT_F_SAMPLE_IS_DIPLOID) ? 2 : 3) != nHap) return set_err(QUILT_ERR_UNSUPPORTED, "mixed ploidy in a chained batch");
+    for (int i = 0; i < prev->n; i++) {
+        if (next->jobs[(size_t)i].a.K != K) return set_err(QUILT_ERR_UNSUPPORTED, "chained calls must share one Ksubset");
+        if (prev->jobs[(size_t)i].a.nSNPs != prev->panel.nSNPsC) return set_err(QUILT_ERR_BAD_ARG, "selection runs on common-SNP calls");
+        if (((prev->jobs[(size_t)i].a.flags & QUILT_F_SAMPLE_IS_DIPLOID) ? 2 : 3) != nHap) return set_err(QUILT_ERR_UNSUPPORTED, "mixed ploidy in a chained batch");
     }
+    return QUILT_OK;
+}
+
+int chain_select_subset(const ChainSpec& cs, QuiltGpuBatch* next, const int* ids, int m) {
+    QuiltGpuBatch* prev = cs.prev;
+    const int K = next->jobs[0].a.K;
+    const int nHap = (prev->jobs[0].a.flags & QUILT_F_SAMPLE_IS_DIPLOID) ? 2 : 3;
     SelPlan pl;
-    int rc = make_sel_plan(prev->panel, nHap, K, nIndices, L, M, 1, &pl);
+    int rc = make_sel_plan(prev->panel, nHap, K, cs.nIndices, cs.L, cs.M, 1, &pl);
     if (rc != QUILT_OK) return rc;
-    // jobs are processed in groups so that the scratch stays bounded
-    const int group = std::max(1, std::min(n, (int)(((size_t)2 << 30) / pl.per_job)));
+    // groups keep the scratch bounded
+    const int group = std::max(1, std::min(m, (int)(((size_t)2 << 30) / pl.per_job)));
     const size_t b_pu = al((size_t)group * K * 8), b_j = al((size_t)group * sizeof(SelJob));
-    DBuf buf;
-    CK(buf.alloc((size_t)group * pl.per_job + b_pu + b_j));
-    char* d = (char*)buf.p;
+    const size_t need = (size_t)group * pl.per_job + b_pu + b_j;
+    if (g_sel_scratch.bytes < need) {
+        CK(cudaStreamSynchronize(g_stream));
+        CK(g_sel_scratch.alloc(need));
+    }
+    char* d = (char*)g_sel_scratch.p;
     double* d_pu = (double*)(d + (size_t)group * pl.per_job);
     SelJob* dj = (SelJob*)(d + (size_t)group * pl.per_job + b_pu);
     std::vector<SelJob> hj((size_t)group);
-    for (int j0 = 0; j0 < n; j0 += group) {
-        const int m = std::min(group, n - j0);
-        CK(cudaMemcpyAsync(d_pu, pad_unif + (size_t)j0 * K, (size_t)m * K * 8, cudaMemcpyHostToDevice, g_stream));
-        for (int q = 0; q < m; q++) {
-            const HostJob& pj = prev->jobs[(size_t)(j0 + q)];
-            const HostJob& nj = next->jobs[(size_t)(j0 + q)];
-            const double* hp = (const double*)((const char*)prev->dout().p + pj.out_off + pj.lo.hap);
+    for (int j0 = 0; j0 < m; j0 += group) {
+        const int mm = std::min(group, m - j0);
+        if (j0 > 0) CK(cudaStreamSynchronize(g_stream));  // the previous group still reads the scratch
+        for (int q = 0; q < mm; q++) {
+            const int id = ids[j0 + q];
+            const HostJob& pj = prev->jobs[(size_t)id];
+            const HostJob& nj = next->jobs[(size_t)id];
+            const double* hp = pj.lo.hap_dev_only ? (const double*)((const char*)prev->doutB.p + pj.outB_off + pj.lo.hap)
+                                                  : (const double*)((const char*)prev->dout().p + pj.out_off + pj.lo.hap);
             int32_t* which = (int32_t*)((char*)next->din().p + nj.in_off + nj.li.which);
+            CK(cudaMemcpyAsync(d_pu + (size_t)q * K, cs.pad_unif + (size_t)id * K, (size_t)K * 8, cudaMemcpyHostToDevice, g_stream));
             fill_sel_job(pl, d + (size_t)q * pl.per_job, hp, which, d_pu + (size_t)q * K, &hj[(size_t)q]);
         }
-        CK(cudaMemcpyAsync(dj, hj.data(), (size_t)m * sizeof(SelJob), cudaMemcpyHostToDevice, g_stream));
-        if ((rc = launch_select(pl, prev->panel, dj, m)) != QUILT_OK) return rc;
-        CK(cudaStreamSynchronize(g_stream));  // hj / the pinned-less uploads are reused by the next group
+        CK(cudaMemcpyAsync(dj, hj.data(), (size_t)mm * sizeof(SelJob), cudaMemcpyHostToDevice, g_stream));
+        if ((rc = launch_select(pl, prev->panel, dj, mm)) != QUILT_OK) return rc;
     }
+    return QUILT_OK;
+}
+
+}  // namespace
+
+int quilt_gpu_batch_chain_select(QuiltGpuBatch* prev, QuiltGpuBatch* next, int32_t nIndices, int32_t L, int32_t M, const double* pad_unif) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!prev || !next || !pad_unif) return set_err(QUILT_ERR_BAD_ARG, "null argument");
+    ChainSpec cs;
+    cs.prev = prev;
+    cs.nIndices = nIndices;
+    cs.L = L;
+    cs.M = M;
+    cs.pad_unif = pad_unif;
+    int rc = chain_check(cs, next);
+    if (rc != QUILT_OK) return rc;
+    std::vector<int> ids((size_t)prev->n);
+    for (int i = 0; i < prev->n; i++) ids[(size_t)i] = i;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    CK(cudaEventRecord(e0, g_stream));
+    if ((rc = chain_select_subset(cs, next, ids.data(), prev->n)) != QUILT_OK) return rc;
+    CK(cudaEventRecord(e1, g_stream));
+    CK(cudaEventSynchronize(e1));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    next->chain_ms = ms;
     next->chained = true;
+    return QUILT_OK;
+}
+
+int quilt_gpu_batch_chain_timing(QuiltGpuBatch* B, double* chain_ms) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!B || !chain_ms) return set_err(QUILT_ERR_BAD_ARG, "null argument");
+    *chain_ms = B->chain_ms;
     return QUILT_OK;
 }
 
@@ -1829,6 +2100,157 @@ int quilt_gpu_batch_which_haps(QuiltGpuBatch* B, int32_t job, int32_t* which_hap
 
 
 
+
+// ------------------------------------------------------------------------------------------------ full-panel haploid pass
+namespace {
+double g_hap_ms = 0, g_hap_bytes = 0;
+
+int launch_hap_fb(int ept, const HapParams& P, const HapJob* dj, int n, const PanelDev& pd) {
+    const size_t sm = hap_smem_bytes(P.nMaxDH);
+#define QB_HAP(E)                                                                                      \
+    {                                                                                                  \
+        CK(cudaFuncSetAttribute(k_hap_fb<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));   \
+        k_hap_fb<E><<<n, HAP_NT, sm, g_stream>>>(P, dj, pd);                                           \
+    }
+    if (ept <= 4) QB_HAP(4)
+    else if (ept <= 10) QB_HAP(10)
+    else if (ept <= 16) QB_HAP(16)
+    else QB_HAP(32)
+#undef QB_HAP
+    LAUNCHED();
+    return QUILT_OK;
+}
+}  // namespace
+
+int quilt_gpu_haploid_dosage_versus_refs_batch(int32_t n, const QuiltHaploidArgs* args, QuiltHaploidOut* out) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (n < 1 || !args || !out || !args[0].panel) return set_err(QUILT_ERR_BAD_ARG, "bad arguments");
+    int rc = ensure_device();
+    if (rc != QUILT_OK) return rc;
+    PanelDev pd;
+    std::shared_ptr<PanelEntry> keep;
+    if ((rc = get_panel(args[0].panel, &pd, &keep)) != QUILT_OK) return rc;
+    const int K = pd.K_full, T = pd.Tc, nS = pd.nSNPsC, NM1 = pd.nMaxDH + 1;
+    if (T < 2) return set_err(QUILT_ERR_BAD_ARG, "the full-panel pass needs at least two grids");
+    if (K > HAP_NT * 32) return set_err(QUILT_ERR_UNSUPPORTED, "full-panel pass: K_full > 16384 needs the multi-CTA form (not built); use the mspbwt selection for such panels");
+    HapParams P;
+    std::memset(&P, 0, sizeof(P));
+    P.K = K;
+    P.T = T;
+    P.nSNPs = nS;
+    P.nMaxDH = pd.nMaxDH;
+    P.n_thin = args[0].n_thinned;
+    P.K_top = args[0].K_top_matches;
+    P.best_cap = args[0].best_cap;
+    P.flags = args[0].flags;
+    P.thr = args[0].min_emission_prob_normalization_threshold;
+    P.ref_error = pd.ref_error;
+    for (int i = 0; i < n; i++) {
+        const QuiltHaploidArgs& a = args[i];
+        if (!a.gl || !a.transMatRate_t) return set_err(QUILT_ERR_BAD_ARG, "gl / transMatRate_t is NULL");
+        if (a.panel != args[0].panel && !same_panel_struct(*a.panel, *args[0].panel)) return set_err(QUILT_ERR_UNSUPPORTED, "all passes of a batch must share one panel");
+        if (a.flags != P.flags || a.n_thinned != P.n_thin || a.K_top_matches != P.K_top || a.best_cap != P.best_cap ||
+            a.min_emission_prob_normalization_threshold != P.thr)
+            return set_err(QUILT_ERR_UNSUPPORTED, "all passes of a batch must share flags / thinning / K_top_matches");
+        if ((a.flags & QUILT_HF_GET_BEST_HAPS) && (!a.gammaSmall_cols_to_get || a.n_thinned < 1 || a.best_cap < 1)) return set_err(QUILT_ERR_BAD_ARG, "best haplotypes need gammaSmall_cols_to_get, n_thinned and best_cap");
+    }
+    if (P.K_top < 1 || P.K_top > HAP_MAXTOP) return set_err(QUILT_ERR_UNSUPPORTED, "K_top_matches must be in 1 .. 16");
+    const bool w_beta = (P.flags & QUILT_HF_RETURN_BETAHAT) != 0, w_gamma = (P.flags & QUILT_HF_RETURN_GAMMA) != 0, w_best = (P.flags & QUILT_HF_GET_BEST_HAPS) != 0;
+    // per-pass device layout
+    size_t o = 0;
+    auto take = [&](size_t nb) {
+        const size_t r = o;
+        o += al(nb);
+        return r;
+    };
+    const size_t KT = (size_t)K * T;
+    const size_t o_gl = take((size_t)nS * 16), o_tm = take((size_t)(T - 1) * 16), o_cols = take((size_t)T * 4), o_em = take((size_t)T * NM1 * 8);
+    const size_t o_emax = take((size_t)T * 8), o_cmin = take((size_t)T * 8), o_hv = take((size_t)T), o_alpha = take(KT * 8);
+    const size_t o_beta = take(w_beta ? KT * 8 : 0), o_gamma = take(w_gamma ? KT * 8 : 0), o_c = take((size_t)T * 8), o_dos = take((size_t)nS * 8);
+    const size_t nb_best = w_best ? (size_t)P.n_thin * P.best_cap : 0;
+    const size_t o_best = take(nb_best * 4), o_bval = take(nb_best * 8), o_bcnt = take((size_t)std::max(P.n_thin, 1) * 4);
+    const size_t per = o;
+    size_t free_b = 0, total_b = 0;
+    CK(cudaMemGetInfo(&free_b, &total_b));
+    const int group = (int)std::max<size_t>(1, std::min<size_t>((size_t)n, (size_t)(free_b * 0.8) / per));
+    DBuf buf, jb;
+    CK(buf.alloc((size_t)group * per));
+    CK(jb.alloc((size_t)group * sizeof(HapJob)));
+    std::vector<HapJob> hj((size_t)group);
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    double ms_total = 0;
+    for (int j0 = 0; j0 < n; j0 += group) {
+        const int m = std::min(group, n - j0);
+        for (int q = 0; q < m; q++) {
+            const QuiltHaploidArgs& a = args[j0 + q];
+            char* d = (char*)buf.p + (size_t)q * per;
+            CK(cudaMemcpyAsync(d + o_gl, a.gl, (size_t)nS * 16, cudaMemcpyHostToDevice, g_stream));
+            CK(cudaMemcpyAsync(d + o_tm, a.transMatRate_t, (size_t)(T - 1) * 16, cudaMemcpyHostToDevice, g_stream));
+            if (w_best) CK(cudaMemcpyAsync(d + o_cols, a.gammaSmall_cols_to_get, (size_t)T * 4, cudaMemcpyHostToDevice, g_stream));
+            HapJob& J = hj[(size_t)q];
+            J.gl = (const double*)(d + o_gl);
+            J.tm = (const double*)(d + o_tm);
+            J.cols = w_best ? (const int32_t*)(d + o_cols) : nullptr;
+            J.eMatDH = (double*)(d + o_em);
+            J.emax = (double*)(d + o_emax);
+            J.cmin = (double*)(d + o_cmin);
+            J.hasvar = (uint8_t*)(d + o_hv);
+            J.alpha = (double*)(d + o_alpha);
+            J.beta = w_beta ? (double*)(d + o_beta) : nullptr;
+            J.gamma = w_gamma ? (double*)(d + o_gamma) : nullptr;
+            J.c = (double*)(d + o_c);
+            J.dosage = (double*)(d + o_dos);
+            J.best = (int32_t*)(d + o_best);
+            J.best_val = (double*)(d + o_bval);
+            J.best_cnt = (int32_t*)(d + o_bcnt);
+        }
+        CK(cudaMemcpyAsync(jb.p, hj.data(), (size_t)m * sizeof(HapJob), cudaMemcpyHostToDevice, g_stream));
+        CK(cudaEventRecord(e0, g_stream));
+        k_hap_eMatDH<<<dim3(T, m), 256, 0, g_stream>>>(P, (const HapJob*)jb.p, pd.distinctHapsB);
+        LAUNCHED();
+        rc = launch_hap_fb((K + HAP_NT - 1) / HAP_NT, P, (const HapJob*)jb.p, m, pd);
+        if (rc != QUILT_OK) return rc;
+        CK(cudaEventRecord(e1, g_stream));
+        CK(cudaGetLastError());
+        for (int q = 0; q < m; q++) {
+            QuiltHaploidOut& O = out[j0 + q];
+            const char* d = (const char*)buf.p + (size_t)q * per;
+            if (O.dosage && (P.flags & QUILT_HF_RETURN_DOSAGE)) CK(cudaMemcpyAsync(O.dosage, d + o_dos, (size_t)nS * 8, cudaMemcpyDeviceToHost, g_stream));
+            if (O.c) CK(cudaMemcpyAsync(O.c, d + o_c, (size_t)T * 8, cudaMemcpyDeviceToHost, g_stream));
+            if (O.alphaHat_t && (P.flags & QUILT_HF_RETURN_ALPHAHAT)) CK(cudaMemcpyAsync(O.alphaHat_t, d + o_alpha, KT * 8, cudaMemcpyDeviceToHost, g_stream));
+            if (O.betaHat_t && w_beta) CK(cudaMemcpyAsync(O.betaHat_t, d + o_beta, KT * 8, cudaMemcpyDeviceToHost, g_stream));
+            if (O.gamma_t && w_gamma) CK(cudaMemcpyAsync(O.gamma_t, d + o_gamma, KT * 8, cudaMemcpyDeviceToHost, g_stream));
+            if (w_best) {
+                if (O.best_haps) CK(cudaMemcpyAsync(O.best_haps, d + o_best, nb_best * 4, cudaMemcpyDeviceToHost, g_stream));
+                if (O.best_haps_values) CK(cudaMemcpyAsync(O.best_haps_values, d + o_bval, nb_best * 8, cudaMemcpyDeviceToHost, g_stream));
+                if (O.best_haps_count) CK(cudaMemcpyAsync(O.best_haps_count, d + o_bcnt, (size_t)P.n_thin * 4, cudaMemcpyDeviceToHost, g_stream));
+            }
+        }
+        CK(cudaStreamSynchronize(g_stream));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        ms_total += ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    g_hap_ms = ms_total;
+    g_hap_bytes = (double)n * (double)KT * (2.0 + 16.0 + (w_beta ? 8.0 : 0.0) + (w_gamma ? 8.0 : 0.0));
+    return QUILT_OK;
+}
+
+int quilt_gpu_haploid_dosage_versus_refs(const QuiltHaploidArgs* args, QuiltHaploidOut* out) {
+    return quilt_gpu_haploid_dosage_versus_refs_batch(1, args, out);
+}
+
+int quilt_gpu_haploid_last_timing(double* kernel_ms, double* algorithmic_bytes) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (kernel_ms) *kernel_ms = g_hap_ms;
+    if (algorithmic_bytes) *algorithmic_bytes = g_hap_bytes;
+    return QUILT_OK;
+}
+
 // ---- component entry points (parity tests of the individual reference functions)
 int quilt_gpu_make_eMatRead_t(const QuiltGibbsArgs* args, double* eMatRead_t, int32_t* read_category) {
     if (!args || !eMatRead_t) return set_err(QUILT_ERR_BAD_ARG, "null argument");
@@ -1840,6 +2262,8 @@ int quilt_gpu_make_eMatRead_t(const QuiltGibbsArgs* args, double* eMatRead_t, in
     {
         std::lock_guard<std::mutex> lk(g_mu);
         rc = cudaMemsetAsync(B->dout().p, 0, B->out_bytes, g_stream) == cudaSuccess ? QUILT_OK : set_err(QUILT_ERR_CUDA, "memset");
+        if (rc == QUILT_OK && B->outB_bytes) rc = cudaMemsetAsync(B->doutB.p, 0, B->outB_bytes, g_stream) == cudaSuccess ? QUILT_OK : set_err(QUILT_ERR_CUDA, "memset");
+        if (rc == QUILT_OK) rc = ensure_slots(B);
         if (rc == QUILT_OK) rc = run_bucket(B, *B->buckets[0], false, true);
         if (rc == QUILT_OK) {
             const HostJob& j = B->jobs[0];
@@ -1885,7 +2309,7 @@ int quilt_gpu_unpack_panel(const QuiltPanel* panel, int32_t K, const int32_t* wh
     if (all_snps) {
         k_unpack_common<<<dim3(kb, PD.Tc, 1), 256, 0, g_stream>>>(PD, d, K, Kp, 1);
         LAUNCHED();
-        k_assemble_all<<<dim3(kb, T, 1), 256, 0, g_stream>>>(PD, d, K, Kp);
+        k_assemble_all<<<dim3(kb, (T + ASM_GPB - 1) / ASM_GPB, 1), 256, 0, g_stream>>>(PD, d, K, Kp, T);
         LAUNCHED();
         k_scatter_rare<<<dim3((K + 255) / 256, 1), 256, 0, g_stream>>>(PD, d, K, Kp);
         LAUNCHED();

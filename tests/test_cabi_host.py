@@ -33,7 +33,7 @@ def test_gpu_library_exports_every_declared_symbol():
 
 def test_oracle_library_exports_every_declared_symbol(oracle):
     names = _declared("quilt_oracle", ("oracle", "quilt_oracle.h"))
-    assert len(names) == 4
+    assert len(names) >= 6
     for n in names:
         assert hasattr(oracle.lib, n), n
 

@@ -1,0 +1,128 @@
+"""Full-panel haploid Li-Stephens pass (Rcpp_haploid_dosage_versus_refs, reference-single.cpp:2189-2413).
+
+The CPU checker here is the reference ITSELF: the unmodified reference-single.cpp compiled against the RcppArmadillo / RcppEigen stand-ins
+(oracle/_ref, entry quilt_ref_haploid_dosage_versus_refs, production settings of functions.R:2034-2070).  CPU tests pin properties of that
+build; the GPU tests compare the CUDA kernels with it (dosage / gamma within 1e-10, best-match lists identical)."""
+import numpy as np
+import pytest
+
+from quilt_b200 import cabi, synth
+
+
+@pytest.fixture(scope="module")
+def ref():
+    from oracle import ref_py
+
+    if not ref_py.available() and not ref_py.can_build():
+        pytest.skip("oracle/_ref/libquiltref.so not built and /root/reference not present")
+    return ref_py.Ref()
+
+
+def make_gl(reads, nSNPs, labels, h, minGL=1e-10):
+    """make_gl_from_u_bq (reference-single.R:19-42) + Rcpp_make_gl_bound (reference-single.cpp:68-94) for the reads labelled h"""
+    gl = np.ones((2, nSNPs))
+    for r in range(reads.nReads):
+        if labels[r] != h:
+            continue
+        for j in range(reads.offsets[r], reads.offsets[r + 1]):
+            bq, u = int(reads.bq[j]), int(reads.u[j])
+            if bq == 0:
+                continue
+            eps = 10 ** (-abs(bq) / 10)
+            pr = (1 - eps, eps / 3) if bq < 0 else (eps / 3, 1 - eps)
+            gl[0, u] *= pr[0]
+            gl[1, u] *= pr[1]
+    fix = np.nonzero((gl < minGL).sum(axis=0) > 0)[0]
+    for c in fix:
+        a, b = gl[0, c], gl[1, c]
+        if a > b:
+            b, a = max(b / a, minGL), 1.0
+        else:
+            a, b = max(a / b, minGL), 1.0
+        gl[0, c], gl[1, c] = a, b
+    return np.asfortranarray(gl)
+
+
+def thinned_cols(T, frac=0.1):
+    """quilt.R:719-721"""
+    ww = np.round(np.linspace(1, T, max(1, round(frac * T)))).astype(int) - 1
+    cols = np.full(T, -1, dtype=np.int32)
+    cols[ww] = np.arange(len(ww), dtype=np.int32)
+    return cols
+
+
+def _inputs(world, reads, seed, h=1):
+    H = np.random.default_rng(seed).integers(1, 3, reads.nReads)
+    return make_gl(reads, world.panel.nSNPs, H, h), thinned_cols(world.panel.nGrids)
+
+
+def test_reference_pass_is_a_posterior(ref, small_world, small_reads):
+    gl, cols = _inputs(small_world, small_reads.common, 1)
+    r = ref.haploid_dosage(small_world.panel, gl, small_world.transMatRate, cols)
+    assert np.allclose(r["gamma_t"].sum(axis=0), 1.0, atol=1e-9)
+    assert r["dosage"].min() >= 0 and r["dosage"].max() <= 1
+    # dosage == sum_k gamma[k, g] * (bit ? 1 - eps : eps): the per-symbol shortcut equals the dense sum
+    bits = small_world.bits_common.astype(np.float64)
+    eps = small_world.panel.ref_error
+    dense = np.einsum("ks,ks->s", np.repeat(r["gamma_t"], 32, axis=1)[:, : bits.shape[1]], bits * (1 - 2 * eps) + eps)
+    assert np.max(np.abs(dense - r["dosage"])) < 1e-9
+    assert np.all(r["best_haps_count"] >= 5)
+
+
+def test_reference_pass_special_haplotypes(ref):
+    """nMaxDH = 5: most (haplotype, grid) words go through the special-symbol path; the posterior must not notice"""
+    w5 = synth.make_world(21, K_full=150, nSNPs=640, region_bp=60_000, nMaxDH=5, n_founders=30)
+    w255 = synth.make_world(21, K_full=150, nSNPs=640, region_bp=60_000, n_founders=30)
+    sr = synth.make_sample_reads(w5, 22, coverage=2.0, region_bp=60_000)
+    gl, cols = _inputs(w5, sr.common, 3)
+    a = ref.haploid_dosage(w5.panel, gl, w5.transMatRate, cols)
+    b = ref.haploid_dosage(w255.panel, gl, w255.transMatRate, cols)
+    assert np.max(np.abs(a["dosage"] - b["dosage"])) < 1e-9
+    assert np.max(np.abs(a["gamma_t"] - b["gamma_t"])) < 1e-9
+
+
+def _cmp(g, r, tag):
+    d_dos = float(np.max(np.abs(g["dosage"] - r["dosage"])))
+    d_gam = float(np.max(np.abs(g["gamma_t"] - r["gamma_t"])))
+    rel = lambda x, y: float(np.max(np.abs(x - y) / (np.abs(y) + 1e-300)))  # noqa: E731
+    print(f"[{tag}] |d dosage| {d_dos:.2e} |d gamma| {d_gam:.2e} alpha rel {rel(g['alphaHat_t'], r['alphaHat_t']):.2e} beta rel {rel(g['betaHat_t'], r['betaHat_t']):.2e} c rel {rel(g['c'], r['c']):.2e}")
+    assert d_dos <= 1e-10 and d_gam <= 1e-10
+    assert rel(g["alphaHat_t"], r["alphaHat_t"]) <= 1e-9 and rel(g["betaHat_t"], r["betaHat_t"]) <= 1e-9 and rel(g["c"], r["c"]) <= 1e-9
+    assert np.array_equal(g["best_haps_count"], r["best_haps_count"])
+    assert np.array_equal(g["best_haps"], r["best_haps"]), "best-match haplotypes at the thinned grids"
+    assert np.max(np.abs(g["best_haps_values"] - r["best_haps_values"])) <= 1e-10
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", [1, 2])
+def test_gpu_pass_equals_reference(gpu, ref, small_world, small_reads, seed):
+    gl, cols = _inputs(small_world, small_reads.common, seed, h=seed)
+    _cmp(gpu.haploid_dosage(small_world.panel, gl, small_world.transMatRate, cols), ref.haploid_dosage(small_world.panel, gl, small_world.transMatRate, cols), f"K_full=600 seed {seed}")
+
+
+@pytest.mark.gpu
+def test_gpu_pass_special_haplotypes(gpu, ref):
+    w = synth.make_world(21, K_full=150, nSNPs=640, region_bp=60_000, nMaxDH=5, n_founders=30)
+    sr = synth.make_sample_reads(w, 22, coverage=2.0, region_bp=60_000)
+    gl, cols = _inputs(w, sr.common, 3)
+    _cmp(gpu.haploid_dosage(w.panel, gl, w.transMatRate, cols), ref.haploid_dosage(w.panel, gl, w.transMatRate, cols), "special haplotypes")
+
+
+@pytest.mark.gpu
+def test_gpu_pass_lazy_normalisation_kicks_in(gpu, ref, small_world):
+    """deep coverage makes the running minimum emission cross 1e-100 inside the region: the lazily normalised alphaHat_t / c must
+    follow the reference's renormalisation points"""
+    sr = synth.make_sample_reads(small_world, 9, coverage=40.0, region_bp=300_000)
+    gl, cols = _inputs(small_world, sr.common, 5)
+    r = ref.haploid_dosage(small_world.panel, gl, small_world.transMatRate, cols)
+    assert np.sum(np.abs(r["alphaHat_t"].sum(axis=0) - 1) < 1e-9) < small_world.panel.nGrids, "every grid normalised: the lazy path is not exercised"
+    _cmp(gpu.haploid_dosage(small_world.panel, gl, small_world.transMatRate, cols), r, "coverage 40")
+
+
+@pytest.mark.gpu
+def test_gpu_pass_full_panel_size(gpu, ref):
+    """the panel of the headline configuration: 5008 haplotypes x 1000 grids"""
+    w = synth.make_world(20260118, K_full=5008, nSNPs=32000, region_bp=3_000_000)
+    sr = synth.make_sample_reads(w, 4000, coverage=1.0, region_bp=3_000_000)
+    gl, cols = _inputs(w, sr.common, 7)
+    _cmp(gpu.haploid_dosage(w.panel, gl, w.transMatRate, cols), ref.haploid_dosage(w.panel, gl, w.transMatRate, cols), "K_full=5008 T=1000")

@@ -144,3 +144,58 @@ def test_gpu_chained_selection_without_host_round_trip(gpu, oracle, small_world,
         o = oracle.gibbs(c)
         assert np.array_equal(r2[j].H, o.H)
         assert np.max(np.abs(r2[j].hapProbs_t - o.hapProbs_t)) <= 1e-4
+
+
+@pytest.mark.gpu
+def test_gpu_chained_host_buffer_calls(gpu, oracle, small_world, small_reads):
+    """the same chain through quilt_gpu_gibbs_batch_chained (host buffers in / out, waves pipelined): the intermediate call keeps its
+    probabilities on the device (QUILT_F_OUTPUT_NO_PROBS), the second call's lists are selected there"""
+    w = small_world
+    K = 250
+    first = [synth.make_call(w, small_reads.common, 80 + j, K=K, first_iteration=True) for j in range(4)]
+    second = [synth.make_call(w, small_reads.common, 90 + j, K=K, first_iteration=False, sort_haps=False) for j in range(4)]
+    for c in first:
+        c.flags |= cabi.F_OUTPUT_NO_PROBS
+    pu = np.random.default_rng(11).random(4 * K)
+    r1, kept = api.run_prepared_chained(gpu, gpu.prepare(first), None, None, keep=True)
+    r2, none = api.run_prepared_chained(gpu, gpu.prepare(second), kept, pu, keep=False)
+    kept.free()
+    assert none is None
+    for j in range(4):
+        o1 = oracle.gibbs(first[j])
+        assert np.array_equal(r1[j].H, o1.H)   # labels are shipped even when the probabilities stay on the device
+        expect = oracle.select_haps_padded(w.panel, o1.hapProbs_t, K, pu[j * K:(j + 1) * K])
+        c = second[j]
+        c.which_haps_to_use = expect
+        o2 = oracle.gibbs(c)
+        assert np.array_equal(r2[j].H, o2.H)
+        assert np.max(np.abs(r2[j].hapProbs_t - o2.hapProbs_t)) <= 1e-4
+        assert np.max(np.abs(r2[j].genProbsM_t - o2.genProbsM_t)) <= 1e-4   # formed on the host from hapProbs_t (one sampling sweep)
+        assert np.max(np.abs(r2[j].genProbsF_t - o2.genProbsF_t)) <= 1e-4
+
+
+@pytest.mark.gpu
+def test_gpu_whole_chain_in_one_call(gpu, oracle, small_world, small_reads):
+    """quilt_gpu_gibbs_chain: three stages (two common-SNP calls, then the all-SNP call) with host buffers, one pipeline; every stage
+    equals the CPU chain (oracle Gibbs call -> oracle selection -> next call)"""
+    w = small_world
+    K, n = 200, 3
+    stages = [[synth.make_call(w, small_reads.common, 100 + j, K=K, first_iteration=True) for j in range(n)],
+              [synth.make_call(w, small_reads.common, 110 + j, K=K, first_iteration=False, sort_haps=False) for j in range(n)],
+              [synth.make_call(w, small_reads.all, 120 + j, K=K, all_snps=True, sort_haps=False) for j in range(n)]]
+    for c in stages[0]:
+        c.flags |= cabi.F_OUTPUT_NO_PROBS
+    rng = np.random.default_rng(13)
+    pads = [rng.random(n * K), rng.random(n * K)]
+    res = api.run_chain_prepared(gpu, [gpu.prepare(st) for st in stages], pads)
+    for j in range(n):
+        prev = oracle.gibbs(stages[0][j])
+        assert np.array_equal(res[0][j].H, prev.H)
+        for s in (1, 2):
+            c = stages[s][j]
+            c.which_haps_to_use = oracle.select_haps_padded(w.panel, prev.hapProbs_t, K, pads[s - 1][j * K:(j + 1) * K])
+            cur = oracle.gibbs(c)
+            assert np.array_equal(res[s][j].H, cur.H), (s, j)
+            assert np.max(np.abs(res[s][j].hapProbs_t - cur.hapProbs_t)) <= 1e-4
+            assert np.max(np.abs(res[s][j].genProbsM_t - cur.genProbsM_t)) <= 1e-4
+            prev = cur
