@@ -301,6 +301,31 @@ int quilt_gpu_haploid_dosage_versus_refs_batch(int32_t n, const QuiltHaploidArgs
  * K_full * nGrids * (2 x 1 symbol byte + 8 alphaHat written + 8 alphaHat read) (+ 8 per returned matrix element) */
 int quilt_gpu_haploid_last_timing(double* kernel_ms, double* algorithmic_bytes);
 
+/*
+ * Per-sample reductions that follow the Gibbs calls (SURVEY.md section 8 row a12 and the INFO counters of section 8e), on the
+ * device from the device-resident hapProbs_t of staged / kept batches, so that only per-sample vectors travel:
+ *   dosage / gp_t running sums over the stored calls in R's order and the final division (QUILT/R/functions.R:999-1020,
+ *   :1100-1122, :1304-1325); recast_haps of the phasing call against the accumulated gp_t (:3180-3209, called at :1211 /
+ *   :1236) -> recast haplotype dosages and the phased GT; eij / fij / max_gen (:1408-1411) and the per-rank counters
+ *   infoCount, afCount, hweCount (QUILT/R/quilt.R:957-961) summed over the samples in order.  Diploid samples.
+ *   (R's round(x, 3) is taken as rint(1000 x) / 1000.)
+ */
+typedef struct QuiltSummaryCall {
+    QuiltGpuBatch* batch;        /* a batch that has been run (staged form or kept by quilt_gpu_gibbs_batch_chained) */
+    int32_t job;                 /* index of the call inside it                                                    */
+} QuiltSummaryCall;
+typedef struct QuiltSampleSummary {
+    int32_t n_calls;             /* stored calls of the sample, in the reference's accumulation order            */
+    const QuiltSummaryCall* calls;
+    QuiltSummaryCall phasing;    /* the phasing chain's final call (phasing_haps)                                 */
+    double* dosage;              /* [nSNPs]      out                                                              */
+    double* gp_t;                /* [3 x nSNPs]  out                                                              */
+    double* hd;                  /* [nSNPs x 2]  out: recast haplotype dosages, column-major                      */
+    int8_t* gt;                  /* [nSNPs x 2]  out: round(hd), the phased genotype                              */
+} QuiltSampleSummary;
+int quilt_gpu_samples_summary(int32_t n_samples, int32_t nSNPs, const QuiltSampleSummary* samples,
+                              double* infoCount /*[nSNPs x 2] or NULL*/, double* afCount /*[nSNPs]*/, double* hweCount /*[nSNPs x 3]*/);
+
 /* component entry points (parity tests of the individual reference functions) */
 int quilt_gpu_make_eMatRead_t(const QuiltGibbsArgs* args, double* eMatRead_t /*[K x nReads]*/,
                               int32_t* read_category /*[nReads] or NULL*/);

@@ -152,6 +152,35 @@ def run_prepared_chained(lib: GpuLib, prep, prev: Optional[KeptBatch], pad_unif,
     return res, (KeptBatch(lib, kept) if keep and kept.value else None)
 
 
+def samples_summary(lib: GpuLib, samples, nSNPs: int):
+    """quilt_gpu_samples_summary: per-sample dosage / gp_t / recast phasing haplotypes / phased GT and this rank's INFO counters, computed on
+    the device from the device-resident hapProbs_t of batches that have run.
+    samples: list of (stored_calls, phasing_call) with stored_calls = [(Batch-or-KeptBatch, job), ...] in the reference's accumulation order.
+    -> (list of dicts, {"infoCount": [nSNPs, 2], "afCount": [nSNPs], "hweCount": [nSNPs, 3]})"""
+    n = len(samples)
+    arr = (cabi.QuiltSampleSummary * n)()
+    keep, outs = [], []
+    for i, (stored, phasing) in enumerate(samples):
+        calls = (cabi.QuiltSummaryCall * len(stored))()
+        for c, (b, j) in enumerate(stored):
+            calls[c].batch, calls[c].job = b._h, j
+        keep.append(calls)
+        o = {"dosage": np.zeros(nSNPs), "gp_t": np.zeros((3, nSNPs), order="F"), "hd": np.zeros((nSNPs, 2), order="F"), "gt": np.zeros((nSNPs, 2), dtype=np.int8, order="F")}
+        outs.append(o)
+        a = arr[i]
+        a.n_calls, a.calls = len(stored), calls
+        a.phasing.batch, a.phasing.job = phasing[0]._h, phasing[1]
+        a.dosage, a.gp_t, a.hd = cabi._ptr(o["dosage"], cabi._pd), cabi._ptr(o["gp_t"], cabi._pd), cabi._ptr(o["hd"], cabi._pd)
+        a.gt = o["gt"].ctypes.data_as(C.POINTER(C.c_int8))
+    cnt = {"infoCount": np.zeros((nSNPs, 2), order="F"), "afCount": np.zeros(nSNPs), "hweCount": np.zeros((nSNPs, 3), order="F")}
+    fn = lib.lib.quilt_gpu_samples_summary
+    fn.argtypes = [C.c_int32, C.c_int32, C.POINTER(cabi.QuiltSampleSummary), cabi._pd, cabi._pd, cabi._pd]
+    fn.restype = C.c_int
+    lib._check(fn(n, nSNPs, arr, cabi._ptr(cnt["infoCount"], cabi._pd), cabi._ptr(cnt["afCount"], cabi._pd), cabi._ptr(cnt["hweCount"], cabi._pd)),
+               "quilt_gpu_samples_summary")
+    return outs, cnt
+
+
 def run_chain_prepared(lib: GpuLib, preps, pads, mspbwt_nindices=4, mspbwtL=3, mspbwtM=1):
     """quilt_gpu_gibbs_chain: all stages of the call chain in one call (host buffers in / out).  preps: one lib.prepare(...) per stage;
     pads: [n x Ksubset] uniforms per link.  -> list of result lists"""

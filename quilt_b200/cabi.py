@@ -146,6 +146,22 @@ class QuiltSelectArgs(C.Structure):
     ]
 
 
+class QuiltSummaryCall(C.Structure):
+    _fields_ = [("batch", C.c_void_p), ("job", C.c_int32)]
+
+
+class QuiltSampleSummary(C.Structure):
+    _fields_ = [
+        ("n_calls", C.c_int32),
+        ("calls", C.POINTER(QuiltSummaryCall)),
+        ("phasing", QuiltSummaryCall),
+        ("dosage", _pd),
+        ("gp_t", _pd),
+        ("hd", _pd),
+        ("gt", C.POINTER(C.c_int8)),
+    ]
+
+
 HF_RETURN_DOSAGE, HF_RETURN_BETAHAT, HF_RETURN_GAMMA, HF_GET_BEST_HAPS, HF_RETURN_ALPHAHAT = 1, 2, 4, 8, 16
 
 

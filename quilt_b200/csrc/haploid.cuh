@@ -144,6 +144,8 @@ __global__ void __launch_bounds__(HAP_NT) k_hap_fb(HapParams P, const HapJob* __
     double* mgw = scr + 2 * NW;                                     // [NW][MGS] per-warp symbol sums
     double* dpart = mgw + (size_t)NW * MGS;                         // [NW][32] dosage partials
     unsigned long long* wtop = reinterpret_cast<unsigned long long*>(dpart + NW * 32);  // [NW][HAP_MAXTOP]
+    uint32_t* swords = reinterpret_cast<uint32_t*>(wtop + NW * HAP_MAXTOP);              // [NM1] the grid's table words (row 0 unused)
+    double* sk = reinterpret_cast<double*>(swords + ((NM1 + 1) & ~1));                   // [K] per-haplotype scratch: special emissions / gamma
     __shared__ unsigned long long s_thr;
     __shared__ int s_cnt;
     __shared__ int s_lk[HAP_LISTCAP];
@@ -169,12 +171,23 @@ __global__ void __launch_bounds__(HAP_NT) k_hap_fb(HapParams P, const HapJob* __
                 scol[i] = (i == 0 && zero_row0) ? 0.0 : v;
             }
         __syncthreads();
+        if (with_col) {
+            // special haplotypes (symbol 0): emission from their own 32-SNP word.  The grid's rows of eMatDH_special_matrix are
+            // walked directly (they are sorted by haplotype, so this is what the reference's binary search returns — including its
+            // quirk that a group of ONE row yields the word 0, gibbs-small.cpp:69-105); the result waits in sk[k] for the owner.
+            const int s1 = __ldg(PD.helper + g), e1 = __ldg(PD.helper + PD.Tc + g);
+            const int n_sp = (s1 > 0 && e1 >= s1) ? e1 - s1 + 1 : 0;
+            if (n_sp > 0) {
+                for (int q = tid; q < n_sp; q += NT) {
+                    const int k = __ldg(PD.special + (s1 - 1 + q));
+                    const uint32_t w = (n_sp == 1) ? 0u : (uint32_t)__ldg(PD.special + PD.n_special + (s1 - 1 + q));
+                    sk[k] = hap_word_prob(w, fA, fR, nloc);
+                }
+                __syncthreads();
+            }
+        }
     };
-    auto special_prob = [&](int k, int g) -> double {
-        const int s1 = __ldg(PD.helper + g), e1 = __ldg(PD.helper + PD.Tc + g);
-        const uint32_t w = (uint32_t)special_search(k, PD.special, PD.n_special, s1, e1);
-        return hap_word_prob(w, fA, fR, min(32, P.nSNPs - 32 * g));
-    };
+    auto special_prob = [&](int k, int g) -> double { return sk[k]; };
 
     // ================================================================= forward
     double a[EPT];
@@ -419,64 +432,57 @@ __global__ void __launch_bounds__(HAP_NT) k_hap_fb(HapParams P, const HapJob* __
             }
         }
         if (want_dosage) {
-            // matched_gammas(symbol) += gamma (:2083-2096), special haplotypes bit by bit (:2101-2128), then the table (:2133-2139)
-            stage_grid(g, false, 1.0, false);  // (only the barriers: scol is not needed, fA / fR unused here)
-            for (int i = lane; i < NM1; i += 32) mgw[(size_t)warp * MGS + i] = 0.0;
-            if (lane < 32) dpart[warp * 32 + lane] = 0.0;
-            __syncwarp();
-            const uint8_t* col = hm + (size_t)g * K;
-            const int nloc = min(32, P.nSNPs - 32 * g);
+            // matched_gammas(symbol) = sum of gamma over the haplotypes showing the symbol (:2083-2096) — through the panel's
+            // per-grid index of haplotypes sorted by symbol (built once per panel): gamma goes to shared memory, warp w adds the
+            // segments of symbols w, w + NW, ... in a fixed order; special haplotypes bit by bit (:2101-2128); then the table
+            // (:2133-2139) with the grid's words staged in shared memory.
+            __syncthreads();
 #pragma unroll
             for (int i = 0; i < EPT; i++) {
                 const int k = tid + i * NT;
-                const bool in = k < K;
-                const int dh = in ? col[k] : -1;
-                // lanes holding the same symbol combine (fixed order: ascending lane), the lowest lane adds to the warp's bin
-                const unsigned peers = __match_any_sync(0xffffffffu, dh);
+                if (k < K) sk[k] = gm[i];
+            }
+            for (int i = tid; i < NM1; i += NT) swords[i] = (i > 0) ? (uint32_t)__ldg(PD.distinctHapsB + (size_t)g * P.nMaxDH + (i - 1)) : 0u;
+            __syncthreads();
+            const int nloc = min(32, P.nSNPs - 32 * g);
+            const uint16_t* __restrict__ perm = PD.hap_perm + (size_t)g * K;
+            const int32_t* __restrict__ soff = PD.hap_symoff + (size_t)g * (NM1 + 1);
+            for (int sym = 1 + warp; sym < NM1; sym += NW) {
+                const int o0 = soff[sym], o1 = soff[sym + 1];
                 double acc = 0;
-                unsigned rem = peers;
-                while (rem) {
-                    const int src = __ffs(rem) - 1;
-                    rem &= rem - 1;
-                    acc += __shfl_sync(peers, gm[i], src);
-                }
-                if (in && dh > 0 && lane == __ffs(peers) - 1) mgw[(size_t)warp * MGS + dh] += acc;
-                __syncwarp();
-                if (in && dh == 0) {
-                    // special haplotype: its own word
-                    const int s1 = __ldg(PD.helper + g), e1 = __ldg(PD.helper + PD.Tc + g);
-                    const uint32_t w = (uint32_t)special_search(k, PD.special, PD.n_special, s1, e1);
-                    const double gk = gm[i] * njp;
-                    for (int bb = 0; bb < nloc; bb++) atomicAdd(&dpart[warp * 32 + bb], gk * (((w >> bb) & 1u) ? ome : eps));
-                }
-            }
-            __syncthreads();
-            // column of per-symbol sums, scaled by not_jump_prob (matched_gammas *= not_jump_prob)
-            for (int i = tid; i < NM1; i += NT) {
-                double s = 0;
+                for (int q = o0 + lane; q < o1; q += 32) acc += sk[perm[q]];
 #pragma unroll
-                for (int w = 0; w < NW; w++) s += mgw[(size_t)w * MGS + i];
-                scol[i] = s * njp;
+                for (int d = 16; d >= 1; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+                if (lane == 0) scol[sym] = acc * njp;  // matched_gammas *= not_jump_prob
+            }
+            {
+                // special haplotypes: segment 0 of the index is the grid's special rows in order
+                const int s1 = __ldg(PD.helper + g), e1 = __ldg(PD.helper + PD.Tc + g);
+                const int n_sp = (s1 > 0 && e1 >= s1) ? e1 - s1 + 1 : 0;
+                double acc = 0;
+                for (int q = warp; q < n_sp; q += NW) {
+                    const int k = __ldg(PD.special + (s1 - 1 + q));
+                    const uint32_t w = (n_sp == 1) ? 0u : (uint32_t)__ldg(PD.special + PD.n_special + (s1 - 1 + q));
+                    const double gk = sk[k] * njp;
+                    acc += gk * (((w >> lane) & 1u) ? ome : eps);
+                }
+                dpart[warp * 32 + lane] = acc;
             }
             __syncthreads();
-            // dosage(s + b) = specials + sum_dh IE(dh, s + b) * matched_gammas(dh + 1): warp w sums its slice of symbols for every SNP
             {
                 double acc = 0;
                 if (lane < nloc)
-                    for (int dh = warp; dh < P.nMaxDH; dh += NW) {
-                        const uint32_t w = (uint32_t)__ldg(PD.distinctHapsB + (size_t)g * P.nMaxDH + dh);
-                        acc += (((w >> lane) & 1u) ? ome : eps) * scol[dh + 1];
-                    }
-                mgw[warp * 32 + lane] = acc;  // (mgw is free again)
+                    for (int dh = warp; dh < P.nMaxDH; dh += NW) acc += (((swords[dh + 1] >> lane) & 1u) ? ome : eps) * scol[dh + 1];
+                mgw[warp * 32 + lane] = acc;
             }
             __syncthreads();
             if (tid < nloc) {
-                double s = 0;
+                double sd = 0;
 #pragma unroll
-                for (int w = 0; w < NW; w++) s += dpart[w * 32 + tid];
+                for (int w = 0; w < NW; w++) sd += dpart[w * 32 + tid];
 #pragma unroll
-                for (int w = 0; w < NW; w++) s += mgw[w * 32 + tid];
-                J.dosage[32 * g + tid] = s;
+                for (int w = 0; w < NW; w++) sd += mgw[w * 32 + tid];
+                J.dosage[32 * g + tid] = sd;
             }
         }
         const double x = J.c[g] * njp;
@@ -492,9 +498,9 @@ __global__ void __launch_bounds__(HAP_NT) k_hap_fb(HapParams P, const HapJob* __
     }
 }
 
-__host__ inline size_t hap_smem_bytes(int nMaxDH) {
+__host__ inline size_t hap_smem_bytes(int nMaxDH, int K) {
     const int NM1 = nMaxDH + 1, NW = HAP_NT / 32, MGS = NM1 > 32 ? NM1 : 32;
-    return (size_t)(((NM1 + 1) & ~1) + 64 + 2 * NW + (size_t)NW * MGS + NW * 32) * 8 + (size_t)NW * HAP_MAXTOP * 8;
+    return (size_t)(((NM1 + 1) & ~1) + 64 + 2 * NW + (size_t)NW * MGS + NW * 32) * 8 + (size_t)NW * HAP_MAXTOP * 8 + (size_t)((NM1 + 1) & ~1) * 4 + (size_t)K * 8;
 }
 
 }  // namespace qb

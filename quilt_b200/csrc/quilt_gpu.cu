@@ -223,6 +223,7 @@ struct PanelEntry {
     PanelKey key;
     PanelDev dev;
     DBuf buf;
+    DBuf hap_index;  // per-grid index of haplotypes sorted by symbol (built on the first full-panel pass)
     uint64_t last_use = 0;
 };
 std::vector<std::shared_ptr<PanelEntry>> g_panels;  // a staged batch holds a reference: eviction never frees a panel in use
@@ -2106,7 +2107,8 @@ namespace {
 double g_hap_ms = 0, g_hap_bytes = 0;
 
 int launch_hap_fb(int ept, const HapParams& P, const HapJob* dj, int n, const PanelDev& pd) {
-    const size_t sm = hap_smem_bytes(P.nMaxDH);
+    const size_t sm = hap_smem_bytes(P.nMaxDH, P.K);
+    if (sm > 227 * 1024) return set_err(QUILT_ERR_UNSUPPORTED, "full-panel pass: the panel does not fit one CTA's shared memory");
 #define QB_HAP(E)                                                                                      \
     {                                                                                                  \
         CK(cudaFuncSetAttribute(k_hap_fb<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));   \
@@ -2122,6 +2124,39 @@ int launch_hap_fb(int ept, const HapParams& P, const HapJob* dj, int n, const Pa
 }
 }  // namespace
 
+namespace {
+// haplotypes of every grid sorted by symbol (stable counting sort), once per panel
+int ensure_hap_index(const QuiltPanel* p, PanelEntry& e) {
+    if (e.hap_index.p) {
+        e.dev.hap_perm = (const uint16_t*)e.hap_index.p;
+        e.dev.hap_symoff = (const int32_t*)((const char*)e.hap_index.p + al((size_t)p->K_full * p->nGrids * 2));
+        return QUILT_OK;
+    }
+    const int K = p->K_full, T = p->nGrids, NM2 = p->nMaxDH + 2;
+    if (K > 65536) return set_err(QUILT_ERR_UNSUPPORTED, "full-panel pass: K_full > 65536");
+    std::vector<uint16_t> perm((size_t)K * T);
+    std::vector<int32_t> off((size_t)T * NM2);
+    parallel_for(T, [&](int g) {
+        const uint8_t* col = p->hapMatcherR + (size_t)g * K;
+        int32_t* o = off.data() + (size_t)g * NM2;
+        std::vector<int32_t> cnt((size_t)NM2, 0);
+        for (int k = 0; k < K; k++) cnt[std::min<int>(col[k], p->nMaxDH) + 1]++;
+        for (int i = 1; i < NM2; i++) cnt[(size_t)i] += cnt[(size_t)i - 1];
+        for (int i = 0; i < NM2; i++) o[i] = cnt[(size_t)i];
+        std::vector<int32_t> pos(cnt.begin(), cnt.end() - 1);
+        uint16_t* pg = perm.data() + (size_t)g * K;
+        for (int k = 0; k < K; k++) pg[pos[std::min<int>(col[k], p->nMaxDH)]++] = (uint16_t)k;
+    });
+    const size_t b_perm = al(perm.size() * 2);
+    CK(e.hap_index.alloc(b_perm + al(off.size() * 4)));
+    CK(cudaMemcpy(e.hap_index.p, perm.data(), perm.size() * 2, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy((char*)e.hap_index.p + b_perm, off.data(), off.size() * 4, cudaMemcpyHostToDevice));
+    e.dev.hap_perm = (const uint16_t*)e.hap_index.p;
+    e.dev.hap_symoff = (const int32_t*)((const char*)e.hap_index.p + b_perm);
+    return QUILT_OK;
+}
+}  // namespace
+
 int quilt_gpu_haploid_dosage_versus_refs_batch(int32_t n, const QuiltHaploidArgs* args, QuiltHaploidOut* out) {
     std::lock_guard<std::mutex> lk(g_mu);
     if (n < 1 || !args || !out || !args[0].panel) return set_err(QUILT_ERR_BAD_ARG, "bad arguments");
@@ -2130,6 +2165,8 @@ int quilt_gpu_haploid_dosage_versus_refs_batch(int32_t n, const QuiltHaploidArgs
     PanelDev pd;
     std::shared_ptr<PanelEntry> keep;
     if ((rc = get_panel(args[0].panel, &pd, &keep)) != QUILT_OK) return rc;
+    if ((rc = ensure_hap_index(args[0].panel, *keep)) != QUILT_OK) return rc;
+    pd = keep->dev;
     const int K = pd.K_full, T = pd.Tc, nS = pd.nSNPsC, NM1 = pd.nMaxDH + 1;
     if (T < 2) return set_err(QUILT_ERR_BAD_ARG, "the full-panel pass needs at least two grids");
     if (K > HAP_NT * 32) return set_err(QUILT_ERR_UNSUPPORTED, "full-panel pass: K_full > 16384 needs the multi-CTA form (not built); use the mspbwt selection for such panels");
@@ -2248,6 +2285,85 @@ int quilt_gpu_haploid_last_timing(double* kernel_ms, double* algorithmic_bytes) 
     std::lock_guard<std::mutex> lk(g_mu);
     if (kernel_ms) *kernel_ms = g_hap_ms;
     if (algorithmic_bytes) *algorithmic_bytes = g_hap_bytes;
+    return QUILT_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------------ per-sample summary
+namespace {
+const double* job_hap_dev(const QuiltGpuBatch* B, int job) {
+    const HostJob& j = B->jobs[(size_t)job];
+    return j.lo.hap_dev_only ? (const double*)((const char*)B->doutB.p + j.outB_off + j.lo.hap) : (const double*)((const char*)B->dout().p + j.out_off + j.lo.hap);
+}
+}  // namespace
+
+int quilt_gpu_samples_summary(int32_t n_samples, int32_t nSNPs, const QuiltSampleSummary* S, double* infoCount, double* afCount, double* hweCount) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (n_samples < 1 || nSNPs < 1 || !S) return set_err(QUILT_ERR_BAD_ARG, "bad arguments");
+    int rc = ensure_device();
+    if (rc != QUILT_OK) return rc;
+    size_t n_ptr = 0;
+    for (int q = 0; q < n_samples; q++) {
+        const QuiltSampleSummary& s = S[q];
+        if (s.n_calls < 1 || !s.calls || !s.phasing.batch) return set_err(QUILT_ERR_BAD_ARG, "sample without stored calls / phasing call");
+        for (int c = 0; c <= s.n_calls; c++) {
+            const QuiltSummaryCall& cc = c < s.n_calls ? s.calls[c] : s.phasing;
+            if (!cc.batch || !cc.batch->ran || cc.job < 0 || cc.job >= cc.batch->n) return set_err(QUILT_ERR_BAD_ARG, "summary call refers to a batch that has not run / a bad job");
+            const QuiltGibbsArgs& a = cc.batch->jobs[(size_t)cc.job].a;
+            if (a.nSNPs != nSNPs) return set_err(QUILT_ERR_BAD_ARG, "summary calls must all be on the same SNP axis");
+            if (!(a.flags & QUILT_F_SAMPLE_IS_DIPLOID)) return set_err(QUILT_ERR_UNSUPPORTED, "the device summary handles diploid samples (recast_nipt_haps is not built)");
+        }
+        n_ptr += (size_t)s.n_calls;
+    }
+    const size_t ns = (size_t)nSNPs;
+    const size_t per = al(ns * 8) + al(ns * 24) + al(ns * 16) + al(ns * 2) + 2 * al(ns * 8) + al(ns);
+    const size_t b_ptr = al(n_ptr * 8), b_s = al((size_t)n_samples * sizeof(SumSample)), b_cnt = al(ns * 16) + al(ns * 8) + al(ns * 24);
+    DBuf buf;
+    CK(buf.alloc((size_t)n_samples * per + b_ptr + b_s + b_cnt));
+    char* d = (char*)buf.p;
+    const double** d_ptr = (const double**)(d + (size_t)n_samples * per);
+    SumSample* d_s = (SumSample*)(d + (size_t)n_samples * per + b_ptr);
+    char* d_cnt = d + (size_t)n_samples * per + b_ptr + b_s;
+    std::vector<const double*> h_ptr;
+    std::vector<SumSample> h_s((size_t)n_samples);
+    for (int q = 0; q < n_samples; q++) {
+        const QuiltSampleSummary& s = S[q];
+        SumSample& J = h_s[(size_t)q];
+        J.call_hp = d_ptr + h_ptr.size();
+        for (int c = 0; c < s.n_calls; c++) h_ptr.push_back(job_hap_dev(s.calls[c].batch, s.calls[c].job));
+        J.phase_hp = job_hap_dev(s.phasing.batch, s.phasing.job);
+        J.n_calls = s.n_calls;
+        char* o = d + (size_t)q * per;
+        J.dosage = (double*)o, o += al(ns * 8);
+        J.gp = (double*)o, o += al(ns * 24);
+        J.hd = (double*)o, o += al(ns * 16);
+        J.gt = (int8_t*)o, o += al(ns * 2);
+        J.eij = (double*)o, o += al(ns * 8);
+        J.fij = (double*)o, o += al(ns * 8);
+        J.maxgen = (int8_t*)o;
+    }
+    CK(cudaMemcpyAsync(d_ptr, h_ptr.data(), n_ptr * 8, cudaMemcpyHostToDevice, g_stream));
+    CK(cudaMemcpyAsync(d_s, h_s.data(), (size_t)n_samples * sizeof(SumSample), cudaMemcpyHostToDevice, g_stream));
+    k_sample_summary<<<dim3((nSNPs + 255) / 256, n_samples), 256, 0, g_stream>>>(d_s, nSNPs);
+    LAUNCHED();
+    double* d_info = (double*)d_cnt;
+    double* d_af = (double*)(d_cnt + al(ns * 16));
+    double* d_hwe = (double*)(d_cnt + al(ns * 16) + al(ns * 8));
+    k_info_counts<<<(nSNPs + 255) / 256, 256, 0, g_stream>>>(d_s, n_samples, nSNPs, d_info, d_af, d_hwe);
+    LAUNCHED();
+    CK(cudaGetLastError());
+    for (int q = 0; q < n_samples; q++) {
+        const QuiltSampleSummary& s = S[q];
+        const SumSample& J = h_s[(size_t)q];
+        if (s.dosage) CK(cudaMemcpyAsync(s.dosage, J.dosage, ns * 8, cudaMemcpyDeviceToHost, g_stream));
+        if (s.gp_t) CK(cudaMemcpyAsync(s.gp_t, J.gp, ns * 24, cudaMemcpyDeviceToHost, g_stream));
+        if (s.hd) CK(cudaMemcpyAsync(s.hd, J.hd, ns * 16, cudaMemcpyDeviceToHost, g_stream));
+        if (s.gt) CK(cudaMemcpyAsync(s.gt, J.gt, ns * 2, cudaMemcpyDeviceToHost, g_stream));
+    }
+    if (infoCount) CK(cudaMemcpyAsync(infoCount, d_info, ns * 16, cudaMemcpyDeviceToHost, g_stream));
+    if (afCount) CK(cudaMemcpyAsync(afCount, d_af, ns * 8, cudaMemcpyDeviceToHost, g_stream));
+    if (hweCount) CK(cudaMemcpyAsync(hweCount, d_hwe, ns * 24, cudaMemcpyDeviceToHost, g_stream));
+    CK(cudaStreamSynchronize(g_stream));
     return QUILT_OK;
 }
 

@@ -441,4 +441,110 @@ __global__ void __launch_bounds__(SEL_RANK_NT) k_sel_rank(SelParams P, const Sel
     }
 }
 
+// ------------------------------------------------------------------------------------------------ per-sample summary
+// R-side reductions after the Gibbs calls of a sample (QUILT/R/functions.R:999-1020, :1304-1325, recast_haps :3180-3209,
+// eij / fij / max_gen :1408-1411), one thread per SNP, the stored calls added in the reference's order.
+struct SumSample {
+    const double* const* call_hp;  // [n_calls] device pointers to hapProbs_t ([3][nSNPs] column-major)
+    const double* phase_hp;
+    int32_t n_calls;
+    double* dosage;   // [nSNPs]
+    double* gp;       // [3][nSNPs] column-major (element (i, s) at 3 s + i)
+    double* hd;       // [2][nSNPs] -> column-major [nSNPs x 2]
+    int8_t* gt;       // [nSNPs x 2]
+    double* eij;      // [nSNPs]
+    double* fij;      // [nSNPs]
+    int8_t* maxgen;   // [nSNPs] 0-based arg-max genotype
+};
+__device__ __forceinline__ double r_round3(double x) { return rint(x * 1000.0) / 1000.0; }
+
+// grid = (ceil(nSNPs / 256), samples)
+__global__ void __launch_bounds__(256) k_sample_summary(const SumSample* __restrict__ S, int nSNPs) {
+    const SumSample& J = S[blockIdx.y];
+    const int s = blockIdx.x * 256 + threadIdx.x;
+    if (s >= nSNPs) return;
+    double dosage = 0, g0 = 0, g1 = 0, g2 = 0;
+    for (int c = 0; c < J.n_calls; c++) {
+        const double* hp = J.call_hp[c];
+        const double hap1 = hp[3 * (size_t)s], hap2 = hp[3 * (size_t)s + 1];
+        dosage = dosage + hap1 + hap2;                               // dosage <- dosage + hap1 + hap2
+        g0 = g0 + (1 - hap1) * (1 - hap2);                           // gp_t <- gp_t + rbind(...)
+        g1 = g1 + ((1 - hap1) * hap2 + hap1 * (1 - hap2));
+        g2 = g2 + hap1 * hap2;
+    }
+    // recast_haps(hd1, hd2, gp = t(gp_t)) with the sums as they stand at the phasing iteration (the arg-max is scale-free)
+    double hd1 = J.phase_hp[3 * (size_t)s], hd2 = J.phase_hp[3 * (size_t)s + 1];
+    {
+        const double gt1 = rint(hd1) + rint(hd2);
+        double max_val = g0;
+        int gt3 = 0;
+        if (g1 > max_val) {
+            gt3 = 1;
+            max_val = g1;
+        }
+        if (g2 > max_val) {
+            gt3 = 2;
+            max_val = g2;
+        }
+        if ((double)gt3 != gt1) {
+            if (gt3 == 0) {
+                hd1 = 0;
+                hd2 = 0;
+            } else if (gt3 == 2) {
+                hd1 = 1;
+                hd2 = 1;
+            } else {
+                const bool first = hd1 > hd2;
+                hd1 = first ? 1 : 0;
+                hd2 = first ? 0 : 1;
+            }
+        }
+    }
+    const double n = (double)J.n_calls;
+    dosage = dosage / n;
+    g0 = g0 / n;
+    g1 = g1 / n;
+    g2 = g2 / n;
+    J.dosage[s] = dosage;
+    J.gp[3 * (size_t)s] = g0;
+    J.gp[3 * (size_t)s + 1] = g1;
+    J.gp[3 * (size_t)s + 2] = g2;
+    J.hd[s] = hd1;
+    J.hd[(size_t)nSNPs + s] = hd2;
+    J.gt[s] = (int8_t)rint(hd1);
+    J.gt[(size_t)nSNPs + s] = (int8_t)rint(hd2);
+    J.eij[s] = r_round3(g1 + 2 * g2);
+    J.fij[s] = r_round3(g1 + 4 * g2);
+    int mg = 0;  // get_max_gen_rapid: the first maximum
+    double mv = g0;
+    if (g1 > mv) {
+        mg = 1;
+        mv = g1;
+    }
+    if (g2 > mv) mg = 2;
+    J.maxgen[s] = (int8_t)mg;
+}
+
+// per-rank counters over the samples IN ORDER (quilt.R:957-961): one thread per SNP
+__global__ void __launch_bounds__(256) k_info_counts(const SumSample* __restrict__ S, int n_samples, int nSNPs, double* __restrict__ info /*[2][nSNPs]*/,
+                                                     double* __restrict__ af, double* __restrict__ hwe /*[3][nSNPs]*/) {
+    const int s = blockIdx.x * 256 + threadIdx.x;
+    if (s >= nSNPs) return;
+    double i1 = 0, i2 = 0, a = 0, h[3] = {0, 0, 0};
+    for (int q = 0; q < n_samples; q++) {
+        const double e = S[q].eij[s], f = S[q].fij[s];
+        i1 = i1 + e;
+        i2 = i2 + (f - e * e);
+        a = a + e / 2;
+        const int mg = S[q].maxgen[s];
+        h[0] += mg == 0;
+        h[1] += mg == 1;
+        h[2] += mg == 2;
+    }
+    info[s] = i1;
+    info[(size_t)nSNPs + s] = i2;
+    af[s] = a;
+    for (int q = 0; q < 3; q++) hwe[(size_t)q * nSNPs + s] = h[q];
+}
+
 }  // namespace qb

@@ -108,6 +108,8 @@ struct PanelDev {
     const int32_t* rare_snps;
     const int8_t* asm_src;         // [T_all][32] all-SNP grid G, bit b: -1 rare, else (common word select << 5) | source bit
     const int32_t* asm_cg0;        // [T_all] first common-axis grid an all-SNP grid draws from
+    const uint16_t* hap_perm;      // [Tc][K_full] haplotypes sorted by their symbol at the grid (stable) — full-panel pass only
+    const int32_t* hap_symoff;     // [Tc][nMaxDH + 2] segment offsets of hap_perm per symbol
     const int32_t* n_used;         // [Tc] rows of distinctHapsB in use per grid (= max symbol of hapMatcherR[, g])
     double ref_error;
 };

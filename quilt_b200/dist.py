@@ -147,6 +147,42 @@ def sum_over_ranks(x: float, device=None) -> float:
     return float(t.item())
 
 
+def allreduce_info_counts(counts: dict, device=None) -> dict:
+    """The one data reduction of the path: every rank holds the INFO-score / allele-frequency / HWE counters of
+    its own samples (infoCount [nSNPs x 2], afCount [nSNPs], hweCount [nSNPs x 3], alleleCount [nSNPs x 2]; QUILT/R/quilt.R:957-961) and
+    the writer needs their sums over all samples (QUILT/R/writers.R:38-47).  One all-reduce (NCCL on a GPU box, gloo in the CPU tests) of
+    the concatenated counters, < 10 MB."""
+    import torch
+    import torch.distributed as td
+
+    if not td.is_initialized() or td.get_world_size() == 1:
+        return {k: np.array(v, dtype=np.float64, copy=True) for k, v in counts.items()}
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device()) if td.get_backend() == "nccl" else torch.device("cpu")
+    keys = sorted(counts)
+    flat = np.concatenate([np.asarray(counts[k], dtype=np.float64).ravel(order="F") for k in keys])
+    t = torch.from_numpy(flat).to(device)
+    td.all_reduce(t, op=td.ReduceOp.SUM)
+    flat = t.cpu().numpy()
+    out, o = {}, 0
+    for k in keys:
+        a = np.asarray(counts[k])
+        out[k] = flat[o:o + a.size].reshape(a.shape, order="F").copy()
+        o += a.size
+    return out
+
+
+def info_scores(total: dict, N: int) -> dict:
+    """the writer's finalisation of the summed counters (QUILT/R/writers.R:48-60): INFO score and estimated allele frequency"""
+    theta = total["infoCount"][:, 0] / 2 / N
+    denom = 2 * N * theta * (1 - theta)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        info = 1 - total["infoCount"][:, 1] / denom
+    info[(np.round(theta, 2) == 0) | (np.round(theta, 2) == 1)] = 1
+    info[info < 0] = 0
+    return {"info": info, "estimatedAlleleFrequency": total["afCount"] / N}
+
+
 def barrier():
     import torch.distributed as td
 

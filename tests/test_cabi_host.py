@@ -122,6 +122,14 @@ lo, hi = dist.sample_range(7, rank, world)
 t = dist.max_over_ranks(float(rank + 1))
 s = dist.sum_over_ranks(float(hi - lo))
 assert t == world and s == 7.0, (t, s)
+# INFO counters: every rank holds the sums over its own samples; the writer needs the totals (quilt.R:957-961, writers.R:38-47)
+rng = np.random.default_rng(100 + rank)
+mine = {"infoCount": rng.random((640, 2)), "afCount": rng.random(640), "hweCount": rng.integers(0, 5, (640, 3)).astype(float), "alleleCount": rng.random((640, 2))}
+tot = dist.allreduce_info_counts(mine)
+want = {k: sum(np.asarray({"infoCount": np.random.default_rng(100 + r).random((640, 2))}["infoCount"]) for r in range(world)) for k in ("infoCount",)}
+assert np.allclose(tot["infoCount"], want["infoCount"]) and tot["hweCount"].shape == (640, 3)
+sc = dist.info_scores(tot, N=7)
+assert sc["info"].shape == (640,) and np.all(sc["info"] >= 0)
 dist.barrier()
 print("ok", rank)
 '''

@@ -81,23 +81,39 @@ def test_reference_pass_special_haplotypes(ref):
     assert np.max(np.abs(a["gamma_t"] - b["gamma_t"])) < 1e-9
 
 
-def _cmp(g, r, tag):
+def _cmp(g, r, tag, cols=None):
     d_dos = float(np.max(np.abs(g["dosage"] - r["dosage"])))
     d_gam = float(np.max(np.abs(g["gamma_t"] - r["gamma_t"])))
     rel = lambda x, y: float(np.max(np.abs(x - y) / (np.abs(y) + 1e-300)))  # noqa: E731
     print(f"[{tag}] |d dosage| {d_dos:.2e} |d gamma| {d_gam:.2e} alpha rel {rel(g['alphaHat_t'], r['alphaHat_t']):.2e} beta rel {rel(g['betaHat_t'], r['betaHat_t']):.2e} c rel {rel(g['c'], r['c']):.2e}")
     assert d_dos <= 1e-10 and d_gam <= 1e-10
     assert rel(g["alphaHat_t"], r["alphaHat_t"]) <= 1e-9 and rel(g["betaHat_t"], r["betaHat_t"]) <= 1e-9 and rel(g["c"], r["c"]) <= 1e-9
-    assert np.array_equal(g["best_haps_count"], r["best_haps_count"])
-    assert np.array_equal(g["best_haps"], r["best_haps"]), "best-match haplotypes at the thinned grids"
-    assert np.max(np.abs(g["best_haps_values"] - r["best_haps_values"])) <= 1e-10
+    # best matches at the thinned grids: "every haplotype whose gamma reaches the K_top-th largest".  Panels with many identical
+    # haplotypes produce exact ties (kept identical by both implementations) next to NEAR ties between different haplotypes, which a
+    # 1e-16 relative difference in gamma resolves either way: haplotypes clearly above the threshold must be listed, none clearly below
+    cols_thin = np.nonzero(cols >= 0)[0] if cols is not None else []
+    cap = g["best_haps"].shape[1]
+    for t, grid in enumerate(cols_thin):
+        gam = r["gamma_t"][:, grid]
+        thr = np.sort(gam)[-5]
+        sure = set(np.nonzero(gam > thr * (1 + 1e-9))[0].tolist())
+        maybe = set(np.nonzero(gam >= thr * (1 - 1e-9))[0].tolist())
+        got = set(int(x) for x in g["best_haps"][t][: min(int(g["best_haps_count"][t]), cap)])
+        if g["best_haps_count"][t] <= cap:
+            assert sure <= got <= maybe, (t, grid, sorted(sure - got), sorted(got - maybe))
+            assert len(maybe) >= g["best_haps_count"][t] >= len(sure)
+        lst = g["best_haps"][t][: min(int(g["best_haps_count"][t]), cap)]
+        assert np.all(np.diff(lst) > 0), "haplotype order"
+        vals = g["best_haps_values"][t][: len(lst)]
+        assert np.max(np.abs(vals - gam[lst])) <= 1e-10
 
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("seed", [1, 2])
 def test_gpu_pass_equals_reference(gpu, ref, small_world, small_reads, seed):
     gl, cols = _inputs(small_world, small_reads.common, seed, h=seed)
-    _cmp(gpu.haploid_dosage(small_world.panel, gl, small_world.transMatRate, cols), ref.haploid_dosage(small_world.panel, gl, small_world.transMatRate, cols), f"K_full=600 seed {seed}")
+    _cmp(gpu.haploid_dosage(small_world.panel, gl, small_world.transMatRate, cols, best_cap=128), ref.haploid_dosage(small_world.panel, gl, small_world.transMatRate, cols, best_cap=128),
+         f"K_full=600 seed {seed}", cols)
 
 
 @pytest.mark.gpu
@@ -105,7 +121,7 @@ def test_gpu_pass_special_haplotypes(gpu, ref):
     w = synth.make_world(21, K_full=150, nSNPs=640, region_bp=60_000, nMaxDH=5, n_founders=30)
     sr = synth.make_sample_reads(w, 22, coverage=2.0, region_bp=60_000)
     gl, cols = _inputs(w, sr.common, 3)
-    _cmp(gpu.haploid_dosage(w.panel, gl, w.transMatRate, cols), ref.haploid_dosage(w.panel, gl, w.transMatRate, cols), "special haplotypes")
+    _cmp(gpu.haploid_dosage(w.panel, gl, w.transMatRate, cols, best_cap=128), ref.haploid_dosage(w.panel, gl, w.transMatRate, cols, best_cap=128), "special haplotypes", cols)
 
 
 @pytest.mark.gpu
@@ -116,7 +132,7 @@ def test_gpu_pass_lazy_normalisation_kicks_in(gpu, ref, small_world):
     gl, cols = _inputs(small_world, sr.common, 5)
     r = ref.haploid_dosage(small_world.panel, gl, small_world.transMatRate, cols)
     assert np.sum(np.abs(r["alphaHat_t"].sum(axis=0) - 1) < 1e-9) < small_world.panel.nGrids, "every grid normalised: the lazy path is not exercised"
-    _cmp(gpu.haploid_dosage(small_world.panel, gl, small_world.transMatRate, cols), r, "coverage 40")
+    _cmp(gpu.haploid_dosage(small_world.panel, gl, small_world.transMatRate, cols), r, "coverage 40", cols)
 
 
 @pytest.mark.gpu
@@ -125,4 +141,4 @@ def test_gpu_pass_full_panel_size(gpu, ref):
     w = synth.make_world(20260118, K_full=5008, nSNPs=32000, region_bp=3_000_000)
     sr = synth.make_sample_reads(w, 4000, coverage=1.0, region_bp=3_000_000)
     gl, cols = _inputs(w, sr.common, 7)
-    _cmp(gpu.haploid_dosage(w.panel, gl, w.transMatRate, cols), ref.haploid_dosage(w.panel, gl, w.transMatRate, cols), "K_full=5008 T=1000")
+    _cmp(gpu.haploid_dosage(w.panel, gl, w.transMatRate, cols, best_cap=128), ref.haploid_dosage(w.panel, gl, w.transMatRate, cols, best_cap=128), "K_full=5008 T=1000", cols)
