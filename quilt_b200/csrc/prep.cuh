@@ -189,6 +189,8 @@ __global__ void __launch_bounds__(TAB_WARPS * 32) k_build_tables(BatchParams P, 
     const int g = blockIdx.x, Kp = P.Kp, T = P.T;
     const int r0 = J.rs[g], r1 = J.rs[g + 1];
     if (r0 >= r1) return;
+    const int nC = J.cinfo ? J.cinfo[g] : 0;  // > 0: every read of the grid is a table-mode run and the class records exist
+    if (nC == 0)
     for (int i = threadIdx.x; i < 3 * Kp; i += TAB_WARPS * 32) {
         const int w = i / Kp, k = i - w * Kp;
         const int gg = g - 1 + w;
@@ -218,6 +220,17 @@ __global__ void __launch_bounds__(TAB_WARPS * 32) k_build_tables(BatchParams P, 
     }
     __syncwarp();
     // 2. how many of the K haplotypes show each pattern
+    if (nC > 0) {
+        // the grid has haplotype classes (classes.cuh): members of a class show the same pattern — add the class sizes
+        const uint4* rec = J.crec + (size_t)g * (CLS_LANES * 32);
+        for (int c = lane; c < nC; c += 32) {
+            const uint4 v = rec[c];
+            const uint32_t lo = d.g0rel < 0 ? v.x : (d.g0rel == 0 ? v.y : v.z), hi = d.g0rel < 0 ? v.y : v.z;
+            const uint32_t pat = __funnelshift_r(lo, hi, d.b0) & ((1u << d.nb) - 1u);
+            atomicAdd(&hs[pat], (int)(v.w >> 16));
+        }
+        __syncwarp();
+    } else
     // (lanes showing the same pattern elect one leader that adds their count: no shared-memory atomics)
     // (four independent match.any per trip: the instruction is slow, its latency is what bounds this loop)
     for (int k0 = 0; k0 < P.K; k0 += 128) {

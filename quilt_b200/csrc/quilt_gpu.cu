@@ -31,6 +31,7 @@
 #include "select.cuh"
 #include "haploid.cuh"
 #include "prep.cuh"
+#include "classes.cuh"
 #include "sweep.cuh"
 #include "types.h"
 
@@ -531,6 +532,8 @@ struct Bucket {
     size_t slot_bytes = 0;
     // slot layout
     size_t o_alpha, o_beta, o_eG, o_c, o_W, o_Wc, o_tabs, o_dense, o_xprob, o_snp_type, o_rate, o_hapLocal, o_blk;
+    size_t o_cinfo, o_cperm, o_ccls, o_cent, o_crec;  // haplotype classes (classes.cuh)
+    bool classes = false;
     char* slots = nullptr;  // into the batch's slot arena (buckets run one after the other and share it)
     DBuf djobs;
     HBuf hjobs;
@@ -921,6 +924,9 @@ void make_params(const QuiltGibbsArgs& a, BatchParams* P) {
     }
     const char* bm = std::getenv("QUILT_B200_DBG");
     P->dbg = bm ? (uint32_t)std::atoi(bm) : 0u;
+    // grids with fewer visited reads walk all K states: the class totals cost about as much as six K-long reads (QUILT_B200_CLS_MIN: experiments)
+    const char* cm = std::getenv("QUILT_B200_CLS_MIN");
+    P->cls_min_reads = cm ? std::atoi(cm) : 8;
 }
 
 // the three-haplotype (NIPT) instance exists for geometries whose shared-memory ring fits (K <= 2048)
@@ -947,7 +953,7 @@ cudaError_t launch_cl(void (*kern)(KArgs...), int n_ctas, int nt, size_t smem, i
 }
 
 template <int NT, int EPT>
-int sweep_occupancy(int Kp, int NH, int CL, int* occ, int* smem) {
+int sweep_occupancy(int Kp, int NH, int CL, bool cls, int* occ, int* smem) {
     const SweepSmemLayout L = sweep_smem_layout(NT * EPT, NH, NT, CL);
     *smem = L.total;
     if (CL == 2) {
@@ -960,7 +966,10 @@ int sweep_occupancy(int Kp, int NH, int CL, int* occ, int* smem) {
             return set_err(QUILT_ERR_UNSUPPORTED, "no cluster sweep kernel for this geometry");
         }
     }
-    if (NH == 2) {
+    if (NH == 2 && cls) {
+        CK(cudaFuncSetAttribute(k_sweep<NT, EPT, 2, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, k_sweep<NT, EPT, 2, 1, true>, NT, L.total));
+    } else if (NH == 2) {
         CK(cudaFuncSetAttribute(k_sweep<NT, EPT, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, k_sweep<NT, EPT, 2>, NT, L.total));
     } else if constexpr (nipt_geo<NT, EPT>()) {
@@ -975,8 +984,16 @@ int sweep_occupancy(int Kp, int NH, int CL, int* occ, int* smem) {
 int setup_bucket(QuiltGpuBatch* B, Bucket& bk, size_t* mem_budget) {
     const BatchParams& P = bk.P;
     if (!pick_geo(P.K, &bk.geo, P.NH)) return set_err(QUILT_ERR_UNSUPPORTED, "Ksubset too large");
+    for (int ji : bk.jobs) bk.R_max = std::max(bk.R_max, B->jobs[ji].R);
+    // haplotype classes in the sweep kernel (classes.cuh): diploid calls, one CTA per job, and enough reads per grid for the
+    // per-grid class totals to pay (common-SNP calls: ~16 visited reads per grid; all-SNP calls: ~6, they keep the K-long instance)
+    {
+        const char* e = std::getenv("QUILT_B200_CLASSES");  // tests / experiments: 0 = never, 1 = whenever possible
+        const int cls_env = e ? 1 + std::atoi(e) : 0;
+        bk.classes = (P.NH == 2 && bk.geo.CL == 1) && (cls_env == 2 || (cls_env == 0 && (double)bk.R_max >= 10.0 * P.T));
+    }
     int occ = 0, smem = 0;
-    int rc = with_geo(bk.geo, [&](auto nt, auto ept) { return sweep_occupancy<decltype(nt)::value, decltype(ept)::value>(P.Kp, P.NH, bk.geo.CL, &occ, &smem); });
+    int rc = with_geo(bk.geo, [&](auto nt, auto ept) { return sweep_occupancy<decltype(nt)::value, decltype(ept)::value>(P.Kp, P.NH, bk.geo.CL, bk.classes, &occ, &smem); });
     if (rc != QUILT_OK) return rc;
     if (occ < 1) return set_err(QUILT_ERR_UNSUPPORTED, "sweep kernel does not fit on an SM for this K");
     for (int ji : bk.jobs) {
@@ -1000,6 +1017,15 @@ int setup_bucket(QuiltGpuBatch* B, Bucket& bk, size_t* mem_budget) {
     bk.o_rate = o, o += al((size_t)P.T * 8);
     bk.o_hapLocal = o, o += al(P.rare_common ? (size_t)P.nSNPs * 24 : 0);
     bk.o_blk = o, o += al(P.NH == 3 ? BlockScratch::bytes(P.T) : 0);
+    // haplotype classes of the sweep kernel
+    {
+        const size_t KA = (size_t)bk.geo.NT * bk.geo.EPT, Tn = bk.classes ? (size_t)P.T : 0;
+        bk.o_cinfo = o, o += al((Tn + 1) * 4);
+        bk.o_cperm = o, o += al(Tn * KA * 2);
+        bk.o_ccls = o, o += al(Tn * KA);
+        bk.o_cent = o, o += al(Tn * bk.geo.NT);
+        bk.o_crec = o, o += al(Tn * CLS_LANES * 32 * 16);
+    }
     bk.slot_bytes = o;
     int cap = (g_sms / bk.geo.CL) * occ;
     const size_t by_mem = std::max<size_t>(1, *mem_budget / std::max<size_t>(bk.slot_bytes, 1));
@@ -1033,6 +1059,11 @@ void make_jobdev(const QuiltGpuBatch* B, const Bucket& bk, const HostJob& j, int
     D->snp_type = (uint8_t*)(s + bk.o_snp_type);
     D->rate = (double*)(s + bk.o_rate);
     D->hapLocal = (double*)(s + bk.o_hapLocal);
+    D->cinfo = bk.classes ? (int32_t*)(s + bk.o_cinfo) : nullptr;
+    D->cperm = (uint16_t*)(s + bk.o_cperm);
+    D->ccls = (uint8_t*)(s + bk.o_ccls);
+    D->cent = (uint8_t*)(s + bk.o_cent);
+    D->crec = (uint4*)(s + bk.o_crec);
     D->which = (const int32_t*)(in + j.li.which);
     D->rs = (const int32_t*)(in + j.li.rs);
     D->roff = (const int32_t*)(in + j.li.roff);
@@ -1099,6 +1130,13 @@ int run_prep(QuiltGpuBatch* B, Bucket& bk, int n, const JobDev* dj) {
         k_unpack_common<<<dim3(kb, P.T, n), 256, 0, g_stream>>>(B->panel, dj, P.K, P.Kp, 0);
         LAUNCHED();
     }
+    if (bk.classes) {
+        const int KA = bk.geo.NT * bk.geo.EPT;
+        const size_t csm = class_dyn_smem(P.Kp, KA);
+        CK(cudaFuncSetAttribute(k_build_classes, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csm));
+        k_build_classes<<<dim3(P.T, n), CLS_NT, csm, g_stream>>>(P, dj, bk.geo.NT, bk.geo.EPT);
+        LAUNCHED();
+    }
     {
         const int tsm = 3 * P.Kp * 4;
         CK(cudaFuncSetAttribute(k_build_tables, cudaFuncAttributeMaxDynamicSharedMemorySize, tsm));
@@ -1125,6 +1163,8 @@ int run_wave_t(QuiltGpuBatch* B, Bucket& bk, int n, const JobDev* dj, bool timed
         } else {
             return set_err(QUILT_ERR_UNSUPPORTED, "no cluster sweep kernel for this geometry");
         }
+    } else if (P.NH == 2 && bk.classes) {
+        CK(cudaFuncSetAttribute(k_sweep<NT, EPT, 2, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
     } else if (P.NH == 2) {
         CK(cudaFuncSetAttribute(k_sweep<NT, EPT, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
     } else if constexpr (nipt_geo<NT, EPT>()) {
@@ -1163,6 +1203,8 @@ int run_wave_t(QuiltGpuBatch* B, Bucket& bk, int n, const JobDev* dj, bool timed
         const int store_alpha = (it >= P.n_burn || (P.NH == 3 && blk_next) || bk.debug || it == P.n_its - 1) ? 1 : 0;
         if (CL == 2) {
             if constexpr (NT == 256 && EPT == 16) CK(launch_cl(k_sweep<NT, EPT, 2, 2>, 2 * n, NT, (size_t)L.total, 2, P, dj, it, store_alpha));
+        } else if (P.NH == 2 && bk.classes) {
+            k_sweep<NT, EPT, 2, 1, true><<<n, NT, L.total, g_stream>>>(P, dj, it, store_alpha);
         } else if (P.NH == 2) {
             k_sweep<NT, EPT, 2><<<n, NT, L.total, g_stream>>>(P, dj, it, store_alpha);
         } else if constexpr (nipt_geo<NT, EPT>()) {

@@ -57,7 +57,7 @@ constexpr int SW_BMAX = 16;  // reads decided per round of the batched resampler
 static_assert(SW_MAXTAB >= (1 << NBMAX), "a single emission table must fit the staging buffer");
 
 struct SweepSmemLayout {
-    int off_bar, off_red, off_cnt, off_sc, off_small[2], off_pat, off_part, off_rec, off_W, off_eG, total;
+    int off_bar, off_red, off_cnt, off_sc, off_small[2], off_pat, off_part, off_rec, off_cls, off_W, off_eG, total;
     int small_desc, small_tab, small_U, small_H;
 };
 __host__ __device__ inline SweepSmemLayout sweep_smem_layout(int KA, int NH, int NT, int CL = 1) {
@@ -85,6 +85,8 @@ __host__ __device__ inline SweepSmemLayout sweep_smem_layout(int KA, int NH, int
     L.off_part = o;
     L.off_rec = o;  // chunking scratch of grids whose reads exceed one staging buffer
     o += 64;
+    L.off_cls = o;  // class path (diploid, one CTA per job): class totals / column factors [2][CLS_AS] + per-warp scan carries [NT / 32][4]
+    if (NH == 2 && CL == 1) o += 2 * CLS_AS * 8 + (NT / 32) * 32;
     o = (o + 127) & ~127;
     L.off_W = o;
     o += 4 * KA * 4;
@@ -488,7 +490,7 @@ __device__ __forceinline__ void upd_loop(double (&am)[NH][EPT], double (&ab)[NH]
 // CL = 2: the job's K states are split over the two CTAs of a thread-block cluster (K > NT * EPT): CTA `crank` owns
 // k in [crank * KA, crank * KA + KA); block sums meet through distributed shared memory (BlockSumV<NT, 2>), both CTAs
 // take every decision redundantly.
-template <int NT, int EPT, int NH, int CL = 1>
+template <int NT, int EPT, int NH, int CL = 1, bool CLSP = false>
 __global__ void __launch_bounds__(NT, (NT * EPT <= 512 ? 4 : (NT * EPT <= 1024 ? 2 : 1))) k_sweep(BatchParams P, const JobDev* __restrict__ jobs, int iteration, int store_alpha) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ JobDev Js;
@@ -506,6 +508,10 @@ __global__ void __launch_bounds__(NT, (NT * EPT <= 512 ? 4 : (NT * EPT <= 1024 ?
     // (per-job scalars — labels, c, label-probability records, the sweep record — are written by both CTAs: the values
     //  are bit-identical, and each CTA only ever reads back what it wrote itself)
     const int T = P.T, R = J.R;
+    // class path: reads of a grid whose haplotypes fall into <= CLS_MAX classes are decided on class totals (classes.cuh)
+    // (CLSP: the instance for calls with many reads per grid — common-SNP calls; calls with few reads per grid run the
+    //  instance without it, whose K-long path keeps the registers to itself)
+    constexpr bool CLS_ON = CLSP && (NH == 2 && CL == 1);
     const SweepSmemLayout L = sweep_smem_layout(KA, NH, NT, CL);
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L.off_bar);
     BlockSumV<NT, CL> bsum(reinterpret_cast<double*>(smem + L.off_red), crank);
@@ -583,10 +589,12 @@ __global__ void __launch_bounds__(NT, (NT * EPT <= 512 ? 4 : (NT * EPT <= 1024 ?
             // first staging chunk}, transition pair, previous c
             unsigned char* sc = smem + L.off_sc + s * 96;
             const int q = (NT > 32) ? tid - 32 : tid;
-            if (q >= 0 && q < 12 + 2 * NH) {
+            if (q >= 0 && q < 12 + 2 * NH + (CLS_ON ? 1 : 0)) {
                 const int32_t* src;
                 bool ok = true;
-                if (q < 8) {
+                if (CLS_ON && q == 12 + 2 * NH) {
+                    src = J.cinfo + g + 1;  // classes of the next grid
+                } else if (q < 8) {
                     src = J.ginfo + 4 * (g + 1) + q;
                     ok = g + 1 + (q >> 2) <= T;
                 } else if (q < 12) {
@@ -687,6 +695,7 @@ __global__ void __launch_bounds__(NT, (NT * EPT <= 512 ? 4 : (NT * EPT <= 1024 ?
     // per-grid scalars arrive with the package (cp.async into the stage's scalar block): nothing on the serial chain
     // waits for a dependent global load
     int cur_r0 = J.ginfo[0], cur_t0 = J.ginfo[1], cur_fcn = J.ginfo[2], cur_fct = J.ginfo[3];
+    int cur_nC = (CLS_ON && !(P.dbg & 16)) ? J.cinfo[0] : 0;
     issue_pkg(0, cur_r0, rs[1], cur_t0, cur_fcn, cur_fct);
     issue_eG(0);
     // =============================================================== forward + read resampling
@@ -702,6 +711,8 @@ __global__ void __launch_bounds__(NT, (NT * EPT <= 512 ? 4 : (NT * EPT <= 1024 ?
         const int fcn = cur_fcn, fct = cur_fct;        // first staging chunk of this grid (already in shared memory)
         const int nx_fcn = sci[2], nx_fct = sci[3];    // ... of the next grid
         const int nx_r1 = sci[4];
+        const int nC = cur_nC;
+        if (CLS_ON) cur_nC = (P.dbg & 16) ? 0 : sci[12 + 2 * NH];
         const double tm_x = scd[4], tm_t1 = scd[5];
         const int n_g = r1 - r0;
         const bool has = n_g > 0;
@@ -734,6 +745,27 @@ __global__ void __launch_bounds__(NT, (NT * EPT <= 512 ? 4 : (NT * EPT <= 1024 ?
                 for (int l = (NT > 32 ? tid - 32 : tid); l >= 0 && l < lines; l += (NT > 32 ? NT - 32 : NT)) {
                     const int h = l / (Kpl >> 4), q = l - h * (Kpl >> 4);
                     prefetch_l2(betaG + ((size_t)h * T + g + 1) * Kp + (q << 4));
+                }
+            }
+        }
+        // class path of this grid (classes.cuh)?  Its layouts are pulled towards L2 one grid ahead and loaded after the forward step.
+        bool use_cls = false;
+        if (CLS_ON) {
+            use_cls = has && nC > 0 && !(iterative && (iteration == 0 || (iteration == 1 && r0 < J.first_read)));
+            if (cur_nC > 0 && g + 1 < T) {
+                // sorted list (2 KA bytes), thread-major classes (KA), entering classes (NT), class records (CLS_LANES * 512)
+                constexpr int L_PERM = (2 * KA + 127) >> 7, L_CLS = (KA + 127) >> 7, L_ENT = (NT + 127) >> 7, L_REC = (CLS_LANES * 32 * 16) >> 7;
+                for (int l = tid; l < L_PERM + L_CLS + L_ENT + L_REC; l += NT) {
+                    const char* p;
+                    if (l < L_PERM)
+                        p = reinterpret_cast<const char*>(J.cperm + (size_t)(g + 1) * KA) + ((size_t)l << 7);
+                    else if (l < L_PERM + L_CLS)
+                        p = reinterpret_cast<const char*>(J.ccls + (size_t)(g + 1) * KA) + ((size_t)(l - L_PERM) << 7);
+                    else if (l < L_PERM + L_CLS + L_ENT)
+                        p = reinterpret_cast<const char*>(J.cent + (size_t)(g + 1) * NT) + ((size_t)(l - L_PERM - L_CLS) << 7);
+                    else
+                        p = reinterpret_cast<const char*>(J.crec + (size_t)(g + 1) * (CLS_LANES * 32)) + ((size_t)(l - L_PERM - L_CLS - L_ENT) << 7);
+                    prefetch_l2(p);
                 }
             }
         }
@@ -794,6 +826,44 @@ __global__ void __launch_bounds__(NT, (NT * EPT <= 512 ? 4 : (NT * EPT <= 1024 ?
         }
         // am now holds alphaHat_t[:, g]; it stays in registers as the previous column of the next grid
         QB_T(2);
+        // class path: worth its per-grid set-up (class totals, column factors) only with enough reads to visit.  The sorted
+        // haplotype list, the classes of this thread's own elements and the records of this thread's classes are L2 hits
+        // (prefetched one grid ahead), consumed after ab_m has been formed.
+        constexpr int CPT = (CLS_LANES * 32 + NT - 1) / NT;  // classes per thread: class tid + j * NT
+        uint32_t pq[EPT / 2];  // sorted positions [EPT * tid, EPT * tid + EPT): haplotype | first-of-its-class << 15
+        uint32_t cq[EPT / 4];  // class of element i of this thread in byte i
+        uint32_t cwp[CPT], cw0[CPT], cwn[CPT];  // allele words of this thread's classes (previous / own / next grid, masked)
+        int ent1 = 0;
+        uint64_t vis = 0;      // bit ir: read ir of the grid is visited (uninformative reads never are, gibbs-nipt.cpp:815)
+        if (CLS_ON && use_cls) {
+            const ReadDesc* dsc = reinterpret_cast<const ReadDesc*>(smem + L.off_small[s] + L.small_desc);
+            const int lane = tid & 31;
+            const bool va = (lane < fcn) && (reinterpret_cast<const uint4*>(dsc + lane)->y & 0xff) != 1;
+            const bool vb = (32 + lane < fcn) && (reinterpret_cast<const uint4*>(dsc + 32 + lane)->y & 0xff) != 1;
+            vis = (uint64_t)__ballot_sync(0xffffffffu, va) | ((uint64_t)__ballot_sync(0xffffffffu, vb) << 32);
+            use_cls = __popcll(vis) >= P.cls_min_reads;
+        }
+        if (CLS_ON && use_cls) {
+            const uint4* gp = reinterpret_cast<const uint4*>(J.cperm + (size_t)g * KA + (size_t)EPT * tid);
+#pragma unroll
+            for (int q = 0; q < EPT / 8; q++) {
+                const uint4 v = __ldg(gp + q);
+                pq[4 * q] = v.x, pq[4 * q + 1] = v.y, pq[4 * q + 2] = v.z, pq[4 * q + 3] = v.w;
+            }
+            const uint2* gc = reinterpret_cast<const uint2*>(J.ccls + (size_t)g * KA + (size_t)EPT * tid);
+#pragma unroll
+            for (int q = 0; q < EPT / 8; q++) {
+                const uint2 v = __ldg(gc + q);
+                cq[2 * q] = v.x, cq[2 * q + 1] = v.y;
+            }
+            ent1 = __ldg(J.cent + (size_t)g * NT + tid);
+            const uint4* gr = J.crec + (size_t)g * (CLS_LANES * 32) + tid;
+#pragma unroll
+            for (int j = 0; j < CPT; j++) {
+                const uint4 v = (tid + j * NT < CLS_LANES * 32) ? __ldg(gr + NT * j) : make_uint4(0u, 0u, 0u, 0u);
+                cwp[j] = v.x, cw0[j] = v.y, cwn[j] = v.z;
+            }
+        }
         if (g + 1 < T && (P.dbg & 2)) issue_pkg(g + 1, r1, nx_r1, ts1, nx_fcn, nx_fct);  // experiment: issue after the forward step
         bool changed = false;
         if (has) {
@@ -820,7 +890,7 @@ __global__ void __launch_bounds__(NT, (NT * EPT <= 512 ? 4 : (NT * EPT <= 1024 ?
                 mbar_wait(&bar[5], n_useB & 1);
                 n_useB++;
                 beta_pending = false;
-                const double* bs = eGs + (size_t)((s ^ 1) * NH) * KA;
+                double* bs = eGs + (size_t)((s ^ 1) * NH) * KA;
 #pragma unroll
                 for (int h = 0; h < NH; h++) {
 #pragma unroll
@@ -830,12 +900,21 @@ __global__ void __launch_bounds__(NT, (NT * EPT <= 512 ? 4 : (NT * EPT <= 1024 ?
                     }
                     sv[h] = Col<NT, EPT>::sum(ab[h]);
                 }
+                if (CLS_ON && use_cls) {
+                    // class path: ab_m takes the place of beta in the ring buffer (each thread overwrites what it has just read),
+                    // to be gathered in class order; the buffer moves on to eMatGrid[:, g + 1] after the gather
+#pragma unroll
+                    for (int h = 0; h < NH; h++)
+#pragma unroll
+                        for (int i = 0; i < EPT; i++) bs[h * KA + tid + i * NT] = ab[h][i];
+                    fence_proxy_async();
+                }
                 bsum.run(sv);  // (every thread is past its reads of the beta buffer)
                 pC.a = sv[0];
                 pC.b = sv[1];
                 if (NH == 3) pC.c = sv[NH - 1];
                 inited = true;
-                if (!eG_next_issued) {
+                if (!eG_next_issued && !(CLS_ON && use_cls)) {
                     issue_eG(g + 1);
                     eG_next_issued = true;
                 }
@@ -996,6 +1075,247 @@ __global__ void __launch_bounds__(NT, (NT * EPT <= 512 ? 4 : (NT * EPT <= 1024 ?
                 }
             };
 
+            bool cls_done = false;
+            if constexpr (CLS_ON) {
+            if (use_cls) {
+                cls_done = true;
+                // ---------------------------------------------------------------- class path (classes.cuh)
+                // The grid's reads only distinguish the nC <= CLS_MAX haplotype classes of the grid, so the two K-long sums of a
+                // read are sums over class totals of ab_m: thread t keeps the totals of class t (both labels) and the factor its
+                // class has accumulated; per read one table look-up, two products and the block sum.  alphaHat_m / eMatGrid
+                // receive the accumulated factor of their class once, at the end of the grid.
+                const int lane = tid & 31, warp = tid >> 5;
+                constexpr int NW = NT / 32;
+                double* As = reinterpret_cast<double*>(smem + L.off_cls);  // [CLS_AS][2]: {label 0, label 1} of class c at index c + 1
+                double* wsc = As + 2 * CLS_AS;                             // [NW][4] carries of the segmented scan
+                double A0[CPT], A1[CPT], M0[CPT], M1[CPT];
+                QB_T(11);
+                init_ab();
+                QB_T(3);
+                // ---- class totals of ab_m: thread t owns the sorted positions [EPT t, EPT t + EPT); runs of one class inside a
+                //      thread are added in order, runs that span threads meet in a segmented scan (fixed tree)
+                {
+                    const double* abS = eGs + (size_t)((s ^ 1) * NH) * KA;
+                    double v0[EPT], v1[EPT];
+#pragma unroll
+                    for (int j = 0; j < EPT; j++) {
+                        const int k = (int)((pq[j >> 1] >> ((j & 1) * 16)) & 0x7fffu);
+                        v0[j] = abS[k];
+                        v1[j] = abS[KA + k];
+                    }
+                    double rs0 = 0, rs1 = 0, P0 = 0, P1 = 0;
+                    bool seen = false;
+                    int c1 = ent1;
+#pragma unroll
+                    for (int j = 0; j < EPT; j++) {
+                        const bool head = ((pq[j >> 1] >> ((j & 1) * 16 + 15)) & 1u) != 0;
+                        if (head) {
+                            if (!seen) {
+                                P0 = rs0;  // the class that entered the thread ends here
+                                P1 = rs1;
+                                seen = true;
+                            } else {
+                                *reinterpret_cast<double2*>(As + 2 * c1) = make_double2(rs0, rs1);  // a class that lies inside the thread
+                            }
+                            c1++;
+                            rs0 = 0;
+                            rs1 = 0;
+                        }
+                        rs0 += v0[j];
+                        rs1 += v1[j];
+                    }
+                    // (x, f): the sum the thread hands on — its last run if a class starts inside it, else its whole range
+                    double x0 = rs0, x1 = rs1;
+                    bool f = seen;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const double y0 = __shfl_up_sync(0xffffffffu, x0, d), y1 = __shfl_up_sync(0xffffffffu, x1, d);
+                        const int gf = __shfl_up_sync(0xffffffffu, (int)f, d);
+                        if (lane >= d && !f) {
+                            x0 = y0 + x0;
+                            x1 = y1 + x1;
+                            f = gf != 0;
+                        }
+                    }
+                    if (NW > 1) {
+                        if (lane == 31) {
+                            wsc[warp * 4] = x0;
+                            wsc[warp * 4 + 1] = x1;
+                            wsc[warp * 4 + 2] = f ? 1.0 : 0.0;
+                        }
+                        __syncthreads();
+                    }
+                    double w0 = 0, w1 = 0;
+#pragma unroll
+                    for (int w = 0; w < NW - 1; w++) {
+                        if (w < warp) {
+                            const double a = wsc[w * 4], b = wsc[w * 4 + 1];
+                            const bool fw = wsc[w * 4 + 2] != 0.0;
+                            w0 = fw ? a : w0 + a;
+                            w1 = fw ? b : w1 + b;
+                        }
+                    }
+                    const double p0 = __shfl_up_sync(0xffffffffu, x0, 1), p1 = __shfl_up_sync(0xffffffffu, x1, 1);
+                    const int pf = __shfl_up_sync(0xffffffffu, (int)f, 1);
+                    double cin0 = w0, cin1 = w1;
+                    if (lane > 0) {
+                        cin0 = pf ? p0 : w0 + p0;
+                        cin1 = pf ? p1 : w1 + p1;
+                    }
+                    if (seen) *reinterpret_cast<double2*>(As + 2 * ent1) = make_double2(cin0 + P0, cin1 + P1);
+                    if (tid == NT - 1) *reinterpret_cast<double2*>(As + 2 * c1) = make_double2(seen ? rs0 : cin0 + rs0, seen ? rs1 : cin1 + rs1);
+                }
+                __syncthreads();  // class totals complete; every thread is past its gather from the ring buffer
+                if (!eG_next_issued) {
+                    issue_eG(g + 1);
+                    eG_next_issued = true;
+                }
+#pragma unroll
+                for (int j = 0; j < CPT; j++) {
+                    const int c = tid + NT * j;
+                    const double2 a = (c < nC) ? *reinterpret_cast<const double2*>(As + 2 * (c + 1)) : make_double2(0.0, 0.0);
+                    A0[j] = a.x;
+                    A1[j] = a.y;
+                    M0[j] = 1.0;
+                    M1[j] = 1.0;
+                }
+                // (the exchange buffer carries the column factors at the end of the grid: every thread writes the slots it has just
+                //  read, nobody else touches them in between)
+                QB_T(12);
+                // ---- the grid's reads; the emission values of the next visited read are fetched while the current one is decided
+#define QB_CLS_LOAD(IR, E_, I_, H_, U_)                                                                  \
+    {                                                                                                    \
+        const uint4 dq_ = *reinterpret_cast<const uint4*>(descs + (IR));                                 \
+        const int nb_ = (dq_.y >> 16) & 0xff;                                                            \
+        const int g0_ = (int)(int8_t)(dq_.y >> 24);                                                      \
+        const uint32_t b0_ = dq_.z & 0xff;                                                               \
+        const uint32_t mask_ = (1u << nb_) - 1u;                                                         \
+        const TabEnt* tab_ = tabs + (dq_.x - (uint32_t)ts0);                                             \
+        _Pragma("unroll") for (int j = 0; j < CPT; j++) {                                                \
+            const uint32_t lo_ = g0_ < 0 ? cwp[j] : (g0_ == 0 ? cw0[j] : cwn[j]);                        \
+            const uint32_t hi_ = g0_ < 0 ? cw0[j] : cwn[j];                                              \
+            const uint32_t pat_ = __funnelshift_r(lo_, hi_, b0_) & mask_;                                \
+            const double2 te_ = *reinterpret_cast<const double2*>(tab_ + pat_);                          \
+            E_[j] = te_.x;                                                                               \
+            I_[j] = te_.y;                                                                               \
+        }                                                                                                \
+        H_ = Hs[(IR)] - 1;                                                                               \
+        U_ = Us[(IR)];                                                                                   \
+    }
+                int ir = __ffsll((long long)vis) - 1;
+                vis &= vis - 1;
+                double Ev[CPT], Iv[CPT], uC;
+                int hC;
+                QB_CLS_LOAD(ir, Ev, Iv, hC, uC)
+                while (true) {
+                    const int r = r0 + ir;
+                    QB_T(11);
+                    QB_N(16);
+                    double sv[NH];
+                    {
+                        double s0 = 0, s1 = 0;
+#pragma unroll
+                        for (int j = 0; j < CPT; j++) {
+                            s0 = fma(hC == 0 ? A0[j] : A1[j], Iv[j], s0);
+                            s1 = fma(hC == 0 ? A1[j] : A0[j], Ev[j], s1);
+                        }
+                        sv[0] = s0;
+                        sv[1] = s1;
+                    }
+                    // the next visited read's static data (independent of this read's outcome)
+                    const bool has_next = vis != 0;
+                    const int ir2 = has_next ? __ffsll((long long)vis) - 1 : ir;
+                    vis &= vis - 1;
+                    double En[CPT], In[CPT], uN;
+                    int hN2;
+                    QB_CLS_LOAD(ir2, En, In, hN2, uN)
+                    QB_T(4);
+                    bsum.run(sv);
+                    QB_T(5);
+                    const FastDecision F = decide_diploid_fast(pC, sv[0], sv[1], hC, uC, prior);
+                    bool change;
+                    if (F.decided) {
+                        change = F.hN != hC;
+                        if (change) {
+                            pC.a = (hC == 0) ? sv[0] : sv[1];
+                            pC.b = (hC == 0) ? sv[1] : sv[0];
+                        }
+                        if (record && tid >= NT - 4) {
+                            const int q = tid - (NT - 4);
+                            const double v = q == 0 ? F.prod_pC : (q == 1 ? F.prod_pA1 : (q == 2 ? F.prod_pA2 : (double)hC));
+                            J.xprob[4 * (size_t)r + q] = v;  // raw products of a read whose label was hC
+                        }
+                    } else {
+                        const Decision D = decide_read<NH>(pC, sv, hC, KIND_NORMAL, uC, prior);
+                        change = D.change;
+                        pC = D.pCnew;
+                        if (record && tid == 0) {
+                            J.xprob[4 * (size_t)r + 0] = D.x.a;
+                            J.xprob[4 * (size_t)r + 1] = D.x.b;
+                            J.xprob[4 * (size_t)r + 2] = D.x.c;
+                            J.xprob[4 * (size_t)r + 3] = -1.0;
+                        }
+                    }
+                    QB_T(6);
+                    if (change) {
+                        QB_N(17);
+                        changed = true;
+                        if (tid == 0) J.H[r] = 2 - hC;  // the other label (1-based)
+                        // gibbs-nipt.cpp:1092-1110 on the class totals and on the accumulated column factors
+                        if (hC == 0) {
+#pragma unroll
+                            for (int j = 0; j < CPT; j++) {
+                                A0[j] = div_by(A0[j], Ev[j], Iv[j]);
+                                M0[j] = div_by(M0[j], Ev[j], Iv[j]);
+                                A1[j] *= Ev[j];
+                                M1[j] *= Ev[j];
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < CPT; j++) {
+                                A1[j] = div_by(A1[j], Ev[j], Iv[j]);
+                                M1[j] = div_by(M1[j], Ev[j], Iv[j]);
+                                A0[j] *= Ev[j];
+                                M0[j] *= Ev[j];
+                            }
+                        }
+                        QB_T(7);
+                    }
+                    if (!has_next) break;
+                    ir = ir2;
+                    hC = hN2;
+                    uC = uN;
+#pragma unroll
+                    for (int j = 0; j < CPT; j++) {
+                        Ev[j] = En[j];
+                        Iv[j] = In[j];
+                    }
+                }
+#undef QB_CLS_LOAD
+                if (changed) {
+                    // every element of alphaHat_m / eMatGrid takes the accumulated factor of its class
+                    QB_T(11);
+#pragma unroll
+                    for (int j = 0; j < CPT; j++) {
+                        const int c = tid + NT * j;
+                        if (c < CLS_LANES * 32) *reinterpret_cast<double2*>(As + 2 * (c + 1)) = make_double2(M0[j], M1[j]);
+                    }
+                    __syncthreads();
+#pragma unroll
+                    for (int i = 0; i < EPT; i++) {
+                        const int c = (int)((cq[i >> 2] >> ((i & 3) * 8)) & 0xffu);
+                        const double2 m = *reinterpret_cast<const double2*>(As + 2 * (c + 1));
+                        const int k = tid + i * NT;
+                        am[0][i] *= m.x;
+                        am[1][i] *= m.y;
+                        eg[k] *= m.x;
+                        eg[KA + k] *= m.y;
+                    }
+                    QB_T(13);
+                }
+            }
+            }
+            if (!cls_done) {
             // ---------------------------------------------------------------- the grid's reads, chunk by chunk
             const bool special_its = iterative && iteration <= 1;  // sweeps with pass-through / initialisation reads
             int c0 = 0;
@@ -1111,6 +1431,7 @@ __global__ void __launch_bounds__(NT, (NT * EPT <= 512 ? 4 : (NT * EPT <= 1024 ?
                 tab0 = tend;
                 c0 += cn;
             }
+            }  // K-long path
 #undef QB_SUM
 #undef QB_SUM_LABELS
 #undef QB_SUM_LOOP
@@ -1314,8 +1635,8 @@ __global__ void __launch_bounds__(NT, (NT * EPT <= 512 ? 4 : (NT * EPT <= 1024 ?
     QB_T(10);
     if (tid == 0 && blockIdx.x == 0 && iteration == QB_CLK_IT) {
         printf("QBCLK it=%d T=%d R=%d wait_pkg=%lld issue=%lld fwd=%lld init_ab=%lld sums=%lld reduce=%lld decide=%lld update=%lld gridend=%lld backward=%lld epilogue=%lld other=%lld "
-               "visited=%lld changed=%lld grids_with_reads=%lld\n",
-               iteration, T, R, clk[0], clk[1], clk[2], clk[3], clk[4], clk[5], clk[6], clk[7], clk[8], clk[9], clk[10], clk[11], clk[16], clk[17], clk[18]);
+               "class_sums=%lld class_apply=%lld visited=%lld changed=%lld grids_with_reads=%lld\n",
+               iteration, T, R, clk[0], clk[1], clk[2], clk[3], clk[4], clk[5], clk[6], clk[7], clk[8], clk[9], clk[10], clk[11], clk[12], clk[13], clk[16], clk[17], clk[18]);
     }
 #endif
 }

@@ -36,6 +36,11 @@ struct ReadDesc {        // 32 bytes, 16-byte aligned (staged to shared memory w
 };
 static_assert(sizeof(ReadDesc) == 32, "ReadDesc must be 32 bytes");
 
+// haplotype classes (k_build_classes / k_sweep): at most CLS_MAX distinct classes per grid, CLS_LANES classes per lane
+constexpr int CLS_LANES = 8;
+constexpr int CLS_MAX = CLS_LANES * 32 - 1;  // one id is left for the padding elements k >= K
+constexpr int CLS_AS = CLS_LANES * 32 + 8;   // stride of the class-sum exchange buffer in shared memory (index = class + 1)
+
 constexpr int LIK_N = 16;  // per-sweep bookkeeping record written by the sweep epilogue
 // lik[0..2] = -sum_g log c_h[g] ; lik[3..5] = #reads with label h ; lik[6..13] = #reads with H_class 0..7 ;
 // lik[14] = 1 if a non-finite sum(c_h) was seen (reference underflow check, gibbs-nipt.cpp:2959-2969)
@@ -72,6 +77,13 @@ struct JobDev {
     const int32_t* ts;     // [T + 1] first table-pool entry of each grid's reads (table-mode reads only)
     const int32_t* ginfo;  // [T + 1][4] per grid {rs, ts, reads in its first staging chunk, table end of that chunk}
     const int32_t* dense_reads;  // [n_dense] read indices stored as dense columns
+    // haplotype classes of the sweep kernel (k_build_classes; diploid, one CTA per job): per grid the K selected haplotypes grouped by
+    // the allele bits the grid's reads can see (own 32-SNP word + the neighbour bits of reads that start / end outside it)
+    int32_t* cinfo;      // [T + 1] classes of the grid, 0 = the grid's reads walk all K states
+    uint16_t* cperm;     // [T][KA] haplotypes sorted by (class, k); bit 15 = first of its class
+    uint8_t* ccls;       // [T][NT][EPT] class of haplotype tid + i * NT at [tid][i]
+    uint8_t* cent;       // [T][NT] 1 + class of sorted position EPT * tid - 1 (0 for tid 0)
+    uint4* crec;         // [T][CLS_LANES * 32] per class {word g-1 & mask, word g, word g+1 & mask, first sorted position | members << 16}
     const double* runif_reads;  // [n_its][R]
     const double* runif_shard;  // [n_ep][T - 1]
     const double* tm;           // [T - 1][2] (sigma, 1 - sigma)
@@ -171,6 +183,7 @@ struct BatchParams {
     int32_t rare_common;
     int32_t Jmax;
     uint32_t dbg;  // experiment switches (env QUILT_B200_DBG; 0 in production)
+    int32_t cls_min_reads;  // the sweep decides a grid's reads on haplotype-class totals when at least this many are visited
     // NIPT block Gibbs (gibbs-nipt-block.cpp): host-evaluated libm constants so that the scores use the reference's values
     int32_t shuffle_bin_radius;
     double block_q;          // block_gibbs_quantile_prob

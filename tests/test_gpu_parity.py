@@ -174,6 +174,26 @@ def test_gibbs_production_common(gpu, oracle, K, iterative):
     _compare(f"production K={K} iterative={iterative}", g, o)
 
 
+@pytest.mark.parametrize("classes", ["0", "1"])
+@pytest.mark.parametrize("kind", ["common", "iterative", "all_snps", "diverse_panel"])
+def test_gibbs_both_sweep_instances(gpu, oracle, small_world, small_reads, monkeypatch, classes, kind):
+    """the sweep kernel has two instances (sweep.cuh): reads decided on haplotype-class totals (classes.cuh; chosen for calls with many reads per
+    grid) and the K-long walk.  Both are forced here on the same calls, including grids that fall back inside the class instance: reads kept as
+    dense columns (all-SNP call), initialisation / pass-through reads (iterative), and a panel with more distinct haplotypes per grid than
+    CLS_MAX (every haplotype carries private flips)."""
+    monkeypatch.setenv("QUILT_B200_CLASSES", classes)
+    if kind == "diverse_panel":
+        w = synth.make_world(4242, K_full=900, nSNPs=1600, region_bp=150_000, n_founders=400, flip_rate=0.03, nMaxDH=255)
+        sr = synth.make_sample_reads(w, 43, coverage=2.0, region_bp=150_000)
+        call = synth.make_call(w, sr.common, 44, K=800, first_iteration=False)
+    elif kind == "all_snps":
+        call = synth.make_call(small_world, small_reads.all, 24, K=600, all_snps=True)
+    else:
+        call = synth.make_call(small_world, small_reads.common, 25, K=600, first_iteration=(kind == "iterative"))
+    g, o = _run_both(gpu, oracle, call)
+    _compare(f"sweep instance classes={classes} {kind}", g, o)
+
+
 @pytest.mark.parametrize("K", [200, 600])
 def test_gibbs_production_all_snps(gpu, oracle, small_world, small_reads, K):
     """the final all-SNP (rare/common) call (rare_common.R:325-391)"""

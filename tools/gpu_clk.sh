@@ -9,4 +9,4 @@ QUILT_B200_LIB=$PWD/quilt_b200/libquiltgpu_clk.so timeout 600 python tools/prof_
 QUILT_B200_LIB=$PWD/quilt_b200/libquiltgpu_clk.so timeout 600 python tools/prof_sweep.py --K 4096 --jobs 148 --its 8 --all-snps > gpurun_out/${TAG}_clk_all.log 2>&1
 timeout 600 python tools/prof_sweep.py --K 4096 --jobs 148 --its 8 > gpurun_out/${TAG}_plain_common.log 2>&1
 grep -h QBCLK gpurun_out/${TAG}_clk_common.log gpurun_out/${TAG}_clk_all.log | head -4
-tail -2 gpurun_out/${TAG}_clk_common.log gpurun_out/${TAG}_plain_common.log
+tail -n 2 gpurun_out/${TAG}_clk_common.log gpurun_out/${TAG}_plain_common.log
