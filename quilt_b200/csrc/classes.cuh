@@ -6,9 +6,9 @@
 // neighbour bits are indistinguishable to every read of the grid: inside sample_reads_in_grid (gibbs-nipt.cpp:733-1295) they
 // always receive the same emission factor.  With C such classes (a few hundred at most on a compressed panel: the
 // distinct-haplotype idea of QUILT2's own hapMatcherR, here on the selected subset and including the read-visible neighbour
-// bits) the K-long sums of the read resampler collapse to C-long sums over class totals of alphaHat_m * betaHat_m, kept per
-// warp in registers by k_sweep.  This kernel builds, once per call and grid:
-//   class ids (rank by member count, ties by key), the haplotypes sorted by (class, k) for the segmented class sums, the
+// bits) the K-long sums of the read resampler collapse to C-long sums over class totals of alphaHat_m * betaHat_m, kept one
+// class per thread by k_sweep.  This kernel builds, once per call and grid:
+//   class ids (rank of the class key), the haplotypes sorted by (class, k) for the segmented class sums, the
 //   thread-major class ids for the lazy column update, the class records {words, offset | count} and cinfo[g] = C (or 0).
 // Everything is a deterministic function of (W, read descriptors): ids never depend on thread timing.
 #pragma once
@@ -24,7 +24,6 @@ constexpr int CLS_NW = CLS_NT / 32;
 
 struct ClassSmem {
     int owner[CLS_HS];      // 0 = empty, else k + 1 of the haplotype that claimed the slot (its key is the slot's key)
-    int scnt[CLS_HS];       // members per slot
     uint16_t scls[CLS_HS];  // slot -> class id
     uint16_t list[256];     // occupied slots
     int ccount[256];        // members per class
@@ -32,6 +31,7 @@ struct ClassSmem {
     int crep[256];          // representative haplotype per class
     uint16_t cntW[CLS_NW][256];  // per-warp members per class (counting sort)
     uint4 crk[256];         // occupied slots, compact: {members, key words} for the ranking loop
+    int wtot[8];            // class-size totals of the eight 32-class groups
     uint32_t mp, mn;        // neighbour bits the grid's reads can see (previous / next word)
     int impure, overflow, ndistinct, nlist;
 };
@@ -54,10 +54,8 @@ __global__ void __launch_bounds__(CLS_NT) k_build_classes(BatchParams P, const J
     uint16_t* sorted = reinterpret_cast<uint16_t*>(clsk + ((Kp + 15) & ~15));
     const int r0 = J.rs[g], r1 = J.rs[g + 1];
     const int n_g = r1 - r0;
-    for (int i = tid; i < CLS_HS; i += CLS_NT) {
-        S.owner[i] = 0;
-        S.scnt[i] = 0;
-    }
+    for (int i = tid; i < CLS_HS; i += CLS_NT) S.owner[i] = 0;
+    if (tid < 256) S.ccount[tid] = 0;
     for (int i = tid; i < CLS_NW * 256; i += CLS_NT) (&S.cntW[0][0])[i] = 0;
     if (tid == 0) {
         S.mp = 0;
@@ -97,6 +95,7 @@ __global__ void __launch_bounds__(CLS_NT) k_build_classes(BatchParams P, const J
             key2[k] = mn ? (J.W[(size_t)(g + 1) * Kp + k] & mn) : 0u;
         }
         __syncthreads();
+        const bool nb_keys = (mp | mn) != 0;  // (most grids: no read sees a neighbour bit, the own word is the whole key)
         for (int k = tid; k < K; k += CLS_NT) {
             const uint32_t a = key0[k], b = key1[k], c = key2[k];
             uint32_t h = (a * 0x9E3779B1u) ^ (b * 0x85EBCA6Bu) ^ (c * 0xC2B2AE35u);
@@ -104,23 +103,24 @@ __global__ void __launch_bounds__(CLS_NT) k_build_classes(BatchParams P, const J
             int s = (int)(h & (CLS_HS - 1));
             bool placed = false;
             while (!*(volatile int*)&S.overflow) {
-                const int o = atomicCAS(&S.owner[s], 0, k + 1);
+                // (nearly every haplotype finds its class already in the table: look before trying to claim)
+                int o = *(volatile int*)&S.owner[s];
                 if (o == 0) {
-                    if (atomicAdd(&S.ndistinct, 1) >= CLS_MAX) S.overflow = 1;
-                    placed = true;
-                    break;
+                    o = atomicCAS(&S.owner[s], 0, k + 1);
+                    if (o == 0) {
+                        if (atomicAdd(&S.ndistinct, 1) >= CLS_MAX) S.overflow = 1;
+                        placed = true;
+                        break;
+                    }
                 }
                 // (the owner's key words were written before the barrier above: plain reads)
-                if (key0[o - 1] == a && key1[o - 1] == b && key2[o - 1] == c) {
+                if (key0[o - 1] == a && (!nb_keys || (key1[o - 1] == b && key2[o - 1] == c))) {
                     placed = true;
                     break;
                 }
                 s = (s + 1) & (CLS_HS - 1);
             }
-            if (placed) {
-                slot_of[k] = (uint16_t)s;
-                atomicAdd(&S.scnt[s], 1);
-            }
+            if (placed) slot_of[k] = (uint16_t)s;
         }
     }
     __syncthreads();
@@ -136,28 +136,33 @@ __global__ void __launch_bounds__(CLS_NT) k_build_classes(BatchParams P, const J
     const int nC = S.nlist;
     if (tid < nC) {
         const int s = S.list[tid], ko = S.owner[s] - 1;
-        S.crk[tid] = make_uint4((uint32_t)S.scnt[s], key0[ko], key1[ko], key2[ko]);
+        S.crk[tid] = make_uint4(0u, key0[ko], key1[ko], key2[ko]);
+    }
+    __syncthreads();
+    {
+        // class id = rank of the key (own word, previous-word bits, next-word bits): CLS_NT / 256 threads per class share the
+        // comparisons (integer counts: the order of the atomic adds does not matter)
+        constexpr int PER = CLS_NT / 256;
+        const int i = tid & 255, part = tid >> 8;
+        if (i < nC) {
+            const uint4 me = S.crk[i];
+            const int q0 = (nC * part) / PER, q1 = (nC * (part + 1)) / PER;
+            int rank = 0;
+            for (int q = q0; q < q1; q++) {
+                const uint4 o = S.crk[q];
+                rank += ((o.y < me.y) || (o.y == me.y && (o.z < me.z || (o.z == me.z && o.w < me.w)))) ? 1 : 0;
+            }
+            atomicAdd(&S.ccount[i], rank);  // (ccount is the scratch of the ranking here; it takes the class sizes below)
+        }
     }
     __syncthreads();
     if (tid < nC) {
-        const uint4 me = S.crk[tid];
-        int rank = 0, off = 0;
-        for (int q = 0; q < nC; q++) {
-            const uint4 o = S.crk[q];  // (broadcast read)
-            const bool key_lt = (o.y < me.y) || (o.y == me.y && (o.z < me.z || (o.z == me.z && o.w < me.w)));
-            const bool before = (o.x > me.x) || (o.x == me.x && key_lt);
-            rank += before ? 1 : 0;
-            off += before ? (int)o.x : 0;
-        }
-        const int s = S.list[tid];
+        const int s = S.list[tid], rank = S.ccount[tid];
         S.scls[s] = (uint16_t)rank;
-        S.ccount[rank] = (int)me.x;
-        S.coffs[rank] = off;
         // representative: any member gives the same key; take the slot's owner (which haplotype claimed the slot depends on
         // timing, its key does not)
         S.crep[rank] = S.owner[s] - 1;
     }
-    if (tid == 0) S.coffs[nC] = K;
     __syncthreads();
     for (int k = tid; k < K; k += CLS_NT) clsk[k] = (uint8_t)S.scls[slot_of[k]];
     __syncthreads();
@@ -177,6 +182,30 @@ __global__ void __launch_bounds__(CLS_NT) k_build_classes(BatchParams P, const J
             if (before == __popc(peers) - 1) S.cntW[warp][c] = (uint16_t)(base + before + 1);  // (the last peer holds the new count)
         }
         __syncwarp();
+    }
+    __syncthreads();
+    // class sizes = the warps' counts; first sorted position per class = exclusive prefix over the class ids
+    if (tid < nC) {
+        int n = 0;
+        for (int w = 0; w < CLS_NW; w++) n += S.cntW[w][tid];
+        S.ccount[tid] = n;
+    }
+    __syncthreads();
+    {
+        // exclusive prefix over the class ids: warp scans of 32 + the warps' totals
+        int v = (tid < nC) ? S.ccount[tid] : 0, incl = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int y = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += y;
+        }
+        if (tid < 256 && lane == 31) S.wtot[warp] = incl;
+        __syncthreads();
+        if (tid <= nC && tid < 257) {
+            int o = 0;
+            for (int w = 0; w < (tid >> 5); w++) o += S.wtot[w];
+            S.coffs[tid] = (tid < 256) ? o + incl - v : o;
+        }
     }
     __syncthreads();
     if (tid < nC) {

@@ -232,7 +232,7 @@ __global__ void __launch_bounds__(TAB_WARPS * 32) k_build_tables(BatchParams P, 
         __syncwarp();
     } else
     // (lanes showing the same pattern elect one leader that adds their count: no shared-memory atomics)
-    // (four independent match.any per trip: the instruction is slow, its latency is what bounds this loop)
+    // (four independent match.any per trip: its latency is what bounds this loop; peer masks from ten ballots measured 55 % slower)
     for (int k0 = 0; k0 < P.K; k0 += 128) {
         uint32_t pat[4], peers[4];
 #pragma unroll
