@@ -326,6 +326,44 @@ typedef struct QuiltSampleSummary {
 int quilt_gpu_samples_summary(int32_t n_samples, int32_t nSNPs, const QuiltSampleSummary* samples,
                               double* infoCount /*[nSNPs x 2] or NULL*/, double* afCount /*[nSNPs]*/, double* hweCount /*[nSNPs x 3]*/);
 
+/*
+ * The steps on either side of the path.
+ *
+ * quilt_gpu_ingest_pileup: one sample's flat pileup (what loadBamAndConvert leaves in sampleReads, QUILT/R/functions.R:243-272:
+ * per read the 0-based SNP indices u, the signed scaled base qualities bq and the 0-based central SNP) -> the reads in the
+ * order the Gibbs path needs them: wif0 = grid[central SNP] (snap_sampleReads_to_grid, :295-298), reads ordered by wif0 (stable),
+ * the first read of every grid, grid_has_read (:314-316), and the sample's allele counts (get_alleleCount, :2779-2800:
+ * alleleCount[, 1] = sum of P(alt), alleleCount[, 2] = sum of P(ref) + P(alt) over the read-SNP entries of the SNP, added in
+ * entry order like increment2N, QUILT/src/copied-from-stitch.cpp:573-579).  BAM decoding stays on the CPU.
+ */
+typedef struct QuiltPileup {
+    int32_t nReads, nSNPs, nGrids;
+    const int32_t* offsets;      /* [nReads + 1]                                    */
+    const int32_t* u;            /* [offsets[nReads]] 0-based SNP index             */
+    const int32_t* bq;           /* [offsets[nReads]] signed scaled base quality    */
+    const int32_t* central_snp;  /* [nReads] 0-based central SNP of the read        */
+    const int32_t* grid;         /* [nSNPs] 0-based grid of every SNP               */
+} QuiltPileup;
+typedef struct QuiltIngestOut {   /* any pointer may be NULL */
+    int32_t* order;              /* [nReads] pileup index of the read at each position of the path order */
+    int32_t* offsets;            /* [nReads + 1] */
+    int32_t* u;                  /* [nU] */
+    int32_t* bq;                 /* [nU] */
+    int32_t* wif0;               /* [nReads] non-decreasing */
+    int32_t* first_read_of_grid; /* [nGrids + 1] */
+    uint8_t* grid_has_read;      /* [nGrids] */
+    double* alleleCount;         /* [nSNPs x 2] column-major */
+} QuiltIngestOut;
+int quilt_gpu_ingest_pileup(const QuiltPileup* in, QuiltIngestOut* out);
+
+/*
+ * quilt_gpu_make_vcf_column: the per-sample VCF column of a diploid sample (QUILT/R/functions.R:1408-1463:
+ * STITCH::rcpp_make_column_of_vcf with the GT replaced by the phased genotype), FORMAT GT:GP:DS:HD, one fixed-width record of
+ * QUILT_VCF_RECORD bytes per SNP, "a|b:%.3f,%.3f,%.3f:%.3f:%.3f,%.3f" (no terminator).
+ */
+#define QUILT_VCF_RECORD 39
+int quilt_gpu_make_vcf_column(int32_t nSNPs, const double* gp_t /*[3 x nSNPs]*/, const double* hd /*[nSNPs x 2]*/, char* out /*[nSNPs][QUILT_VCF_RECORD]*/);
+
 /* component entry points (parity tests of the individual reference functions) */
 int quilt_gpu_make_eMatRead_t(const QuiltGibbsArgs* args, double* eMatRead_t /*[K x nReads]*/,
                               int32_t* read_category /*[nReads] or NULL*/);

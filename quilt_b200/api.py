@@ -181,6 +181,36 @@ def samples_summary(lib: GpuLib, samples, nSNPs: int):
     return outs, cnt
 
 
+def ingest_pileup(lib: GpuLib, offsets, u, bq, central_snp, grid, nGrids: int):
+    """quilt_gpu_ingest_pileup: one sample's flat pileup -> the reads in the order the Gibbs path needs them + allele counts
+    (QUILT/R/functions.R:243-316, :2779-2800).  -> dict(order, offsets, u, bq, wif0, first_read_of_grid, grid_has_read, alleleCount)"""
+    offsets, u, bq, central_snp, grid = (np.ascontiguousarray(x, dtype=np.int32) for x in (offsets, u, bq, central_snp, grid))
+    R, nS, nU = offsets.shape[0] - 1, grid.shape[0], int(offsets[-1])
+    a = cabi.QuiltPileup(R, nS, nGrids, cabi._ptr(offsets, cabi._pi), cabi._ptr(u, cabi._pi), cabi._ptr(bq, cabi._pi), cabi._ptr(central_snp, cabi._pi), cabi._ptr(grid, cabi._pi))
+    res = {"order": np.zeros(R, np.int32), "offsets": np.zeros(R + 1, np.int32), "u": np.zeros(nU, np.int32), "bq": np.zeros(nU, np.int32), "wif0": np.zeros(R, np.int32),
+           "first_read_of_grid": np.zeros(nGrids + 1, np.int32), "grid_has_read": np.zeros(nGrids, np.uint8), "alleleCount": np.zeros((nS, 2), order="F")}
+    o = cabi.QuiltIngestOut(*(cabi._ptr(res[k], cabi._pi) for k in ("order", "offsets", "u", "bq", "wif0", "first_read_of_grid")),
+                            res["grid_has_read"].ctypes.data_as(C.POINTER(C.c_uint8)), cabi._ptr(res["alleleCount"], cabi._pd))
+    fn = lib.lib.quilt_gpu_ingest_pileup
+    fn.argtypes = [C.POINTER(cabi.QuiltPileup), C.POINTER(cabi.QuiltIngestOut)]
+    fn.restype = C.c_int
+    lib._check(fn(C.byref(a), C.byref(o)), "quilt_gpu_ingest_pileup")
+    return res
+
+
+def make_vcf_column(lib: GpuLib, gp_t: np.ndarray, hd: np.ndarray):
+    """quilt_gpu_make_vcf_column: GT:GP:DS:HD text of one diploid sample (QUILT/R/functions.R:1408-1463) -> list of str, one per SNP"""
+    gp_t = np.asfortranarray(gp_t, dtype=np.float64)
+    hd = np.asfortranarray(hd, dtype=np.float64)
+    nS = gp_t.shape[1]
+    out = np.zeros((nS, cabi.VCF_RECORD), dtype=np.uint8)
+    fn = lib.lib.quilt_gpu_make_vcf_column
+    fn.argtypes = [C.c_int32, cabi._pd, cabi._pd, C.c_char_p]
+    fn.restype = C.c_int
+    lib._check(fn(nS, cabi._ptr(gp_t, cabi._pd), cabi._ptr(hd, cabi._pd), out.ctypes.data_as(C.c_char_p)), "quilt_gpu_make_vcf_column")
+    return [bytes(r).decode("ascii") for r in out]
+
+
 def run_chain_prepared(lib: GpuLib, preps, pads, mspbwt_nindices=4, mspbwtL=3, mspbwtM=1):
     """quilt_gpu_gibbs_chain: all stages of the call chain in one call (host buffers in / out).  preps: one lib.prepare(...) per stage;
     pads: [n x Ksubset] uniforms per link.  -> list of result lists"""

@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 SO = os.path.join(_HERE, "libquiltgpu.so")
 SOURCES = ["quilt_gpu.cu"]
-HEADERS = ["types.h", "device_common.cuh", "prep.cuh", "classes.cuh", "sweep.cuh", "passes.cuh", "block_nipt.cuh", "select.cuh", "haploid.cuh", os.path.join("..", "..", "include", "quilt_b200.h")]
+HEADERS = ["types.h", "device_common.cuh", "prep.cuh", "classes.cuh", "io_rows.cuh", "sweep.cuh", "passes.cuh", "block_nipt.cuh", "select.cuh", "haploid.cuh", os.path.join("..", "..", "include", "quilt_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -162,6 +162,34 @@ class QuiltSampleSummary(C.Structure):
     ]
 
 
+class QuiltPileup(C.Structure):
+    _fields_ = [
+        ("nReads", C.c_int32),
+        ("nSNPs", C.c_int32),
+        ("nGrids", C.c_int32),
+        ("offsets", _pi),
+        ("u", _pi),
+        ("bq", _pi),
+        ("central_snp", _pi),
+        ("grid", _pi),
+    ]
+
+
+class QuiltIngestOut(C.Structure):
+    _fields_ = [
+        ("order", _pi),
+        ("offsets", _pi),
+        ("u", _pi),
+        ("bq", _pi),
+        ("wif0", _pi),
+        ("first_read_of_grid", _pi),
+        ("grid_has_read", C.POINTER(C.c_uint8)),
+        ("alleleCount", _pd),
+    ]
+
+
+VCF_RECORD = 39
+
 HF_RETURN_DOSAGE, HF_RETURN_BETAHAT, HF_RETURN_GAMMA, HF_GET_BEST_HAPS, HF_RETURN_ALPHAHAT = 1, 2, 4, 8, 16
 
 

@@ -32,6 +32,7 @@
 #include "haploid.cuh"
 #include "prep.cuh"
 #include "classes.cuh"
+#include "io_rows.cuh"
 #include "sweep.cuh"
 #include "types.h"
 
@@ -2405,6 +2406,118 @@ int quilt_gpu_samples_summary(int32_t n_samples, int32_t nSNPs, const QuiltSampl
     if (infoCount) CK(cudaMemcpyAsync(infoCount, d_info, ns * 16, cudaMemcpyDeviceToHost, g_stream));
     if (afCount) CK(cudaMemcpyAsync(afCount, d_af, ns * 8, cudaMemcpyDeviceToHost, g_stream));
     if (hweCount) CK(cudaMemcpyAsync(hweCount, d_hwe, ns * 24, cudaMemcpyDeviceToHost, g_stream));
+    CK(cudaStreamSynchronize(g_stream));
+    return QUILT_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ ingestion / VCF column
+int quilt_gpu_ingest_pileup(const QuiltPileup* in, QuiltIngestOut* out) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!in || !out || in->nReads < 1 || in->nSNPs < 1 || in->nGrids < 1 || !in->offsets || !in->u || !in->bq || !in->central_snp || !in->grid)
+        return set_err(QUILT_ERR_BAD_ARG, "bad pileup");
+    int rc = ensure_device();
+    if (rc != QUILT_OK) return rc;
+    const int R = in->nReads, nS = in->nSNPs, T = in->nGrids, nU = in->offsets[R];
+    if (nU < R) return set_err(QUILT_ERR_BAD_ARG, "every read needs at least one SNP");
+    for (int r = 0; r < R; r++)
+        if (in->central_snp[r] < 0 || in->central_snp[r] >= nS) return set_err(QUILT_ERR_BAD_ARG, "central SNP outside [0, nSNPs)");
+    for (int s = 0; s < nS; s++)
+        if (in->grid[s] < 0 || in->grid[s] >= T) return set_err(QUILT_ERR_BAD_ARG, "grid outside [0, nGrids)");
+    // convertScaledBQtoProbs (STITCH): bq < 0 -> (1 - eps, eps / 3), bq > 0 -> (eps / 3, 1 - eps) with eps = 10^(-|bq| / 10), libm pow
+    std::vector<double> prob((size_t)nU * 2, 0.0);
+    for (int t = 0; t < nU; t++) {
+        if (in->u[t] < 0 || in->u[t] >= nS) return set_err(QUILT_ERR_BAD_ARG, "SNP index outside [0, nSNPs)");
+        const int bq = in->bq[t];
+        if (bq < 0) {
+            const double eps = std::pow(10, double(bq) / 10);
+            prob[2 * (size_t)t] = 1 - eps;
+            prob[2 * (size_t)t + 1] = eps * (1.0 / 3.0);
+        } else if (bq > 0) {
+            const double eps = std::pow(10, -double(bq) / 10);
+            prob[2 * (size_t)t] = eps * (1.0 / 3.0);
+            prob[2 * (size_t)t + 1] = 1 - eps;
+        }
+    }
+    size_t o = 0;
+    auto take = [&](size_t nb) {
+        const size_t r = o;
+        o += al(nb);
+        return r;
+    };
+    const size_t o_off = take((size_t)(R + 1) * 4), o_u = take((size_t)nU * 4), o_bq = take((size_t)nU * 4), o_cen = take((size_t)R * 4), o_grid = take((size_t)nS * 4);
+    const size_t o_prob = take((size_t)nU * 16), o_wif = take((size_t)R * 4);
+    const size_t o_zero = o;  // counters (zeroed)
+    const size_t o_cntG = take((size_t)(T + 1) * 4), o_fillG = take((size_t)T * 4), o_cntS = take((size_t)(nS + 1) * 4), o_fillS = take((size_t)nS * 4);
+    const size_t o_zero_end = o;
+    const size_t o_ordG = take((size_t)R * 4), o_ordS = take((size_t)nU * 4), o_ncnt = take((size_t)(R + 1) * 4);
+    const size_t o_us = take((size_t)nU * 4), o_bqs = take((size_t)nU * 4), o_wifs = take((size_t)R * 4), o_ac = take((size_t)nS * 16), o_ghr = take((size_t)T);
+    DBuf buf;
+    CK(buf.alloc(o));
+    char* d = (char*)buf.p;
+    CK(cudaMemcpyAsync(d + o_off, in->offsets, (size_t)(R + 1) * 4, cudaMemcpyHostToDevice, g_stream));
+    CK(cudaMemcpyAsync(d + o_u, in->u, (size_t)nU * 4, cudaMemcpyHostToDevice, g_stream));
+    CK(cudaMemcpyAsync(d + o_bq, in->bq, (size_t)nU * 4, cudaMemcpyHostToDevice, g_stream));
+    CK(cudaMemcpyAsync(d + o_cen, in->central_snp, (size_t)R * 4, cudaMemcpyHostToDevice, g_stream));
+    CK(cudaMemcpyAsync(d + o_grid, in->grid, (size_t)nS * 4, cudaMemcpyHostToDevice, g_stream));
+    CK(cudaMemcpyAsync(d + o_prob, prob.data(), (size_t)nU * 16, cudaMemcpyHostToDevice, g_stream));
+    CK(cudaMemsetAsync(d + o_zero, 0, o_zero_end - o_zero, g_stream));
+    IngestDev D;
+    D.R = R, D.nU = nU, D.nSNPs = nS, D.T = T;
+    D.off = (const int32_t*)(d + o_off), D.u = (const int32_t*)(d + o_u), D.bq = (const int32_t*)(d + o_bq), D.central = (const int32_t*)(d + o_cen);
+    D.grid = (const int32_t*)(d + o_grid), D.prob = (const double*)(d + o_prob), D.wif = (int32_t*)(d + o_wif);
+    D.cntG = (int32_t*)(d + o_cntG), D.fillG = (int32_t*)(d + o_fillG), D.ordG = (int32_t*)(d + o_ordG);
+    D.cntS = (int32_t*)(d + o_cntS), D.fillS = (int32_t*)(d + o_fillS), D.ordS = (int32_t*)(d + o_ordS), D.ncnt = (int32_t*)(d + o_ncnt);
+    D.u_s = (int32_t*)(d + o_us), D.bq_s = (int32_t*)(d + o_bqs), D.wif_s = (int32_t*)(d + o_wifs), D.alleleCount = (double*)(d + o_ac), D.grid_has_read = (uint8_t*)(d + o_ghr);
+    const int nmax = std::max(std::max(R, nU), std::max(T, nS));
+    k_ing_count<<<(nmax + 255) / 256, 256, 0, g_stream>>>(D);
+    LAUNCHED();
+    k_exscan_i32<<<1, 1024, 0, g_stream>>>(D.cntG, T);
+    LAUNCHED();
+    k_exscan_i32<<<1, 1024, 0, g_stream>>>(D.cntS, nS);
+    LAUNCHED();
+    k_ing_place<<<(nmax + 255) / 256, 256, 0, g_stream>>>(D);
+    LAUNCHED();
+    k_ing_sort<<<(nmax + 255) / 256, 256, 0, g_stream>>>(D);
+    LAUNCHED();
+    k_ing_lens<<<(R + 255) / 256, 256, 0, g_stream>>>(D);
+    LAUNCHED();
+    k_exscan_i32<<<1, 1024, 0, g_stream>>>(D.ncnt, R);
+    LAUNCHED();
+    k_ing_copy<<<R, 256, 0, g_stream>>>(D);
+    LAUNCHED();
+    k_ing_allele<<<(nS + 255) / 256, 256, 0, g_stream>>>(D);
+    LAUNCHED();
+    CK(cudaGetLastError());
+    if (out->order) CK(cudaMemcpyAsync(out->order, D.ordG, (size_t)R * 4, cudaMemcpyDeviceToHost, g_stream));
+    if (out->offsets) CK(cudaMemcpyAsync(out->offsets, D.ncnt, (size_t)(R + 1) * 4, cudaMemcpyDeviceToHost, g_stream));
+    if (out->u) CK(cudaMemcpyAsync(out->u, D.u_s, (size_t)nU * 4, cudaMemcpyDeviceToHost, g_stream));
+    if (out->bq) CK(cudaMemcpyAsync(out->bq, D.bq_s, (size_t)nU * 4, cudaMemcpyDeviceToHost, g_stream));
+    if (out->wif0) CK(cudaMemcpyAsync(out->wif0, D.wif_s, (size_t)R * 4, cudaMemcpyDeviceToHost, g_stream));
+    if (out->first_read_of_grid) CK(cudaMemcpyAsync(out->first_read_of_grid, D.cntG, (size_t)(T + 1) * 4, cudaMemcpyDeviceToHost, g_stream));
+    if (out->grid_has_read) CK(cudaMemcpyAsync(out->grid_has_read, D.grid_has_read, (size_t)T, cudaMemcpyDeviceToHost, g_stream));
+    if (out->alleleCount) CK(cudaMemcpyAsync(out->alleleCount, D.alleleCount, (size_t)nS * 16, cudaMemcpyDeviceToHost, g_stream));
+    CK(cudaStreamSynchronize(g_stream));
+    return QUILT_OK;
+}
+
+int quilt_gpu_make_vcf_column(int32_t nSNPs, const double* gp_t, const double* hd, char* out) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (nSNPs < 1 || !gp_t || !hd || !out) return set_err(QUILT_ERR_BAD_ARG, "bad arguments");
+    int rc = ensure_device();
+    if (rc != QUILT_OK) return rc;
+    const size_t ns = (size_t)nSNPs;
+    DBuf buf;
+    CK(buf.alloc(al(ns * 24) + al(ns * 16) + al(ns * VCF_REC)));
+    char* d = (char*)buf.p;
+    double* d_gp = (double*)d;
+    double* d_hd = (double*)(d + al(ns * 24));
+    char* d_out = d + al(ns * 24) + al(ns * 16);
+    CK(cudaMemcpyAsync(d_gp, gp_t, ns * 24, cudaMemcpyHostToDevice, g_stream));
+    CK(cudaMemcpyAsync(d_hd, hd, ns * 16, cudaMemcpyHostToDevice, g_stream));
+    k_vcf_column<<<(nSNPs + 255) / 256, 256, 0, g_stream>>>(nSNPs, d_gp, d_hd, d_out);
+    LAUNCHED();
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, d_out, ns * VCF_REC, cudaMemcpyDeviceToHost, g_stream));
     CK(cudaStreamSynchronize(g_stream));
     return QUILT_OK;
 }
