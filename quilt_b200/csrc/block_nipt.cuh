@@ -67,287 +67,318 @@ __global__ void __launch_bounds__(256) k_block_rate(BatchParams P, const JobDev*
     }
 }
 
-// stable merge sort of indices 0..n-1 by key (ascending, or descending when desc), single thread; result in idx
-__device__ inline void stable_sort_idx(const double* key, int n, int32_t* idx, int32_t* tmp, bool desc) {
-    for (int i = 0; i < n; i++) idx[i] = i;
-    int32_t* src = idx;
-    int32_t* dst = tmp;
-    for (int w = 1; w < n; w <<= 1) {
-        for (int lo = 0; lo < n; lo += 2 * w) {
-            const int mid = min(lo + w, n), hi = min(lo + 2 * w, n);
-            int i = lo, j = mid, o = lo;
-            while (i < mid && j < hi) {
-                const double a = key[src[i]], b = key[src[j]];
-                const bool take_right = desc ? (b > a) : (b < a);  // stable: ties keep the left element
-                dst[o++] = take_right ? src[j++] : src[i++];
+// ---------------------------------------------------------------------------------------------------------------------
+// Block definition + "considers" (Rcpp_define_blocked_snps_using_gamma_on_the_fly gibbs-nipt-block.cpp:311-523 with
+// rcpp_make_smoothed_rate / rcpp_determine_where_to_stop copied-from-stitch.cpp:446-567, Rcpp_make_gibbs_considers
+// gibbs-nipt-block.cpp:1307-1553), as one CTA per job:
+//   1. smoothed switch rate: one thread per grid boundary (every window is independent; the additions keep the reference's
+//      order: nearest interval first, left side before right side);
+//   2. both stable orders of the smoothed rate (ascending for the quantile, descending for the peak list) from ONE
+//      all-pairs rank count — no sort;
+//   3. peak picking: the only truly serial part (a peak claims its valley and removes the candidates inside it) is walked by
+//      one warp: 32 list entries are screened per ballot, the two valley walks evaluate 32 steps at a time (prefix minimum by
+//      shuffle scan, first stopping step by ballot), ranges are cleared lane-parallel;
+//   4. block ids, block / read ranges, removal of read-less blocks: flags + block-wide prefix counts.
+// The outputs (n_blocks, grid_start/_end, reads_start/_end, grid_where) are integers defined by comparisons of doubles that
+// are computed with the reference's operation order, so they are identical to the reference's.
+constexpr int BD_NT = 256;
+
+// exclusive prefix count of flag[0..n) into out[0..n) (may alias), returns the total; contiguous chunk per thread
+__device__ inline int bd_scan_excl(const int32_t* flag, int32_t* out, int n, int* s_part /*[BD_NT / 32]*/) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int chunk = (n + BD_NT - 1) / BD_NT;
+    const int lo = min(n, tid * chunk), hi = min(n, lo + chunk);
+    int mine = 0;
+    for (int i = lo; i < hi; i++) mine += flag[i];
+    int incl = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += y;
+    }
+    __syncthreads();  // (s_part may still be read from a previous call)
+    if (lane == 31) s_part[warp] = incl;
+    __syncthreads();
+    int base = incl - mine, total = 0;
+#pragma unroll
+    for (int w = 0; w < BD_NT / 32; w++) {
+        const int v = s_part[w];
+        if (w < warp) base += v;
+        total += v;
+    }
+    for (int i = lo; i < hi; i++) {
+        const int f = flag[i];
+        out[i] = base;
+        base += f;
+    }
+    __syncthreads();
+    return total;
+}
+
+// One side of a peak's valley (copied-from-stitch.cpp:522-567): step c looks at position peak + dir * c; the walk ends at
+// the first step that is near an end of the region, whose outer neighbour is no longer available, that has climbed to more
+// than three times the smallest rate seen, or that is below the threshold but rising over five steps; the result is the
+// position of the smallest rate seen up to and including that step (first occurrence).  Warp-cooperative: lane l evaluates
+// step c0 + l + 1; all lanes return the same value.
+__device__ inline int bd_valley(const double* rate, const uint8_t* avail, int peak, double thresh, int T, int dir, int lane) {
+    double carry_min = rate[peak];
+    int carry_arg = peak;
+    const double at_peak = carry_min;
+    for (int c0 = 0;; c0 += 32) {
+        const int c = c0 + lane + 1;
+        const int pos = peak + dir * c;
+        const bool valid = pos >= 0 && pos <= T - 2;
+        const double v = valid ? rate[pos] : __longlong_as_double(0x7ff0000000000000ll);
+        // smallest rate over steps c0 + 1 .. c (strict comparisons: the earliest position wins ties), then the carry
+        double m = v;
+        int arg = pos;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const double om = __shfl_up_sync(0xffffffffu, m, d);
+            const int oa = __shfl_up_sync(0xffffffffu, arg, d);
+            if (lane >= d && !(m < om)) {
+                m = om;
+                arg = oa;
             }
-            while (i < mid) dst[o++] = src[i++];
-            while (j < hi) dst[o++] = src[j++];
         }
-        int32_t* t = src;
-        src = dst;
-        dst = t;
+        if (!(m < carry_min)) {
+            m = carry_min;
+            arg = carry_arg;
+        }
+        const double five_back = (c >= 5 && valid) ? rate[pos - 5 * dir] : at_peak;
+        bool stop = !valid || pos <= 2 || pos >= T - 3;
+        if (!stop) stop = avail[pos + dir] == 0 || (3 * m) < v || (v < thresh && five_back < v);
+        const unsigned st = __ballot_sync(0xffffffffu, stop);
+        if (st) return __shfl_sync(0xffffffffu, arg, __ffs(st) - 1);
+        carry_min = __shfl_sync(0xffffffffu, m, 31);
+        carry_arg = __shfl_sync(0xffffffffu, arg, 31);
     }
-    if (src != idx)
-        for (int i = 0; i < n; i++) idx[i] = src[i];
 }
 
-// copied-from-stitch.cpp:522-567
-__device__ inline int determine_where_to_stop(const double* smoothed_rate, const uint8_t* available, int snp_best, double thresh, int nGrids,
-                                              bool is_left) {
-    const int mult = is_left ? 1 : -1;
-    int snp_consider = snp_best;
-    double val_cur = smoothed_rate[snp_consider];
-    double val_prev = smoothed_rate[snp_best];
-    int snp_min = snp_consider;
-    double val_min = smoothed_rate[snp_min];
-    int c = 1;
-    bool are_done = false;
-    while (!are_done) {
-        snp_consider = snp_consider + (-1) * mult;
-        val_cur = smoothed_rate[snp_consider];
-        if (5 <= c) val_prev = smoothed_rate[snp_consider + 5 * mult];
-        c += 1;
-        if (val_cur < val_min) {
-            snp_min = snp_consider;
-            val_min = val_cur;
-        }
-        if ((snp_consider <= 2) | ((nGrids - 3) <= snp_consider)) {
-            are_done = true;
-        } else if (available[snp_consider + (-1) * mult] == 0) {
-            are_done = true;
-        } else if ((3 * val_min) < val_cur) {
-            are_done = true;
-        } else if ((val_cur < thresh) & (val_prev < val_cur)) {
-            are_done = true;
-        }
-    }
-    return snp_min;
-}
+__device__ inline double bd_half_up(double x) { return (double(int(x)) < x) ? x + 0.5 : x; }  // gibbs-nipt-block.cpp:1296-1303
 
-__device__ inline double ceiling_point5(double x) {
-    if (double(int(x)) < x) return x + 0.5;
-    return x;
-}
-
-// Block definition + "considers": small, strictly serial integer / scalar logic — one thread per job walks it exactly
-// in the reference's order.  grid = jobs, 32 threads (lane 0 works).
-__global__ void __launch_bounds__(32) k_block_define(BatchParams P, const JobDev* __restrict__ jobs) {
-    if (threadIdx.x != 0) return;
+// grid = jobs, BD_NT threads; dynamic shared memory: rate [T] f64, peak list [T] i32, availability [T] u8 when they fit
+// (use_smem), else the same arrays in the job's global scratch.
+__global__ void __launch_bounds__(BD_NT) k_block_define(BatchParams P, const JobDev* __restrict__ jobs, int use_smem) {
+    extern __shared__ __align__(16) unsigned char bd_dyn[];
+    __shared__ int s_part[BD_NT / 32];
+    __shared__ int s_count;
+    __shared__ double s_thresh;
     const JobDev& J = jobs[blockIdx.x];
     if (*J.underflow) return;
-    const int nGrids = P.T, nReads = J.R;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int T = P.T, R = J.R, n1 = T - 1;
     BlockScratch B;
-    B.carve(J.blk, nGrids);
-    const int32_t* L_grid = J.L_grid;
-    const int shuffle_bin_radius = P.shuffle_bin_radius;
-    double* smoothed_rate = B.smoothed;
-    const double* sigma_rate = B.rate2;
-    const int n1 = nGrids - 1;
-    // ---- make_smoothed_rate (copied-from-stitch.cpp:446-518)
-    for (int iGrid = 0; iGrid < n1; iGrid++) {
-        const int focal_point = (L_grid[iGrid] + L_grid[iGrid + 1]) / 2;
-        int iGrid_left = iGrid;
-        int bp_remaining = shuffle_bin_radius;
-        int bp_prev = focal_point;
-        double total_bp_added = 0;
-        double acc = 0;
-        int bp_to_add;
-        while ((0 < bp_remaining) & (0 <= iGrid_left)) {
-            bp_to_add = (bp_prev - L_grid[iGrid_left]);
-            if ((bp_remaining - bp_to_add) < 0) {
-                bp_to_add = bp_remaining;
-                bp_remaining = 0;
-            } else {
-                bp_remaining = bp_remaining - bp_to_add;
-            }
-            acc = acc + bp_to_add * sigma_rate[iGrid_left];
-            total_bp_added += bp_to_add;
-            bp_prev = L_grid[iGrid_left];
-            iGrid_left = iGrid_left - 1;
-        }
-        int iGrid_right = iGrid + 1;
-        bp_remaining = shuffle_bin_radius;
-        bp_prev = focal_point;
-        while ((0 < bp_remaining) & (iGrid_right < nGrids)) {
-            bp_to_add = (L_grid[iGrid_right] - bp_prev);
-            if ((bp_remaining - bp_to_add) < 0) {
-                bp_to_add = bp_remaining;
-                bp_remaining = 0;
-            } else {
-                bp_remaining = bp_remaining - bp_to_add;
-            }
-            acc = acc + bp_to_add * sigma_rate[iGrid_right - 1];
-            total_bp_added += bp_to_add;
-            bp_prev = L_grid[iGrid_right];
-            iGrid_right = iGrid_right + 1;
-        }
-        smoothed_rate[iGrid] = acc / total_bp_added;
+    B.carve(J.blk, T);
+    double* rate = use_smem ? reinterpret_cast<double*>(bd_dyn) : B.smoothed;
+    int32_t* peaks = use_smem ? reinterpret_cast<int32_t*>(bd_dyn + (size_t)T * 8) : B.idx_a;
+    uint8_t* avail = use_smem ? bd_dyn + (size_t)T * 12 : B.available;
+    int32_t* keep = B.to_keep;  // flag per grid: a block boundary
+    const int32_t* __restrict__ Lg = J.L_grid;
+    const double* __restrict__ raw = B.rate2;
+    if (tid == 0) {
+        s_count = 0;
+        s_thresh = 1.0;
     }
-    // ---- threshold = min(1, quantile) (gibbs-nipt-block.cpp:81-85, :386-392)
-    double break_thresh = 1;
+    // ---- 1. rate averaged over +- shuffle_bin_radius bp around the midpoint of grids i and i + 1: every inter-grid interval
+    //         weighs in with the base pairs of it that fall inside the window
+    for (int i = tid; i < n1; i += BD_NT) {
+        const int mid = (Lg[i] + Lg[i + 1]) / 2;
+        double acc = 0, bp = 0;
+        int budget = P.shuffle_bin_radius, edge = mid;
+        for (int j = i; j >= 0 && budget > 0; j--) {
+            const int span = min(edge - Lg[j], budget);
+            budget -= span;
+            acc = acc + span * raw[j];
+            bp += span;
+            edge = Lg[j];
+        }
+        budget = P.shuffle_bin_radius;
+        edge = mid;
+        for (int j = i + 1; j < T && budget > 0; j++) {
+            const int span = min(Lg[j] - edge, budget);
+            budget -= span;
+            acc = acc + span * raw[j - 1];
+            bp += span;
+            edge = Lg[j];
+        }
+        rate[i] = acc / bp;
+    }
+    for (int g = tid; g < T; g += BD_NT) {
+        keep[g] = 0;
+        peaks[g] = 0;
+    }
+    __syncthreads();
+    // ---- 2. stable ranks by counting: ascending rank v = int(n1 * q) is the quantile (gibbs-nipt-block.cpp:81-85),
+    //         the descending order is the peak list (ties: lower index first in both, as a stable sort leaves them)
+    const int qpos = int(n1 * P.block_q);
+    for (int i = tid; i < n1; i += BD_NT) {
+        const double x = rate[i];
+        int less = 0, greater = 0, tie_before = 0;
+        for (int j = 0; j < n1; j++) {
+            const double y = rate[j];
+            less += (y < x) ? 1 : 0;
+            greater += (y > x) ? 1 : 0;
+            tie_before += (y == x && j < i) ? 1 : 0;
+        }
+        if (less + tie_before == qpos) s_thresh = fmin(1.0, x);
+        peaks[min(greater + tie_before, n1 - 1)] = i;
+    }
+    __syncthreads();
+    const double thresh = s_thresh;
     {
-        stable_sort_idx(smoothed_rate, n1, B.idx_a, B.idx_b, false);
-        const int v = int(n1 * P.block_q);
-        const double d = smoothed_rate[B.idx_a[v]];
-        if (d < break_thresh) break_thresh = d;
+        int mine = 0;
+        for (int i = tid; i < n1; i += BD_NT) {
+            const uint8_t a = (thresh < rate[i]) ? 1 : 0;
+            avail[i] = a;
+            mine += a;
+        }
+        if (tid == 0) avail[n1] = 0;
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, d);
+        if (lane == 0 && mine) atomicAdd(&s_count, mine);
     }
-    uint8_t* available = B.available;
-    int nAvailable = 0;
-    for (int i = 0; i < n1; i++) {
-        uint8_t av = 0;
-        if (smoothed_rate[i] < 0.01) av = 0;
-        if (break_thresh < smoothed_rate[i]) av = 1;
-        available[i] = av;
-        nAvailable += av;
-    }
-    int32_t* blocked_grid = B.blocked_grid;
-    for (int i = 0; i < nGrids; i++) blocked_grid[i] = 0;
-    int n_keep = 0;
-    if (nAvailable > 0) {
-        stable_sort_idx(smoothed_rate, n1, B.idx_a, B.idx_b, true);
-        const int32_t* best2 = B.idx_a;
-        int32_t* to_keep = B.to_keep;
-        int kmin = 0x7fffffff, kmax = -1;
-        for (int iBest = 0; iBest < nAvailable; iBest++) {
-            const int snp_best = best2[iBest];
-            if (available[snp_best]) {
-                const int a = max(snp_best - 1, 0);
-                const int b = min(snp_best + 1, nGrids - 1 - 1);
-                int dd = 0;
-                for (int j = a; j <= b; j++)
-                    if (available[j]) dd += 1;
-                if (dd == 3) {
-                    const int snp_left = determine_where_to_stop(smoothed_rate, available, snp_best, break_thresh, nGrids, true);
-                    const int snp_right = determine_where_to_stop(smoothed_rate, available, snp_best, break_thresh, nGrids, false);
-                    for (int j = snp_left; j <= snp_right; j++) available[j] = 0;
-                } else {
-                    for (int j = a; j <= b; j++) available[j] = 0;
-                }
-                to_keep[n_keep++] = snp_best + 1;
-                kmin = min(kmin, snp_best + 1);
-                kmax = max(kmax, snp_best + 1);
+    __syncthreads();
+    const int n_avail = s_count;
+    // ---- 3. peaks in order of decreasing rate; a peak with both neighbours still available claims its valley
+    if (warp == 0 && n_avail > 0) {
+        int at = 0;
+        while (at < n_avail) {
+            const int q = at + lane;
+            const int cand = (q < n_avail) ? min(max(peaks[q], 0), n1 - 1) : -1;
+            const unsigned live = __ballot_sync(0xffffffffu, cand >= 0 && avail[cand] != 0);
+            if (!live) {
+                at += 32;
+                continue;
             }
-        }
-        if (kmin != 0) to_keep[n_keep++] = 0;
-        if (kmax != (nGrids - 1)) to_keep[n_keep++] = nGrids - 1;
-        // sort ascending (insertion sort: the list is short)
-        for (int i = 1; i < n_keep; i++) {
-            const int v = to_keep[i];
-            int j = i - 1;
-            while (j >= 0 && to_keep[j] > v) {
-                to_keep[j + 1] = to_keep[j];
-                j--;
+            const int first = __ffs(live) - 1;
+            const int peak = __shfl_sync(0xffffffffu, cand, first);
+            at += first + 1;
+            int lo = max(peak - 1, 0), hi = min(peak + 1, n1 - 1);
+            if (hi - lo == 2 && avail[lo] && avail[hi]) {  // (the peak itself is available)
+                lo = bd_valley(rate, avail, peak, thresh, T, -1, lane);
+                hi = bd_valley(rate, avail, peak, thresh, T, +1, lane);
             }
-            to_keep[j + 1] = v;
+            __syncwarp();
+            for (int j = lo + lane; j <= hi; j += 32) avail[j] = 0;
+            if (lane == 0) keep[peak + 1] = 1;
+            __syncwarp();
         }
-        for (int i = 0; i < (n_keep - 1); i++) {
-            const int a = to_keep[i], b = to_keep[i + 1];
-            for (int j = a; j <= b; j++) blocked_grid[j] = i;
+        if (lane == 0) {
+            keep[0] = 1;
+            keep[T - 1] = 1;
         }
     }
-    // ---- Rcpp_make_gibbs_considers on blocked_snps[iSNP] = blocked_grid[iSNP / 32] (grid32): a block's SNPs are
-    //      the SNPs of its grids, so grid_start / grid_end follow directly; the SNP-level outputs are not consumed
-    int n_blocks = blocked_grid[nGrids - 1] + 1;
-    int32_t* grid_start = B.grid_start;
-    int32_t* grid_end = B.grid_end;
+    __syncthreads();
+    // ---- 4. block id of a grid = boundaries at or before it - 1 (the last grid stays in the last block)
+    int32_t* bgrid = B.blocked_grid;
+    if (n_avail > 0) {
+        const int n_keep = bd_scan_excl(keep, bgrid, T, s_part);
+        for (int g = tid; g < T; g += BD_NT) bgrid[g] = min(bgrid[g] + keep[g] - 1, n_keep - 2);
+    } else {
+        for (int g = tid; g < T; g += BD_NT) bgrid[g] = 0;
+    }
+    __syncthreads();
+    int n_blocks = bgrid[T - 1] + 1;
+    // grid ranges: a block ends where the id rises (or at the last grid)
+    int32_t* gs = B.grid_start;
+    int32_t* ge = B.grid_end;
+    int32_t* rs = B.reads_start;
+    int32_t* re = B.reads_end;
+    int32_t* flag = B.rmflag;
+    int32_t* seg = B.idx_b;  // first read of the run of reads that currently maps to a block
+    for (int g = tid; g < T; g += BD_NT) flag[g] = (g == T - 1 || bgrid[g] < bgrid[g + 1]) ? 1 : 0;
+    __syncthreads();
+    bd_scan_excl(flag, B.grid_where, T, s_part);  // (grid_where is scratch here; it is filled at the end)
+    for (int g = tid; g < T; g += BD_NT) {
+        if (flag[g]) {
+            const int b = B.grid_where[g];
+            ge[b] = g;
+            if (g + 1 < T) gs[b + 1] = g + 1;
+        }
+        if (g == 0) gs[0] = 0;
+    }
+    for (int b = tid; b < n_blocks; b += BD_NT) {
+        rs[b] = -1;
+        re[b] = -1;
+    }
+    __syncthreads();
+    // read ranges (gibbs-nipt-block.cpp:1400-1436): reads are ordered by grid, so the block id never falls.  A run of reads
+    // is recorded when a LATER read (before the last one) opens a new block; the last read records its own block with the
+    // start of the run that was open when it arrived.
+    auto block_of_read = [&](int r) { return bgrid[J.wif0[r]]; };
+    for (int r = tid; r < R - 1; r += BD_NT)
+        if (r == 0 || block_of_read(r) > block_of_read(r - 1)) seg[block_of_read(r)] = r;
+    __syncthreads();
+    for (int r = tid + 1; r < R; r += BD_NT) {
+        const int before = block_of_read(r - 1);
+        if (r == R - 1) {
+            const int b = block_of_read(r);
+            rs[b] = seg[before];
+            re[b] = r;
+        } else if (block_of_read(r) > before) {
+            rs[before] = seg[before];
+            re[before] = r - 1;
+        }
+    }
+    __syncthreads();
+    // ---- blocks without reads (gibbs-nipt-block.cpp:1440-1530): every maximal run [s, e] of them hands its grids to the
+    //      neighbours, split at the half-way point; runs touch disjoint entries, one thread per run
+    for (int b = tid; b < n_blocks; b += BD_NT) flag[b] = (rs[b] == -1) ? 1 : 0;
+    __syncthreads();
+    for (int b = tid; b < n_blocks; b += BD_NT) {
+        if (flag[b] && (b == 0 || !flag[b - 1])) {
+            int s = b, e = b;
+            while (e + 1 < n_blocks && flag[e + 1]) e++;
+            double x = bd_half_up(0.5 * double(gs[s] + ge[e]));
+            if (s == 0) {
+                s = 1;
+                x = 0;
+            }
+            if (e == n_blocks - 1) {
+                e = e - 1;
+                x = ge[n_blocks - 1];
+            }
+            gs[e + 1] = (int)x;
+            ge[s - 1] = (int)(x - 1);
+        }
+    }
+    __syncthreads();
     {
-        int iBlock = 0, start = 0;
-        for (int g = 0; g < nGrids; g++) {
-            const bool record = (g == nGrids - 1) || (blocked_grid[g] < blocked_grid[g + 1]);
-            if (record) {
-                grid_start[iBlock] = start;
-                grid_end[iBlock] = g;
-                start = g + 1;
-                iBlock++;
-            }
-        }
-        // the reference rebuilds blocked_grid from grid_start / grid_end (identical here)
-    }
-    int32_t* reads_start = B.reads_start;
-    int32_t* reads_end = B.reads_end;
-    for (int b = 0; b < n_blocks; b++) {
-        reads_start[b] = -1;
-        reads_end[b] = -1;
-    }
-    {
-        const int32_t* wif0 = J.wif0;
-        int previous_block_first_iRead = 0;
-        int previous_block = blocked_grid[wif0[0]];
-        for (int this_iRead = 1; this_iRead < nReads; this_iRead++) {
-            const int this_block = blocked_grid[wif0[this_iRead]];
-            if (this_iRead == (nReads - 1)) {
-                reads_start[this_block] = previous_block_first_iRead;
-                reads_end[this_block] = this_iRead;
-            } else if (previous_block < this_block) {
-                reads_start[previous_block] = previous_block_first_iRead;
-                reads_end[previous_block] = this_iRead - 1;
-                previous_block_first_iRead = this_iRead;
-                previous_block = this_block;
-            }
-        }
-    }
-    // ---- removal of blocks without reads (gibbs-nipt-block.cpp:1440-1530)
-    {
-        int32_t* remove = B.rmflag;
-        int n_to_remove = 0;
-        for (int b = 0; b < n_blocks; b++) {
-            remove[b] = (reads_start[b] == -1) ? 1 : 0;
-            n_to_remove += remove[b];
-        }
-        if (n_to_remove > 0) {
-            int32_t* w = B.idx_b;  // indices of the removed blocks
-            int a = 0;
-            for (int b = 0; b < n_blocks; b++)
-                if (remove[b]) w[a++] = b;
-            int jBefore = 0;
-            bool todo = false;
-            for (int jNow = 0; jNow < n_to_remove; jNow++) {
-                if (jNow == (n_to_remove - 1)) {
-                    todo = true;
-                } else {
-                    if ((w[jNow + 1] - w[jNow]) == 1) {
-                        todo = false;
-                        jBefore -= 1;
-                    } else {
-                        todo = true;
-                    }
-                }
-                if (todo) {
-                    int s1 = w[jBefore];
-                    int e1 = w[jNow];
-                    double x = ceiling_point5(0.5 * double(grid_start[s1] + grid_end[e1]));
-                    if (s1 == 0) {
-                        s1 = 1;
-                        x = 0;
-                    }
-                    if (e1 == (n_blocks - 1)) {
-                        e1 = e1 - 1;
-                        x = grid_end[n_blocks - 1];
-                    }
-                    grid_start[e1 + 1] = (int)x;  // double -> int truncation, as the IntegerVector assignment
-                    grid_end[s1 - 1] = (int)(x - 1);
-                    jBefore = jNow;
-                }
-                jBefore += 1;
-            }
-            int o = 0;
-            for (int b = 0; b < n_blocks; b++) {
-                if (!remove[b]) {
-                    reads_start[o] = reads_start[b];
-                    reads_end[o] = reads_end[b];
-                    grid_start[o] = grid_start[b];
-                    grid_end[o] = grid_end[b];
-                    o++;
+        // compaction: surviving blocks move up (through scratch, then back)
+        int32_t* t0 = reinterpret_cast<int32_t*>(B.smoothed);  // [2 T] ints: the smoothed rate is no longer needed
+        int32_t* t1 = t0 + T;
+        int32_t* t2 = B.idx_a;
+        int32_t* t3 = B.to_keep;
+        int32_t* posn = B.grid_where;
+        for (int b = tid; b < n_blocks; b += BD_NT) flag[b] = 1 - flag[b];
+        __syncthreads();
+        const int n_left = bd_scan_excl(flag, posn, n_blocks, s_part);
+        if (n_left != n_blocks) {
+            for (int b = tid; b < n_blocks; b += BD_NT) {
+                if (flag[b]) {
+                    const int o = posn[b];
+                    t0[o] = rs[b];
+                    t1[o] = re[b];
+                    t2[o] = gs[b];
+                    t3[o] = ge[b];
                 }
             }
-            n_blocks = o;
+            __syncthreads();
+            for (int b = tid; b < n_left; b += BD_NT) {
+                rs[b] = t0[b];
+                re[b] = t1[b];
+                gs[b] = t2[b];
+                ge[b] = t3[b];
+            }
+            n_blocks = n_left;
         }
+        __syncthreads();
     }
-    int32_t* grid_where = B.grid_where;
-    for (int g = 0; g < nGrids; g++) grid_where[g] = -1;
-    for (int b = 0; b < n_blocks; b++) grid_where[grid_end[b]] = b;
-    B.n_blocks[0] = n_blocks;
+    for (int g = tid; g < T; g += BD_NT) B.grid_where[g] = -1;
+    __syncthreads();
+    for (int b = tid; b < n_blocks; b += BD_NT) B.grid_where[ge[b]] = b;
+    if (tid == 0) B.n_blocks[0] = n_blocks;
 }
 
 // emission value of read r (descriptor d, staged nowhere: global tables) for haplotype k at grid g

@@ -1231,7 +1231,13 @@ int run_wave_t(QuiltGpuBatch* B, Bucket& bk, int n, const JobDev* dj, bool timed
                     if (P.T > 2) {
                         k_block_rate<<<dim3(P.T, n), 256, 0, g_stream>>>(P, dj);
                         LAUNCHED();
-                        k_block_define<<<n, 32, 0, g_stream>>>(P, dj);
+                        {
+                            // rate / peak list / availability of the block definition live in shared memory when they fit
+                            const size_t bds = (size_t)P.T * 13 + 16;
+                            const int in_smem = bds <= (size_t)160 * 1024;
+                            if (in_smem && bds > 48 * 1024) CK(cudaFuncSetAttribute(k_block_define, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bds));
+                            k_block_define<<<n, BD_NT, in_smem ? bds : 0, g_stream>>>(P, dj, in_smem);
+                        }
                         LAUNCHED();
                         k_block_nipt<NT, EPT><<<n, NT, 0, g_stream>>>(P, dj, episode);
                         LAUNCHED();
