@@ -49,6 +49,9 @@ WORKLOADS = {
     "chr20_2Mb_1x_K512": dict(K=512, K_full=5008, nSNPs=32000, factor=3, region_bp=3_000_000, coverage=1.0, samples=64),
     # BASELINE.json config #4 (per-GPU share): NIPT, three haplotypes, fetal fraction 10 %, 0.5x, K = 2048; common-SNP calls only
     "nipt_2Mb_0.5x_K2048": dict(K=2048, K_full=5008, nSNPs=32000, factor=0, region_bp=3_000_000, coverage=0.5, samples=48, ff=0.1),
+    # BASELINE.json config #5 (per-GPU share, scaled): K = 8192 (two-CTA cluster kernels) drawn from a 20 000-haplotype synthetic panel
+    # (a 200 000-haplotype panel needs 6.4 GB of NumPy bits per rank just to be synthesised); common-SNP calls only
+    "chr20_2Mb_1x_K8192_20k": dict(K=8192, K_full=20000, nSNPs=32000, factor=0, region_bp=3_000_000, coverage=1.0, samples=37),
     "tiny": dict(K=256, K_full=600, nSNPs=3200, factor=3, region_bp=300_000, coverage=1.0, samples=4),
 }
 METRIC = "diploid samples/sec, chr20 2Mb @1x cov, K=4096, 5008-hap panel; 1/2/4/8 GPU"
@@ -64,11 +67,12 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic():
-    """dram bytes per sweep launch from the committed ncu capture (profiles/), or None"""
+def ncu_traffic(workload):
+    """dram bytes per sweep launch of THIS workload from the committed ncu captures (profiles/sweep_traffic.json), or None when no
+    capture of the workload exists (a number taken on another shape would be meaningless)"""
     try:
         with open(os.path.join(ROOT, "profiles", "sweep_traffic.json")) as fh:
-            return json.load(fh)
+            return json.load(fh)["workloads"].get(workload)
     except Exception:
         return None
 
@@ -469,7 +473,7 @@ def main():
     launches_per_run = sweep_launches / args.steps
     avg_launch_s = (sweep_ms / 1e3) / max(sweep_launches, 1)
     achieved = (alg_bytes_per_run / max(launches_per_run, 1)) / avg_launch_s / 1e9
-    tr = ncu_traffic()
+    tr = ncu_traffic(args.workload)
     roofline = {
         "bound": "hbm", "kernel": "k_sweep", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
         "traffic": (tr or {}).get("dram_bytes_per_launch"),

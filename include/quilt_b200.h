@@ -378,6 +378,13 @@ int         quilt_gpu_device_count(void);
 int         quilt_gpu_set_device(int32_t device);
 const char* quilt_gpu_last_error(void);
 int64_t     quilt_gpu_kernel_launches(void);   /* cumulative count of this library's kernel launches */
+/* Per-section timing: the reference's print_extra_timing_information / suppressOutput = 0 switch (QUILT/src/copied-from-stitch.cpp:31-45
+ * prints the time spent between code sections).  enable != 0: from now on every kernel launch of the library is followed by a CUDA
+ * event; quilt_gpu_section_report writes a table "section, launches, total ms, avg ms, share" (device time between consecutive
+ * events on the library stream, per kernel) into buf (NUL-terminated, truncated to cap) and returns the size the full text needs.
+ * enable == 0 switches it off and drops the events.  Off by default (no events are created). */
+int         quilt_gpu_section_timing(int32_t enable);
+int64_t     quilt_gpu_section_report(char* buf, int64_t cap);
 void        quilt_gpu_release_panel_cache(void);
 
 #ifdef __cplusplus

@@ -61,6 +61,10 @@ class GpuLib(cabi._LibAPI):
         L.quilt_gpu_last_error.restype = C.c_char_p
         L.quilt_gpu_kernel_launches.restype = C.c_int64
         L.quilt_gpu_release_panel_cache.restype = None
+        L.quilt_gpu_section_timing.argtypes = [C.c_int32]
+        L.quilt_gpu_section_timing.restype = C.c_int
+        L.quilt_gpu_section_report.argtypes = [C.c_char_p, C.c_int64]
+        L.quilt_gpu_section_report.restype = C.c_int64
         L.quilt_gpu_batch_chain_select.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_double)]
         L.quilt_gpu_batch_chain_select.restype = C.c_int
         L.quilt_gpu_gibbs_batch_chained.argtypes = [C.c_int32, pa, po, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_double),
@@ -88,6 +92,16 @@ class GpuLib(cabi._LibAPI):
 
     def release_panel_cache(self):
         self.lib.quilt_gpu_release_panel_cache()
+
+    def section_timing(self, enable: bool = True):
+        """the reference's print_extra_timing_information switch (copied-from-stitch.cpp:31-45): per-kernel device time"""
+        self._check(self.lib.quilt_gpu_section_timing(int(bool(enable))), "quilt_gpu_section_timing")
+
+    def section_report(self) -> str:
+        n = int(self.lib.quilt_gpu_section_report(None, 0))
+        buf = C.create_string_buffer(max(n, 1))
+        self.lib.quilt_gpu_section_report(buf, n)
+        return buf.value.decode()
 
     def _check(self, rc: int, what: str):
         if rc != cabi.OK:

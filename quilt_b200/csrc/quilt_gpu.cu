@@ -60,6 +60,34 @@ int set_err(int code, const std::string& msg) {
     } while (0)
 #define LAUNCHED() (g_launches.fetch_add(1, std::memory_order_relaxed))
 
+// Per-section timing — the reference's print_extra_timing_information / suppressOutput = 0 switch (copied-from-stitch.cpp:31-45
+// prints the wall time between code sections): when enabled, every tagged launch site records a CUDA event behind its kernel.  The
+// library stream is in-order, so the time between two consecutive events is the duration of the kernel launched in between (plus
+// its launch gap; copies queued between two waves are charged to the first kernel after them).  Off by default: no events, no cost.
+struct SectionTimer {
+    bool on = false;
+    cudaEvent_t begin = nullptr;
+    std::vector<std::pair<const char*, cudaEvent_t>> marks;
+    std::mutex mu;
+    void reset() {
+        for (auto& m : marks) cudaEventDestroy(m.second);
+        marks.clear();
+        if (begin) cudaEventDestroy(begin);
+        begin = nullptr;
+    }
+};
+SectionTimer g_sect;
+inline void launched_k(const char* name) {
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    if (!g_sect.on) return;
+    std::lock_guard<std::mutex> lk(g_sect.mu);
+    cudaEvent_t e = nullptr;
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    cudaEventRecord(e, g_stream);
+    g_sect.marks.emplace_back(name, e);
+}
+#define LAUNCHED_K(name) launched_k(name)
+
 int ensure_device() {
     if (g_stream) return QUILT_OK;
     int n = 0;
@@ -1120,33 +1148,33 @@ int run_prep(QuiltGpuBatch* B, Bucket& bk, int n, const JobDev* dj) {
     const int kb = (P.Kp + 255) / 256;
     if (P.rare_common) {
         k_unpack_common<<<dim3(kb, B->panel.Tc, n), 256, 0, g_stream>>>(B->panel, dj, P.K, P.Kp, 1);
-        LAUNCHED();
+        LAUNCHED_K("k_unpack_common");
         k_assemble_all<<<dim3(kb, (P.T + ASM_GPB - 1) / ASM_GPB, n), 256, 0, g_stream>>>(B->panel, dj, P.K, P.Kp, P.T);
-        LAUNCHED();
+        LAUNCHED_K("k_assemble_all");
         k_scatter_rare<<<dim3((P.K + 255) / 256, n), 256, 0, g_stream>>>(B->panel, dj, P.K, P.Kp);
-        LAUNCHED();
+        LAUNCHED_K("k_scatter_rare");
         k_snp_type<<<dim3(P.T, n), 128, 0, g_stream>>>(B->panel, dj, P.K, P.Kp);
-        LAUNCHED();
+        LAUNCHED_K("k_snp_type");
     } else {
         k_unpack_common<<<dim3(kb, P.T, n), 256, 0, g_stream>>>(B->panel, dj, P.K, P.Kp, 0);
-        LAUNCHED();
+        LAUNCHED_K("k_unpack_common");
     }
     if (bk.classes) {
         const int KA = bk.geo.NT * bk.geo.EPT;
         const size_t csm = class_dyn_smem(P.Kp, KA);
         CK(cudaFuncSetAttribute(k_build_classes, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csm));
         k_build_classes<<<dim3(P.T, n), CLS_NT, csm, g_stream>>>(P, dj, bk.geo.NT, bk.geo.EPT);
-        LAUNCHED();
+        LAUNCHED_K("k_build_classes");
     }
     {
         const int tsm = 3 * P.Kp * 4;
         CK(cudaFuncSetAttribute(k_build_tables, cudaFuncAttributeMaxDynamicSharedMemorySize, tsm));
         k_build_tables<<<dim3(P.T, n), TAB_WARPS * 32, tsm, g_stream>>>(P, dj);
-        LAUNCHED();
+        LAUNCHED_K("k_build_tables");
     }
     if (bk.n_dense_max > 0) {
         k_build_dense<<<dim3(bk.n_dense_max, n), 256, 0, g_stream>>>(P, dj);
-        LAUNCHED();
+        LAUNCHED_K("k_build_dense");
     }
     CK(cudaGetLastError());
     return QUILT_OK;
@@ -1174,20 +1202,20 @@ int run_wave_t(QuiltGpuBatch* B, Bucket& bk, int n, const JobDev* dj, bool timed
         return set_err(QUILT_ERR_UNSUPPORTED, "no three-haplotype sweep kernel for this K");
     }
     k_copy_H<<<dim3((bk.R_max + 255) / 256, n), 256, 0, g_stream>>>(dj);
-    LAUNCHED();
+    LAUNCHED_K("k_copy_H");
     int rc = run_prep(B, bk, n, dj);
     if (rc != QUILT_OK) return rc;
     if (P.flags & QUILT_F_GIBBS_INITIALIZE_ITERATIVELY) {
         k_init_iterative<<<dim3(P.T, n), 256, 0, g_stream>>>(P, dj);
-        LAUNCHED();
+        LAUNCHED_K("k_init_iterative");
     } else {
         k_make_eG<<<dim3(P.T, n), 256, 0, g_stream>>>(P, dj);
-        LAUNCHED();
+        LAUNCHED_K("k_make_eG");
         if (CL == 2)
             k_fb_generic<512, 16><<<dim3(n, P.NH), 512, 0, g_stream>>>(P, dj, 1);  // one CTA holds all K <= 8192 states here
         else
             k_fb_generic<NT, EPT><<<dim3(n, P.NH), NT, 0, g_stream>>>(P, dj, 1);
-        LAUNCHED();
+        LAUNCHED_K("k_fb_generic");
     }
     int episode = 0;
     for (int it = 0; it < P.n_its; it++) {
@@ -1211,7 +1239,7 @@ int run_wave_t(QuiltGpuBatch* B, Bucket& bk, int n, const JobDev* dj, bool timed
         } else if constexpr (nipt_geo<NT, EPT>()) {
             k_sweep<NT, EPT, 3><<<n, NT, L.total, g_stream>>>(P, dj, it, store_alpha);
         }
-        LAUNCHED();
+        LAUNCHED_K("k_sweep");
         if (timed) {
             CK(cudaEventRecord(e1, g_stream));
             B->sweep_events.emplace_back(e0, e1);
@@ -1230,7 +1258,7 @@ int run_wave_t(QuiltGpuBatch* B, Bucket& bk, int n, const JobDev* dj, bool timed
                 if constexpr (nipt_geo<NT, EPT>()) {
                     if (P.T > 2) {
                         k_block_rate<<<dim3(P.T, n), 256, 0, g_stream>>>(P, dj);
-                        LAUNCHED();
+                        LAUNCHED_K("k_block_rate");
                         {
                             // rate / peak list / availability of the block definition live in shared memory when they fit
                             const size_t bds = (size_t)P.T * 13 + 16;
@@ -1238,18 +1266,18 @@ int run_wave_t(QuiltGpuBatch* B, Bucket& bk, int n, const JobDev* dj, bool timed
                             if (in_smem && bds > 48 * 1024) CK(cudaFuncSetAttribute(k_block_define, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bds));
                             k_block_define<<<n, BD_NT, in_smem ? bds : 0, g_stream>>>(P, dj, in_smem);
                         }
-                        LAUNCHED();
+                        LAUNCHED_K("k_block_define");
                         k_block_nipt<NT, EPT><<<n, NT, 0, g_stream>>>(P, dj, episode);
-                        LAUNCHED();
+                        LAUNCHED_K("k_block_nipt");
                     }
                     k_sample_H<<<n, 256, 0, g_stream>>>(P, dj, episode);
-                    LAUNCHED();
+                    LAUNCHED_K("k_sample_H");
                     k_make_eG<<<dim3(P.T, n), 256, 0, g_stream>>>(P, dj);
-                    LAUNCHED();
+                    LAUNCHED_K("k_make_eG");
                     k_fb_generic<NT, EPT><<<dim3(n, P.NH), NT, 0, g_stream>>>(P, dj, 0);
-                    LAUNCHED();
+                    LAUNCHED_K("k_fb_generic");
                     k_bwd_fast<NT, EPT><<<dim3(n, P.NH), NT, 0, g_stream>>>(P, dj);
-                    LAUNCHED();
+                    LAUNCHED_K("k_bwd_fast");
                 }
             }
             if (bk.do_shard && P.T > 1) {
@@ -1263,7 +1291,7 @@ int run_wave_t(QuiltGpuBatch* B, Bucket& bk, int n, const JobDev* dj, bool timed
                     CK(cudaFuncSetAttribute(k_shard<NT, EPT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssm));
                     k_shard<NT, EPT, 1><<<n, NT, ssm, g_stream>>>(P, dj, episode);
                 }
-                LAUNCHED();
+                LAUNCHED_K("k_shard");
             }
             episode++;
         }
@@ -1271,17 +1299,17 @@ int run_wave_t(QuiltGpuBatch* B, Bucket& bk, int n, const JobDev* dj, bool timed
             const int n_sample = P.n_its - P.n_burn;
             if (n_sample > 1) {
                 k_snapshot_H<<<dim3((bk.R_max + 255) / 256, n), 256, 0, g_stream>>>(dj, it - P.n_burn);
-                LAUNCHED();
+                LAUNCHED_K("k_snapshot_H");
             }
             if (P.NH == 2)
                 k_happrobs<2><<<dim3(P.T, n), 256, 0, g_stream>>>(P, dj, it == P.n_burn, it == P.n_its - 1, 1.0 / double(n_sample));
             else
                 k_happrobs<3><<<dim3(P.T, n), 384, 0, g_stream>>>(P, dj, it == P.n_burn, it == P.n_its - 1, 1.0 / double(n_sample));
-            LAUNCHED();
+            LAUNCHED_K("k_happrobs");
         }
     }
     k_export_cat<<<dim3((bk.R_max + 255) / 256, n), 256, 0, g_stream>>>(dj);
-    LAUNCHED();
+    LAUNCHED_K("k_export_cat");
     CK(cudaGetLastError());
     return QUILT_OK;
 }
@@ -1315,7 +1343,7 @@ int fetch_debug(QuiltGpuBatch* B, Bucket& bk, int w0, int n) {
             CK(d.alloc((size_t)P.K * j.R * 8));
             const JobDev* dj = (const JobDev*)bk.djobs.p + w0 + i;
             k_expand_eMatRead<<<j.R, 256, 0, g_stream>>>(P, dj, (double*)d.p);
-            LAUNCHED();
+            LAUNCHED_K("k_expand_eMatRead");
             CK(cudaStreamSynchronize(g_stream));
             j.dbg_eMatRead.assign((size_t)P.K * j.R, 0.0);
             CK(cudaMemcpy(j.dbg_eMatRead.data(), d.p, (size_t)P.K * j.R * 8, cudaMemcpyDeviceToHost));
@@ -1342,11 +1370,11 @@ int run_wave(QuiltGpuBatch* B, Bucket& bk, int w0, int n, bool timed, bool prep_
     int rc;
     if (prep_only) {
         k_copy_H<<<dim3((bk.R_max + 255) / 256, n), 256, 0, g_stream>>>(dj);
-        LAUNCHED();
+        LAUNCHED_K("k_copy_H");
         rc = run_prep(B, bk, n, dj);
         if (rc == QUILT_OK) {
             k_export_cat<<<dim3((bk.R_max + 255) / 256, n), 256, 0, g_stream>>>(dj);
-            LAUNCHED();
+            LAUNCHED_K("k_export_cat");
         }
     } else {
         rc = with_geo(bk.geo, [&](auto nt, auto ept) { return run_wave_t<decltype(nt)::value, decltype(ept)::value>(B, bk, n, dj, timed); });
@@ -1443,6 +1471,58 @@ int quilt_gpu_set_device(int32_t device) {
 const char* quilt_gpu_last_error(void) { return g_err.c_str(); }
 
 int64_t quilt_gpu_kernel_launches(void) { return g_launches.load(); }
+
+int quilt_gpu_section_timing(int32_t enable) {
+    int rc = ensure_device();
+    if (rc != QUILT_OK) return rc;
+    CK(cudaStreamSynchronize(g_stream));
+    std::lock_guard<std::mutex> lk(g_sect.mu);
+    g_sect.reset();
+    g_sect.on = enable != 0;
+    if (g_sect.on) {
+        CK(cudaEventCreate(&g_sect.begin));
+        CK(cudaEventRecord(g_sect.begin, g_stream));
+    }
+    return QUILT_OK;
+}
+
+int64_t quilt_gpu_section_report(char* buf, int64_t cap) {
+    if (!g_stream) return 0;
+    cudaStreamSynchronize(g_stream);
+    std::lock_guard<std::mutex> lk(g_sect.mu);
+    std::vector<std::pair<std::string, std::pair<double, long>>> acc;  // first-appearance order
+    cudaEvent_t prev = g_sect.begin;
+    double total = 0;
+    for (auto& m : g_sect.marks) {
+        float ms = 0;
+        if (prev && cudaEventElapsedTime(&ms, prev, m.second) == cudaSuccess) {
+            auto it = std::find_if(acc.begin(), acc.end(), [&](const auto& a) { return a.first == m.first; });
+            if (it == acc.end()) {
+                acc.push_back({m.first, {0.0, 0}});
+                it = acc.end() - 1;
+            }
+            it->second.first += ms;
+            it->second.second += 1;
+            total += ms;
+        }
+        prev = m.second;
+    }
+    std::string out = "section                      launches     total ms       avg ms    share\n";
+    char line[160];
+    for (auto& a : acc) {
+        std::snprintf(line, sizeof line, "%-28s %8ld %12.3f %12.4f %7.1f%%\n", a.first.c_str(), a.second.second, a.second.first,
+                      a.second.first / std::max<long>(a.second.second, 1), total > 0 ? 100.0 * a.second.first / total : 0.0);
+        out += line;
+    }
+    std::snprintf(line, sizeof line, "%-28s %8zu %12.3f\n", "TOTAL", g_sect.marks.size(), total);
+    out += line;
+    if (buf && cap > 0) {
+        const size_t n = std::min<size_t>(out.size(), (size_t)cap - 1);
+        std::memcpy(buf, out.data(), n);
+        buf[n] = 0;
+    }
+    return (int64_t)out.size() + 1;
+}
 
 void quilt_gpu_release_panel_cache(void) {
     std::lock_guard<std::mutex> lk(g_mu);
@@ -2003,11 +2083,11 @@ void fill_sel_job(const SelPlan& pl, char* scratch, const double* hapProbs, int3
 int launch_select(const SelPlan& pl, const PanelDev& pd, const SelJob* djobs, int n) {
     const SelParams& P = pl.P;
     k_sel_symbols<<<dim3(P.Tc, P.nHap, n), SEL_NT, 0, g_stream>>>(P, djobs, pd.distinctHapsB, pd.n_used);
-    LAUNCHED();
+    LAUNCHED_K("k_sel_symbols");
     k_sel_match<<<dim3(P.nIndices, P.nHap, n), SEL_NT, 0, g_stream>>>(P, djobs, pd.hapMatcherR);
-    LAUNCHED();
+    LAUNCHED_K("k_sel_match");
     k_sel_rank<<<n, SEL_RANK_NT, 0, g_stream>>>(P, djobs);
-    LAUNCHED();
+    LAUNCHED_K("k_sel_rank");
     CK(cudaGetLastError());
     return QUILT_OK;
 }
@@ -2168,7 +2248,7 @@ int launch_hap_fb(int ept, const HapParams& P, const HapJob* dj, int n, const Pa
     else if (ept <= 16) QB_HAP(16)
     else QB_HAP(32)
 #undef QB_HAP
-    LAUNCHED();
+    LAUNCHED_K("k_hap_fb");
     return QUILT_OK;
 }
 }  // namespace
@@ -2295,7 +2375,7 @@ int quilt_gpu_haploid_dosage_versus_refs_batch(int32_t n, const QuiltHaploidArgs
         CK(cudaMemcpyAsync(jb.p, hj.data(), (size_t)m * sizeof(HapJob), cudaMemcpyHostToDevice, g_stream));
         CK(cudaEventRecord(e0, g_stream));
         k_hap_eMatDH<<<dim3(T, m), 256, 0, g_stream>>>(P, (const HapJob*)jb.p, pd.distinctHapsB);
-        LAUNCHED();
+        LAUNCHED_K("k_hap_eMatDH");
         rc = launch_hap_fb((K + HAP_NT - 1) / HAP_NT, P, (const HapJob*)jb.p, m, pd);
         if (rc != QUILT_OK) return rc;
         CK(cudaEventRecord(e1, g_stream));
@@ -2394,12 +2474,12 @@ int quilt_gpu_samples_summary(int32_t n_samples, int32_t nSNPs, const QuiltSampl
     CK(cudaMemcpyAsync(d_ptr, h_ptr.data(), n_ptr * 8, cudaMemcpyHostToDevice, g_stream));
     CK(cudaMemcpyAsync(d_s, h_s.data(), (size_t)n_samples * sizeof(SumSample), cudaMemcpyHostToDevice, g_stream));
     k_sample_summary<<<dim3((nSNPs + 255) / 256, n_samples), 256, 0, g_stream>>>(d_s, nSNPs);
-    LAUNCHED();
+    LAUNCHED_K("k_sample_summary");
     double* d_info = (double*)d_cnt;
     double* d_af = (double*)(d_cnt + al(ns * 16));
     double* d_hwe = (double*)(d_cnt + al(ns * 16) + al(ns * 8));
     k_info_counts<<<(nSNPs + 255) / 256, 256, 0, g_stream>>>(d_s, n_samples, nSNPs, d_info, d_af, d_hwe);
-    LAUNCHED();
+    LAUNCHED_K("k_info_counts");
     CK(cudaGetLastError());
     for (int q = 0; q < n_samples; q++) {
         const QuiltSampleSummary& s = S[q];
@@ -2476,23 +2556,23 @@ int quilt_gpu_ingest_pileup(const QuiltPileup* in, QuiltIngestOut* out) {
     D.u_s = (int32_t*)(d + o_us), D.bq_s = (int32_t*)(d + o_bqs), D.wif_s = (int32_t*)(d + o_wifs), D.alleleCount = (double*)(d + o_ac), D.grid_has_read = (uint8_t*)(d + o_ghr);
     const int nmax = std::max(std::max(R, nU), std::max(T, nS));
     k_ing_count<<<(nmax + 255) / 256, 256, 0, g_stream>>>(D);
-    LAUNCHED();
+    LAUNCHED_K("k_ing_count");
     k_exscan_i32<<<1, 1024, 0, g_stream>>>(D.cntG, T);
-    LAUNCHED();
+    LAUNCHED_K("k_exscan_i32");
     k_exscan_i32<<<1, 1024, 0, g_stream>>>(D.cntS, nS);
-    LAUNCHED();
+    LAUNCHED_K("k_exscan_i32");
     k_ing_place<<<(nmax + 255) / 256, 256, 0, g_stream>>>(D);
-    LAUNCHED();
+    LAUNCHED_K("k_ing_place");
     k_ing_sort<<<(nmax + 255) / 256, 256, 0, g_stream>>>(D);
-    LAUNCHED();
+    LAUNCHED_K("k_ing_sort");
     k_ing_lens<<<(R + 255) / 256, 256, 0, g_stream>>>(D);
-    LAUNCHED();
+    LAUNCHED_K("k_ing_lens");
     k_exscan_i32<<<1, 1024, 0, g_stream>>>(D.ncnt, R);
-    LAUNCHED();
+    LAUNCHED_K("k_exscan_i32");
     k_ing_copy<<<R, 256, 0, g_stream>>>(D);
-    LAUNCHED();
+    LAUNCHED_K("k_ing_copy");
     k_ing_allele<<<(nS + 255) / 256, 256, 0, g_stream>>>(D);
-    LAUNCHED();
+    LAUNCHED_K("k_ing_allele");
     CK(cudaGetLastError());
     if (out->order) CK(cudaMemcpyAsync(out->order, D.ordG, (size_t)R * 4, cudaMemcpyDeviceToHost, g_stream));
     if (out->offsets) CK(cudaMemcpyAsync(out->offsets, D.ncnt, (size_t)(R + 1) * 4, cudaMemcpyDeviceToHost, g_stream));
@@ -2521,7 +2601,7 @@ int quilt_gpu_make_vcf_column(int32_t nSNPs, const double* gp_t, const double* h
     CK(cudaMemcpyAsync(d_gp, gp_t, ns * 24, cudaMemcpyHostToDevice, g_stream));
     CK(cudaMemcpyAsync(d_hd, hd, ns * 16, cudaMemcpyHostToDevice, g_stream));
     k_vcf_column<<<(nSNPs + 255) / 256, 256, 0, g_stream>>>(nSNPs, d_gp, d_hd, d_out);
-    LAUNCHED();
+    LAUNCHED_K("k_vcf_column");
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(out, d_out, ns * VCF_REC, cudaMemcpyDeviceToHost, g_stream));
     CK(cudaStreamSynchronize(g_stream));
@@ -2585,14 +2665,14 @@ int quilt_gpu_unpack_panel(const QuiltPanel* panel, int32_t K, const int32_t* wh
     const int kb = (Kp + 255) / 256;
     if (all_snps) {
         k_unpack_common<<<dim3(kb, PD.Tc, 1), 256, 0, g_stream>>>(PD, d, K, Kp, 1);
-        LAUNCHED();
+        LAUNCHED_K("k_unpack_common");
         k_assemble_all<<<dim3(kb, (T + ASM_GPB - 1) / ASM_GPB, 1), 256, 0, g_stream>>>(PD, d, K, Kp, T);
-        LAUNCHED();
+        LAUNCHED_K("k_assemble_all");
         k_scatter_rare<<<dim3((K + 255) / 256, 1), 256, 0, g_stream>>>(PD, d, K, Kp);
-        LAUNCHED();
+        LAUNCHED_K("k_scatter_rare");
     } else {
         k_unpack_common<<<dim3(kb, T, 1), 256, 0, g_stream>>>(PD, d, K, Kp, 0);
-        LAUNCHED();
+        LAUNCHED_K("k_unpack_common");
     }
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(g_stream));
@@ -2641,12 +2721,12 @@ int quilt_gpu_forward_backward(int32_t K, int32_t T, const double* eMatGrid_t, c
     P.one_over_K = 1 / double(K);
     if (geo.CL == 2) {
         k_fb_generic<512, 16><<<dim3(1, 1), 512, 0, g_stream>>>(P, (const JobDev*)dj.p, 1);
-        LAUNCHED();
+        LAUNCHED_K("k_fb_generic");
         rc = QUILT_OK;
     } else {
         rc = with_geo(geo, [&](auto nt, auto ept) {
             k_fb_generic<decltype(nt)::value, decltype(ept)::value><<<dim3(1, 1), decltype(nt)::value, 0, g_stream>>>(P, (const JobDev*)dj.p, 1);
-            LAUNCHED();
+            LAUNCHED_K("k_fb_generic");
             return QUILT_OK;
         });
     }

@@ -661,6 +661,7 @@ __global__ void __launch_bounds__(NT, (NT * EPT <= 512 ? 4 : (NT * EPT <= 1024 ?
     auto issue_eG = [&](int g) {  // caller: every thread is done with buffer g & 1
         if (tid == 0) {
             const int s = g & 1;
+            bulk_wait_read_all();  // (a changed eMatGrid column may still be leaving this buffer by bulk store)
             fence_proxy_async();
             mbar_arrive_expect_tx(&bar[3 + s], NH * Kpl * 8);
 #pragma unroll
@@ -679,6 +680,7 @@ __global__ void __launch_bounds__(NT, (NT * EPT <= 512 ? 4 : (NT * EPT <= 1024 ?
     auto issue_beta = [&](int g) {  // into the buffer eMatGrid[:, g - 1] has left
         if (tid == 0) {
             const int s = (g & 1) ^ 1;
+            bulk_wait_read_all();  // (eMatGrid[:, g - 1], if it changed, leaves that buffer by bulk store)
             fence_proxy_async();
             mbar_arrive_expect_tx(&bar[5], NH * Kpl * 8);
 #pragma unroll
@@ -1455,7 +1457,8 @@ __global__ void __launch_bounds__(NT, (NT * EPT <= 512 ? 4 : (NT * EPT <= 1024 ?
                 double sv[NH];
 #pragma unroll
                 for (int h = 0; h < NH; h++) sv[h] = Col<NT, EPT>::sum(am[h]);
-                bsum.run(sv);
+                fence_proxy_async();  // this thread's updates of the eMatGrid column (generic proxy) before the bulk store below (async proxy)
+                bsum.run(sv);         // (its barrier: every thread's updates are done and fenced)
 #pragma unroll
                 for (int h = 0; h < NH; h++) {
                     const double alphaConst = 1 / sv[h];
@@ -1470,23 +1473,24 @@ __global__ void __launch_bounds__(NT, (NT * EPT <= 512 ? 4 : (NT * EPT <= 1024 ?
             // alphaHat_t in HBM is only read by the passes that may follow a sweep (gamma -> hapProbs after a sampling
             // sweep, the NIPT block episode, debug export); the next sweep rebuilds alpha from its registers
             if (store_alpha) Col<NT, EPT>::store(am[h], alphaG + ((size_t)h * T + g) * Kp, K);
-            if (changed) {
-                // (loads first: a generic store may alias shared memory, so interleaving would serialise them)
-                double tmp[EPT];
-#pragma unroll
-                for (int i = 0; i < EPT; i++) tmp[i] = eg[h * KA + tid + i * NT];
-                Col<NT, EPT>::store(tmp, eGg + ((size_t)h * T + g) * Kp, K);
-            }
             if (tid == 0) cG[h * T + g] = cnew[h];
             cfin[h] = cnew[h];
+        }
+        if (changed && tid == 0) {
+            // the changed eMatGrid column already sits in the ring buffer: one bulk store per haplotype instead of EPT shared-memory
+            // loads + EPT global stores per thread (the padding k in [K, Kp) travels along; nothing reads it)
+#pragma unroll
+            for (int h = 0; h < NH; h++) bulk_s2g(eGg + ((size_t)h * T + g) * Kp, eg + (size_t)h * KA, Kpl * 8);
+            bulk_commit();
         }
         QB_T(8);
     }
     QB_T(11);
 
     // =============================================================== backward (Rcpp_run_backward_haploid_QUILT_faster)
-    // the eMatGrid columns changed above were written through the generic proxy; order them before the
-    // bulk (async proxy) reads below
+    // the eMatGrid columns changed above left by bulk stores issued by thread 0: their group completes before the block barrier
+    // behind which the bulk loads below start
+    if (tid == 0) bulk_wait_all();  // the bulk stores of the changed eMatGrid columns are complete
     __threadfence();
     fence_proxy_async_all();
     __syncthreads();

@@ -95,3 +95,21 @@ def test_long_region_many_grids(gpu, oracle):
     call = synth.make_call(w, sr.all, 49, K=256, all_snps=True, sort_haps=False, n_burn_in=5, n_sample=1, block_its=(2,))
     g, o = _run_both(gpu, oracle, call)
     _compare(f"long region all-SNP T={w.nGrids_all} R={sr.all.nReads}", g, o, state=False)
+
+
+def test_section_timing_switch(gpu, small_world, small_reads):
+    """the per-section timing switch (reference: print_extra_timing_information, copied-from-stitch.cpp:31-45): every kernel of a
+    Gibbs call shows up with its launch count and a positive device time; switched off, nothing is recorded"""
+    call = synth.make_call(small_world, small_reads.common, 11, K=200, n_burn_in=4, n_sample=1, block_its=(2,))
+    gpu.section_timing(True)
+    n0 = gpu.kernel_launches()
+    gpu.gibbs_batch([call])
+    n = gpu.kernel_launches() - n0
+    rep = gpu.section_report()
+    rows = {ln.split()[0]: ln.split() for ln in rep.splitlines()[1:] if ln.strip()}
+    assert int(rows["k_sweep"][1]) == 5 and float(rows["k_sweep"][2]) > 0
+    assert "k_shard" in rows and "k_happrobs" in rows and "k_build_tables" in rows
+    assert int(rows["TOTAL"][1]) == n
+    gpu.section_timing(False)
+    gpu.gibbs_batch([call])
+    assert gpu.section_report().splitlines()[-1].split()[1] == "0"
