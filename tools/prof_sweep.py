@@ -26,8 +26,14 @@ for j in range(a.jobs):
                                  n_burn_in=a.its - 1, n_sample=1, block_its=(3,), ff=a.ff))
 lib = api.GpuLib()
 b = api.Batch(lib, calls)
+sections = os.environ.get("QUILT_B200_SECTIONS") == "1"  # per-kernel device time of the second run (quilt_gpu_section_timing)
 for i in range(2):
+    if sections and i == 1:
+        lib.section_timing(True)
     b.run()
     b.sync()
     print(b.timing(), file=sys.stderr)
+if sections:
+    print(lib.section_report())
+    lib.section_timing(False)
 b.free()
