@@ -11,6 +11,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <atomic>
 #include <cmath>
 #include <cstdio>
@@ -77,6 +78,12 @@ struct SectionTimer {
     }
 };
 SectionTimer g_sect;
+// QUILT_B200_TRACE=1: host wall-clock stamps of the pipelined paths on stderr (where the end-to-end time outside the kernels goes)
+inline bool trace_on() {
+    static const bool on = std::getenv("QUILT_B200_TRACE") != nullptr;
+    return on;
+}
+inline double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 inline void launched_k(const char* name) {
     g_launches.fetch_add(1, std::memory_order_relaxed);
     if (!g_sect.on) return;
@@ -1850,6 +1857,7 @@ struct WavePipe {
     };
     std::vector<Wave> waves;
     size_t unpacked = 0;
+    double t_fill = 0, t_unpack = 0;  // host time spent staging inputs / waiting for and unpacking results (trace)
     ~WavePipe() {
         for (auto& w : waves) {
             if (w.ev_in) cudaEventDestroy(w.ev_in);
@@ -1858,11 +1866,13 @@ struct WavePipe {
         }
     }
     int unpack_through(size_t upto) {  // waves [unpacked, upto)
+        const double t0 = now_ms();
         for (; unpacked < upto; unpacked++) {
             Wave& w = waves[unpacked];
             CK(cudaEventSynchronize(w.ev_out));
             parallel_for(w.n, [&](int i) { unpack_job(w.B, w.bk->jobs[w.w0 + i], w.out); });
         }
+        t_unpack += now_ms() - t0;
         return QUILT_OK;
     }
     int push_batch(QuiltGpuBatch* B, QuiltGibbsOut* out, const ChainSpec* chain) {
@@ -1881,10 +1891,12 @@ struct WavePipe {
                 const size_t out_lo = first.out_off, out_hi = last.out_off + last.lo.end;
                 // host: this wave's inputs into the pinned block (runs while the previous wave computes)
                 char* hin = (char*)B->hin().p;
+                const double t_f = now_ms();
                 parallel_for(w.n, [&](int i) {
                     const HostJob& j = B->jobs[w.bk->jobs[w.w0 + i]];
                     fill_in(j, hin + j.in_off);
                 });
+                t_fill += now_ms() - t_f;
                 CK(cudaEventCreateWithFlags(&w.ev_in, cudaEventDisableTiming));
                 CK(cudaEventCreateWithFlags(&w.ev_done, cudaEventDisableTiming));
                 CK(cudaEventCreateWithFlags(&w.ev_out, cudaEventDisableTiming));
@@ -1979,8 +1991,10 @@ int quilt_gpu_gibbs_chain(int32_t n_stages, int32_t n, const QuiltGibbsArgs* con
                 break;
             }
             QuiltGpuBatch* B = nullptr;
+            const double t_a = now_ms();
             rc = stage_impl(n, args[s], &B, false);  // host preparation: the GPU is busy with the previous stage meanwhile
             if (rc != QUILT_OK) break;
+            if (trace_on()) std::fprintf(stderr, "[quilt trace] chain stage %d: stage_impl %.1f ms\n", s, now_ms() - t_a);
             Bs.emplace_back(B);
             ChainSpec cs;
             if (s > 0) {
@@ -1992,10 +2006,15 @@ int quilt_gpu_gibbs_chain(int32_t n_stages, int32_t n, const QuiltGibbsArgs* con
                 rc = chain_check(cs, B);
                 if (rc != QUILT_OK) break;
             }
+            const double t_b = now_ms();
             rc = pipe.push_batch(B, out[s], s > 0 ? &cs : nullptr);
+            if (trace_on()) std::fprintf(stderr, "[quilt trace] chain stage %d: push_batch %.1f ms (fill %.1f, wait+unpack %.1f)\n", s, now_ms() - t_b, pipe.t_fill, pipe.t_unpack);
+            pipe.t_fill = pipe.t_unpack = 0;
         }
+        const double t_c = now_ms();
         if (rc == QUILT_OK) rc = pipe.drain();
         sync_all_streams();
+        if (trace_on()) std::fprintf(stderr, "[quilt trace] chain drain %.1f ms\n", now_ms() - t_c);
     }
     return rc;
 }
