@@ -442,6 +442,14 @@ __global__ void __launch_bounds__(NT) k_block_nipt(BatchParams P, const JobDev* 
         double el[3][EPT];
 #pragma unroll
         for (int i = 0; i < 3; i++) Col<NT, EPT>::load(el[i], J.eG + i * hs + (size_t)g * Kp, K, 0.0);
+        if (g + 1 < T) {
+            // pull the next grid's eMatGrid columns towards L2 (one 128-byte line per 16 doubles): the walk is serial over the grids
+            const int lines = (Kp + 15) >> 4;
+            for (int l = tid; l < 3 * lines; l += NT) {
+                const int i = l / lines, q = l - i * lines;
+                prefetch_l2(J.eG + i * hs + (size_t)(g + 1) * Kp + (q << 4));
+            }
+        }
         double t0 = 0, jump = 0;
         if (g > 0) {
             t0 = J.tm[2 * (g - 1)];
@@ -578,21 +586,49 @@ __global__ void __launch_bounds__(NT) k_block_nipt(BatchParams P, const JobDev* 
 #pragma unroll
                         for (int e = 0; e < EPT; e++) eg[h][e] = 1.0;
                     const int r0 = J.rs[g2], r1 = J.rs[g2 + 1];
-                    for (int r = r0; r < r1; r++) {
-                        const ReadDesc d = J.desc[r];
-                        const int h = swap8[J.H[r]] - 1;
+                    // the allele words of this thread's haplotypes around grid g2 are loaded once (coalesced) and shared by the
+                    // grid's reads: per (read, haplotype) a shift, a mask and one table load (every branch is uniform over the CTA)
+                    uint32_t wm[EPT], w0[EPT], wp[EPT];
+                    if (r1 > r0) {
 #pragma unroll
                         for (int e = 0; e < EPT; e++) {
                             const int k = tid + e * NT;
-                            if (k < K) {
-                                const double E = read_emission_global(J, d, Kp, g2, k);
-                                if (h == 0)
-                                    eg[0][e] *= E;
-                                else if (h == 1)
-                                    eg[1][e] *= E;
-                                else
-                                    eg[2][e] *= E;
+                            const bool live = k < K;
+                            wm[e] = (live && g2 > 0) ? J.W[(size_t)(g2 - 1) * Kp + k] : 0u;
+                            w0[e] = live ? J.W[(size_t)g2 * Kp + k] : 0u;
+                            wp[e] = (live && g2 + 1 < T) ? J.W[(size_t)(g2 + 1) * Kp + k] : 0u;
+                        }
+                    }
+                    for (int r = r0; r < r1; r++) {
+                        const ReadDesc d = J.desc[r];
+                        const int h = swap8[J.H[r]] - 1;
+                        double E[EPT];
+                        const bool crossing = d.b0 + d.nb > 32;
+                        if (d.mode == MODE_RUN && !(crossing && d.g0rel > 0)) {
+                            const uint32_t mask = (1u << d.nb) - 1u;
+                            const TabEnt* __restrict__ tb = J.tabs + d.off;
+#pragma unroll
+                            for (int e = 0; e < EPT; e++) {
+                                const uint32_t lo = d.g0rel < 0 ? wm[e] : (d.g0rel == 0 ? w0[e] : wp[e]);
+                                const uint32_t hi = d.g0rel < 0 ? w0[e] : wp[e];  // (only the crossing bits survive the mask)
+                                E[e] = tb[__funnelshift_r(lo, hi, d.b0) & mask].E;
                             }
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < EPT; e++) {
+                                const int k = tid + e * NT;
+                                E[e] = (k < K) ? read_emission_global(J, d, Kp, g2, k) : 1.0;
+                            }
+                        }
+                        if (h == 0) {
+#pragma unroll
+                            for (int e = 0; e < EPT; e++) eg[0][e] *= E[e];
+                        } else if (h == 1) {
+#pragma unroll
+                            for (int e = 0; e < EPT; e++) eg[1][e] *= E[e];
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < EPT; e++) eg[2][e] *= E[e];
                         }
                     }
                     double sv[3];
