@@ -798,6 +798,7 @@ __global__ void __launch_bounds__(NT, (NT * EPT <= 512 ? 4 : (NT * EPT <= 1024 ?
 #pragma unroll
             for (int h = 0; h < NH; h++) sp[h] = Col<NT, EPT>::sum(am[h]);
             bsum.run(sp);
+            QB_T(20);
             const double x = tm_x, t1 = tm_t1;
             double sv[NH];
 #pragma unroll
@@ -817,6 +818,7 @@ __global__ void __launch_bounds__(NT, (NT * EPT <= 512 ? 4 : (NT * EPT <= 1024 ?
                 sv[h] = Col<NT, EPT>::sum(am[h]);
             }
             bsum.run(sv);
+            QB_T(21);
 #pragma unroll
             for (int h = 0; h < NH; h++) {
                 double sc = 1 / (c_old[h] * sv[h]);
@@ -866,6 +868,7 @@ __global__ void __launch_bounds__(NT, (NT * EPT <= 512 ? 4 : (NT * EPT <= 1024 ?
                 cwp[j] = v.x, cw0[j] = v.y, cwn[j] = v.z;
             }
         }
+        QB_T(14);
         if (g + 1 < T && (P.dbg & 2)) issue_pkg(g + 1, r1, nx_r1, ts1, nx_fcn, nx_fct);  // experiment: issue after the forward step
         bool changed = false;
         if (has) {
@@ -1294,6 +1297,7 @@ __global__ void __launch_bounds__(NT, (NT * EPT <= 512 ? 4 : (NT * EPT <= 1024 ?
                     }
                 }
 #undef QB_CLS_LOAD
+                QB_T(15);
                 if (changed) {
                     // every element of alphaHat_m / eMatGrid takes the accumulated factor of its class
                     QB_T(11);
@@ -1467,6 +1471,7 @@ __global__ void __launch_bounds__(NT, (NT * EPT <= 512 ? 4 : (NT * EPT <= 1024 ?
                     for (int i = 0; i < EPT; i++) am[h][i] *= alphaConst;
                 }
             }
+            QB_T(19);
         }
 #pragma unroll
         for (int h = 0; h < NH; h++) {
@@ -1639,8 +1644,9 @@ __global__ void __launch_bounds__(NT, (NT * EPT <= 512 ? 4 : (NT * EPT <= 1024 ?
     QB_T(10);
     if (tid == 0 && blockIdx.x == 0 && iteration == QB_CLK_IT) {
         printf("QBCLK it=%d T=%d R=%d wait_pkg=%lld issue=%lld fwd=%lld init_ab=%lld sums=%lld reduce=%lld decide=%lld update=%lld gridend=%lld backward=%lld epilogue=%lld other=%lld "
-               "class_sums=%lld class_apply=%lld visited=%lld changed=%lld grids_with_reads=%lld\n",
-               iteration, T, R, clk[0], clk[1], clk[2], clk[3], clk[4], clk[5], clk[6], clk[7], clk[8], clk[9], clk[10], clk[11], clk[12], clk[13], clk[16], clk[17], clk[18]);
+               "class_sums=%lld class_apply=%lld visited=%lld changed=%lld grids_with_reads=%lld | cls_layout_issue=%lld reads_tail=%lld renorm=%lld fwd_sum1=%lld fwd_step=%lld\n",
+               iteration, T, R, clk[0], clk[1], clk[2], clk[3], clk[4], clk[5], clk[6], clk[7], clk[8], clk[9], clk[10], clk[11], clk[12], clk[13], clk[16], clk[17], clk[18],
+               clk[14], clk[15], clk[19], clk[20], clk[21]);
     }
 #endif
 }
