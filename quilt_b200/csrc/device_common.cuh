@@ -110,6 +110,16 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
 __device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, uint32_t bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
 }
+// L2 prefetch of a whole range by the TMA engine: one instruction instead of one prefetch.global.L2 per 128-byte line (which
+// fills the LSU queue of the warps that issue them).  Address 16-byte aligned, size a positive multiple of 16.
+__device__ __forceinline__ void bulk_prefetch_l2(const void* gptr, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
+}
+// the same for an arbitrary byte range inside an allocation: start rounded down, end rounded down to 16 bytes
+__device__ __forceinline__ void bulk_prefetch_l2_range(const void* p, size_t bytes) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p), lo = a & ~(uintptr_t)15, hi = (a + bytes) & ~(uintptr_t)15;
+    if (hi > lo) bulk_prefetch_l2(reinterpret_cast<const void*>(lo), (uint32_t)(hi - lo));
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }

@@ -629,17 +629,17 @@ __global__ void __launch_bounds__(NT, (NT * EPT <= 512 ? 4 : (NT * EPT <= 1024 ?
             constexpr int PF_READS = 32, PF_TAB = 512;
             const int t1 = fct;  // (tables of the following grid start at or after the end of this grid's first chunk)
             const int nd = min(PF_READS, R - r1), ntb = min(PF_TAB, n_tab_total - t1);
-            const int l_desc = (nd * 32 + 127) >> 7, l_tab = (ntb * 16 + 127) >> 7, l_u = (nd * 8 + 127) >> 7, l_h = (nd * 4 + 127) >> 7;
-            int l = tid - 64;  // (warps 0 and 1 carry the bulk-copy issue and the scalar package)
-            if (l < 0) {
-            } else if (l < l_desc) {
-                prefetch_l2(reinterpret_cast<const char*>(J.desc + r1) + (l << 7));
-            } else if ((l -= l_desc) < l_tab) {
-                prefetch_l2(reinterpret_cast<const char*>(J.tabs + t1) + (l << 7));
-            } else if ((l -= l_tab) < l_u) {
-                prefetch_l2(reinterpret_cast<const char*>(U + r1) + (l << 7));
-            } else if ((l -= l_u) < l_h) {
-                prefetch_l2(reinterpret_cast<const char*>(J.H + r1) + (l << 7));
+            // one bulk L2 prefetch per array, each issued by lane 0 of a different warp (warps 0 and 1 carry the bulk-copy issue and
+            // the scalar package)
+            const int wq = (NT >= 192) ? tid - 64 : tid;
+            if (wq == 0) {
+                if (nd > 0) bulk_prefetch_l2_range(J.desc + r1, (size_t)nd * 32);
+            } else if (wq == 32) {
+                if (ntb > 0) bulk_prefetch_l2_range(J.tabs + t1, (size_t)ntb * 16);
+            } else if (wq == 64) {
+                if (nd > 0) bulk_prefetch_l2_range(U + r1, (size_t)nd * 8);
+            } else if (wq == 96) {
+                if (nd > 0) bulk_prefetch_l2_range(J.H + r1, (size_t)nd * 4);
             }
         }
     };
@@ -741,13 +741,11 @@ __global__ void __launch_bounds__(NT, (NT * EPT <= 512 ? 4 : (NT * EPT <= 1024 ?
         if (g + 1 < T) {
             if (!(P.dbg & 2)) issue_pkg(g + 1, r1, nx_r1, ts1, nx_fcn, nx_fct);
             if (P.dbg & 4) cp_async_wait_all();  // experiment: does the next barrier already wait for the cp.async package?
-            // pull the next grid's beta columns towards L2 (one 128-byte line per 16 doubles)
+            // pull the next grid's beta columns towards L2: one bulk prefetch per haplotype, lane 0 of warp h + 1
             if (nx_r1 > r1 && !(P.dbg & 1)) {
-                const int lines = (NH * Kpl) >> 4;
-                for (int l = (NT > 32 ? tid - 32 : tid); l >= 0 && l < lines; l += (NT > 32 ? NT - 32 : NT)) {
-                    const int h = l / (Kpl >> 4), q = l - h * (Kpl >> 4);
-                    prefetch_l2(betaG + ((size_t)h * T + g + 1) * Kp + (q << 4));
-                }
+#pragma unroll
+                for (int h = 0; h < NH; h++)
+                    if (tid == 32 * ((h + 1) % (NT / 32))) bulk_prefetch_l2(betaG + ((size_t)h * T + g + 1) * Kp, (uint32_t)Kpl * 8);
             }
         }
         // class path of this grid (classes.cuh)?  Its layouts are pulled towards L2 one grid ahead and loaded after the forward step.
@@ -756,18 +754,13 @@ __global__ void __launch_bounds__(NT, (NT * EPT <= 512 ? 4 : (NT * EPT <= 1024 ?
             use_cls = has && nC > 0 && !(iterative && (iteration == 0 || (iteration == 1 && r0 < J.first_read)));
             if (cur_nC > 0 && g + 1 < T) {
                 // sorted list (2 KA bytes), thread-major classes (KA), entering classes (NT), class records (CLS_LANES * 512)
-                constexpr int L_PERM = (2 * KA + 127) >> 7, L_CLS = (KA + 127) >> 7, L_ENT = (NT + 127) >> 7, L_REC = (CLS_LANES * 32 * 16) >> 7;
-                for (int l = tid; l < L_PERM + L_CLS + L_ENT + L_REC; l += NT) {
-                    const char* p;
-                    if (l < L_PERM)
-                        p = reinterpret_cast<const char*>(J.cperm + (size_t)(g + 1) * KA) + ((size_t)l << 7);
-                    else if (l < L_PERM + L_CLS)
-                        p = reinterpret_cast<const char*>(J.ccls + (size_t)(g + 1) * KA) + ((size_t)(l - L_PERM) << 7);
-                    else if (l < L_PERM + L_CLS + L_ENT)
-                        p = reinterpret_cast<const char*>(J.cent + (size_t)(g + 1) * NT) + ((size_t)(l - L_PERM - L_CLS) << 7);
-                    else
-                        p = reinterpret_cast<const char*>(J.crec + (size_t)(g + 1) * (CLS_LANES * 32)) + ((size_t)(l - L_PERM - L_CLS - L_ENT) << 7);
-                    prefetch_l2(p);
+                const int wl = tid >> 5;
+                if ((tid & 31) == 0) {
+                    constexpr int NWc = NT / 32;
+                    if (wl == 4 % NWc) bulk_prefetch_l2_range(J.cperm + (size_t)(g + 1) * KA, (size_t)2 * KA);
+                    if (wl == 5 % NWc) bulk_prefetch_l2_range(J.ccls + (size_t)(g + 1) * KA, (size_t)KA);
+                    if (wl == 6 % NWc) bulk_prefetch_l2_range(J.cent + (size_t)(g + 1) * NT, (size_t)NT);
+                    if (wl == 7 % NWc) bulk_prefetch_l2_range(J.crec + (size_t)(g + 1) * (CLS_LANES * 32), (size_t)CLS_LANES * 32 * 16);
                 }
             }
         }
