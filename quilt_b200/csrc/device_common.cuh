@@ -204,11 +204,18 @@ struct Col {
             if (k < K) st_stream(p + k, v[i]);
         }
     }
+    // this thread's share of a K-long sum as a pairwise tree: log2(EPT) dependent additions instead of EPT - 1 (the block-wide sums
+    // are trees over lanes and warps anyway, so no summation order of the reference is given up here)
     __device__ static __forceinline__ double sum(const double (&v)[EPT]) {
-        double s = v[0];
+        double t[EPT];
 #pragma unroll
-        for (int i = 1; i < EPT; i++) s += v[i];
-        return s;
+        for (int i = 0; i < EPT; i++) t[i] = v[i];
+#pragma unroll
+        for (int st = 1; st < EPT; st <<= 1) {
+#pragma unroll
+            for (int i = 0; i + st < EPT; i += 2 * st) t[i] += t[i + st];
+        }
+        return t[0];
     }
 };
 

@@ -29,18 +29,21 @@
 #ifndef QB_CLK_IT
 #define QB_CLK_IT 5
 #endif
+#ifndef QB_CLK_TID
+#define QB_CLK_TID 0  // the thread whose clock is read (its warp's view of every phase)
+#endif
 #if QB_CLK
 #define QB_T(i)                                 \
     do {                                        \
-        if (tid == 0) {                         \
+        if (tid == QB_CLK_TID) {                \
             const long long n_ = clock64();     \
             clk[i] += n_ - tlast;               \
             tlast = n_;                         \
         }                                       \
     } while (0)
-#define QB_N(i)                  \
-    do {                         \
-        if (tid == 0) clk[i]++;  \
+#define QB_N(i)                           \
+    do {                                  \
+        if (tid == QB_CLK_TID) clk[i]++;  \
     } while (0)
 #else
 #define QB_T(i) ((void)0)
@@ -1635,7 +1638,7 @@ __global__ void __launch_bounds__(NT, (NT * EPT <= 512 ? 4 : (NT * EPT <= 1024 ?
     }
 #if QB_CLK
     QB_T(10);
-    if (tid == 0 && blockIdx.x == 0 && iteration == QB_CLK_IT) {
+    if (tid == QB_CLK_TID && blockIdx.x == 0 && iteration == QB_CLK_IT) {
         printf("QBCLK it=%d T=%d R=%d wait_pkg=%lld issue=%lld fwd=%lld init_ab=%lld sums=%lld reduce=%lld decide=%lld update=%lld gridend=%lld backward=%lld epilogue=%lld other=%lld "
                "class_sums=%lld class_apply=%lld visited=%lld changed=%lld grids_with_reads=%lld | cls_layout_issue=%lld reads_tail=%lld renorm=%lld fwd_sum1=%lld fwd_step=%lld\n",
                iteration, T, R, clk[0], clk[1], clk[2], clk[3], clk[4], clk[5], clk[6], clk[7], clk[8], clk[9], clk[10], clk[11], clk[12], clk[13], clk[16], clk[17], clk[18],
