@@ -503,6 +503,7 @@ def main():
         t0 = time.perf_counter()
         res = api.run_chain_prepared(lib, preps, batch_pad)
         e2e_s.append(time.perf_counter() - t0)
+        log(f"e2e step {i}: {1e3 * e2e_s[-1]:.1f} ms")
         n_under = sum(int(r.underflow_problem) for st_res in res for r in st_res)
     e2e_step = dist.max_over_ranks(statistics.mean(e2e_s))
     e2e = {"value": total_samples / e2e_step, "unit": "samples/s", "h2d_bytes_per_step": nbytes["h2d_bytes"], "d2h_bytes_per_step": nbytes["d2h_bytes"],

@@ -194,12 +194,33 @@ struct BufCache {
     void clear() { free_.clear(); }
 };
 BufCache<DBuf> g_dcache_in, g_dcache_out;
+// small per-batch buffers (device-only result zone, JobDev records): cudaMalloc / cudaFree / cudaMallocHost per batch cost
+// milliseconds each and cudaFree synchronises the device, so they are recycled too
+BufCache<DBuf> g_dcache_outB, g_dcache_jobs;
+template <class B>
+cudaError_t cached_alloc(B& b, BufCache<B>& cache, size_t n) {
+    cudaError_t e;
+    std::unique_ptr<B> t = cache.acquire(n == 0 ? 256 : n, &e);
+    if (e != cudaSuccess) return e;
+    b.release();
+    std::swap(b.p, t->p);
+    std::swap(b.bytes, t->bytes);
+    return cudaSuccess;
+}
+template <class B>
+void cached_release(B& b, BufCache<B>& cache) {
+    if (!b.p) return;
+    std::unique_ptr<B> t(new B());
+    std::swap(b.p, t->p);
+    std::swap(b.bytes, t->bytes);
+    cache.release(std::move(t));
+}
 // The wave state (alpha / beta / eMatGrid / allele words / tables of the jobs in flight) is scratch that only lives while
 // a batch runs.  Batches run one after the other on the library stream, so ALL staged batches share one arena (grown to
 // the largest request): several batches can be staged at once — the stages of a device-resident call chain — without
 // multiplying tens of GB of state.  JobDev records are rebuilt at every run (upload_jobdevs), so the arena may move.
 DBuf g_slots;
-BufCache<HBuf> g_hcache_in, g_hcache_out;
+BufCache<HBuf> g_hcache_in, g_hcache_out, g_hcache_jobs;
 
 int host_threads() {
     static int n = 0;
@@ -574,6 +595,10 @@ struct Bucket {
     DBuf djobs;
     HBuf hjobs;
     bool perform_block = false, do_shard = false, debug = false;
+    ~Bucket() {
+        cached_release(djobs, g_dcache_jobs);
+        cached_release(hjobs, g_hcache_jobs);
+    }
 };
 
 }  // namespace
@@ -602,6 +627,7 @@ struct QuiltGpuBatch {
     double total_ms = 0, sweep_ms = 0;
     int n_sweep_launches = 0;
     ~QuiltGpuBatch() {
+        cached_release(doutB, g_dcache_outB);
         g_dcache_in.release(std::move(din_));
         g_dcache_out.release(std::move(dout_));
         g_hcache_in.release(std::move(hin_));
@@ -1066,8 +1092,8 @@ int setup_bucket(QuiltGpuBatch* B, Bucket& bk, size_t* mem_budget) {
     int cap = (g_sms / bk.geo.CL) * occ;
     const size_t by_mem = std::max<size_t>(1, *mem_budget / std::max<size_t>(bk.slot_bytes, 1));
     bk.n_slots = (int)std::min<size_t>(std::min<size_t>(cap, bk.jobs.size()), by_mem);
-    CK(bk.djobs.alloc(bk.jobs.size() * sizeof(JobDev)));
-    CK(bk.hjobs.alloc(bk.jobs.size() * sizeof(JobDev)));
+    CK(cached_alloc(bk.djobs, g_dcache_jobs, bk.jobs.size() * sizeof(JobDev)));
+    CK(cached_alloc(bk.hjobs, g_hcache_jobs, bk.jobs.size() * sizeof(JobDev)));
     bk.perform_block = (P.flags & QUILT_F_PERFORM_BLOCK_GIBBS) != 0;
     bk.do_shard = (P.flags & QUILT_F_DO_SHARD_BLOCK_GIBBS) != 0;
     bk.debug = (P.flags & (QUILT_F_RETURN_ALPHA | QUILT_F_RETURN_EXTRA)) != 0;
@@ -1539,6 +1565,9 @@ void quilt_gpu_release_panel_cache(void) {
     g_slots.release();
     g_hcache_in.clear();
     g_hcache_out.clear();
+    g_dcache_outB.clear();
+    g_dcache_jobs.clear();
+    g_hcache_jobs.clear();
 }
 
 int quilt_gpu_batch_free(QuiltGpuBatch* b) {
@@ -1609,7 +1638,7 @@ static int stage_impl(int32_t n, const QuiltGibbsArgs* args, QuiltGpuBatch** bat
     B->in_bytes = in_total;
     B->out_bytes = out_total;
     B->outB_bytes = outB_total;
-    CK(B->doutB.alloc(outB_total));
+    CK(cached_alloc(B->doutB, g_dcache_outB, outB_total));
     {
         cudaError_t e;
         B->din_ = g_dcache_in.acquire(in_total, &e);
@@ -2016,6 +2045,9 @@ int quilt_gpu_gibbs_chain(int32_t n_stages, int32_t n, const QuiltGibbsArgs* con
         sync_all_streams();
         if (trace_on()) std::fprintf(stderr, "[quilt trace] chain drain %.1f ms\n", now_ms() - t_c);
     }
+    const double t_d = now_ms();
+    Bs.clear();  // (buffers go back to the caches)
+    if (trace_on()) std::fprintf(stderr, "[quilt trace] chain teardown %.1f ms\n", now_ms() - t_d);
     return rc;
 }
 
