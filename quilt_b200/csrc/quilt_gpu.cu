@@ -196,7 +196,7 @@ struct BufCache {
 BufCache<DBuf> g_dcache_in, g_dcache_out;
 // small per-batch buffers (device-only result zone, JobDev records): cudaMalloc / cudaFree / cudaMallocHost per batch cost
 // milliseconds each and cudaFree synchronises the device, so they are recycled too
-BufCache<DBuf> g_dcache_outB, g_dcache_jobs;
+BufCache<DBuf> g_dcache_outB, g_dcache_jobs, g_dcache_hap;
 template <class B>
 cudaError_t cached_alloc(B& b, BufCache<B>& cache, size_t n) {
     cudaError_t e;
@@ -1567,6 +1567,7 @@ void quilt_gpu_release_panel_cache(void) {
     g_hcache_out.clear();
     g_dcache_outB.clear();
     g_dcache_jobs.clear();
+    g_dcache_hap.clear();
     g_hcache_jobs.clear();
 }
 
@@ -2390,9 +2391,20 @@ int quilt_gpu_haploid_dosage_versus_refs_batch(int32_t n, const QuiltHaploidArgs
     size_t free_b = 0, total_b = 0;
     CK(cudaMemGetInfo(&free_b, &total_b));
     const int group = (int)std::max<size_t>(1, std::min<size_t>((size_t)n, (size_t)(free_b * 0.8) / per));
-    DBuf buf, jb;
-    CK(buf.alloc((size_t)group * per));
-    CK(jb.alloc((size_t)group * sizeof(HapJob)));
+    // (the state of a group of passes is tens of GB: the buffers are recycled across calls like the Gibbs staging buffers)
+    struct Recycled {
+        DBuf b;
+        ~Recycled() {
+            if (b.bytes > ((size_t)16 << 30))
+                b.release();  // (a very large group state is not worth keeping away from the Gibbs batches)
+            else
+                cached_release(b, g_dcache_hap);
+        }
+    } buf_r, jb_r;
+    DBuf& buf = buf_r.b;
+    DBuf& jb = jb_r.b;
+    CK(cached_alloc(buf, g_dcache_hap, (size_t)group * per));
+    CK(cached_alloc(jb, g_dcache_hap, (size_t)group * sizeof(HapJob)));
     std::vector<HapJob> hj((size_t)group);
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     CK(cudaEventCreate(&e0));
