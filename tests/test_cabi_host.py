@@ -175,3 +175,19 @@ def test_rcpp_shim_compiles_with_the_gpu_back_end():
     r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-Wall", "-I" + os.path.join(root, "oracle", "refshim"), "-I" + os.path.join(root, "include"),
                         os.path.join(root, "shim", "quilt_gpu_shim.cpp")], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-3000:]
+
+
+def test_roofline_traffic_is_keyed_by_workload():
+    """bench.py reports the ncu DRAM traffic only for a workload that has a capture under profiles/ (null otherwise)"""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    t = bench.ncu_traffic("chr20_2Mb_1x_K4096")
+    assert t is not None and t["dram_bytes_per_launch"] > 1e10
+    # the kernel moves fewer bytes than the dense-emission algorithmic figure of SURVEY.md section 8(d)
+    for kind in ("common", "allsnp"):
+        assert t[kind]["dram_bytes_per_launch"] < t[kind]["algorithmic_bytes_of_captured_launch"]
+    assert bench.ncu_traffic("chr20_2Mb_1x_K512") is None
+    assert bench.ncu_traffic("no such workload") is None
