@@ -355,7 +355,18 @@ __device__ __forceinline__ Decision decide_read(const P3& pC_in, const double (&
     const double prod_pA1 = pA1.prod() * prior.get(hA1);
     const double prod_pA2 = pA2.prod() * prior.get(hA2);
     const double denom = prod_pC + prod_pA1 + prod_pA2;
-    const double norm_pC = prod_pC / denom, norm_pA1 = prod_pA1 / denom, norm_pA2 = prod_pA2 / denom;
+    double norm_pC, norm_pA1, norm_pA2;
+    if (denom > 0 && denom < 1e300) {
+        // one reciprocal + three corrected products = the correctly rounded quotients (see quot), a third of the division work
+        const double rd = 1 / denom;
+        norm_pC = quot(prod_pC, denom, rd);
+        norm_pA1 = quot(prod_pA1, denom, rd);
+        norm_pA2 = quot(prod_pA2, denom, rd);
+    } else {  // zero / non-finite sums (underflow): plain IEEE divisions, whatever they give
+        norm_pC = prod_pC / denom;
+        norm_pA1 = prod_pA1 / denom;
+        norm_pA2 = prod_pA2 / denom;
+    }
     P3 cum = {0, 0, 0};
     cum.set(hC, norm_pC);
     cum.set(hA1, norm_pA1);
